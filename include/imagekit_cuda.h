@@ -1,0 +1,198 @@
+/*
+ * imagekit_cuda.h -- C ABI of libimagekit_cuda.so, the B200 (sm_100a) drop-in for the one
+ * data-parallel hot path of the imagekit service: the `resize_image` step.
+ *
+ * Reference interface this library replaces (citations into the reference repository):
+ *   pub fn resize_image(img: DynamicImage, w: Option<u32>, h: Option<u32>)
+ *       -> Result<DynamicImage, ImageKitError>                  src/transform.rs:62-66
+ *   imported at src/lib.rs:32, called at src/lib.rs:180 (/img) and src/lib.rs:286 (/upload).
+ * Its arithmetic is `DynamicImage::resize(tw, th, FilterType::Lanczos3)` (src/transform.rs:85-89)
+ * of crate image 0.25.8 (Cargo.toml:20): dynimage.rs `resize`, math/utils.rs
+ * `resize_dimensions`, imageops/sample.rs `resize`/`vertical_sample`/`horizontal_sample`.
+ *
+ * The reference has no plugin registry: the function itself is the seam.  A Rust crate
+ * `imagekit-cuda` binds the entry points below through `extern "C"` (see INTEGRATION.md and
+ * rust-image-transform_b200/crate/) and re-exports a `resize_image` with the reference's
+ * exact signature.
+ *
+ * Rules of the boundary
+ *   - plain pointers and sizes only; the caller owns every buffer it passes and the library
+ *     never frees or retains caller memory past the call's return;
+ *   - every function is thread-safe and re-entrant (the reference calls resize_image
+ *     synchronously from N tokio worker threads: src/lib.rs:180,286);
+ *   - nothing panics, aborts or throws across the boundary: status codes + ikc_last_error();
+ *   - there is NO CPU fallback: without a usable CUDA device ikc_create fails with
+ *     IKC_ERR_CUDA and nothing else can be called.
+ */
+#ifndef IMAGEKIT_CUDA_H
+#define IMAGEKIT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define IKC_API __attribute__((visibility("default")))
+#else
+#define IKC_API
+#endif
+
+#define IKC_VERSION_MAJOR 0
+#define IKC_VERSION_MINOR 1
+
+typedef struct ikc_ctx ikc_ctx;       /* process-wide context: devices, streams, staging, tables */
+typedef struct ikc_batch ikc_batch;   /* a prepared, device-resident batch (replayable)          */
+
+/* Status codes.  Rust maps any non-zero status to ImageKitError::TransformError(msg)
+ * (src/lib.rs:38-39), which the handlers turn into HTTP 400 "Resize error: ..." (src/lib.rs:182,288). */
+enum ikc_status {
+    IKC_OK = 0,
+    IKC_ERR_INVALID_ARG = 1,   /* null pointer, zero size, pitch < row bytes, bad enum          */
+    IKC_ERR_UNSUPPORTED = 2,   /* layout the kernels do not handle (e.g. channels > 4)          */
+    IKC_ERR_TOO_LARGE = 3,     /* request exceeds IKC_MAX_DIM / IKC_MAX_PIXELS (the reference has no
+                                  bound on w/h -- src/lib.rs:61-63 -- and would try to allocate) */
+    IKC_ERR_CUDA = 4,          /* CUDA runtime/driver error; text in ikc_last_error()           */
+    IKC_ERR_OOM = 5            /* host or device allocation failed                              */
+};
+
+/* image::imageops::FilterType, same order as the crate's enum.  resize_image always uses
+ * IKC_FILTER_LANCZOS3 (src/transform.rs:88); the others exist because imageops::resize has them. */
+enum ikc_filter {
+    IKC_FILTER_NEAREST = 0,
+    IKC_FILTER_TRIANGLE = 1,
+    IKC_FILTER_CATMULLROM = 2,
+    IKC_FILTER_GAUSSIAN = 3,
+    IKC_FILTER_LANCZOS3 = 4
+};
+
+/* What the dims rule decided (return value of ikc_target_dims when >= 0). */
+enum ikc_dims_code {
+    IKC_DIMS_RESAMPLE = 0,     /* resample to (*tw,*th)                                          */
+    IKC_DIMS_PASSTHROUGH = 1,  /* w and h both None: input returned untouched (transform.rs:67-69) */
+    IKC_DIMS_CLONE = 2,        /* requested size == current size: DynamicImage::resize clones    */
+    IKC_DIMS_COPY = 3          /* aspect-fit size == current size: imageops::resize copies       */
+};
+
+/* Arithmetic mode of the resampling kernels. */
+enum ikc_mode {
+    IKC_MODE_FAST = 0,   /* fused single-launch kernels, FMA accumulation: max |delta| <= 1 LSB  */
+    IKC_MODE_EXACT = 1   /* two-launch verification path: separate mul/add in ascending tap order,
+                            vertical then horizontal, f32 intermediate in HBM: delta == 0 vs the
+                            CPU restatement of image 0.25.8                                      */
+};
+
+#define IKC_MAX_DIM 65535u              /* per-axis bound on source and destination             */
+#define IKC_MAX_PIXELS (1ull << 28)     /* per-image bound on width*height (268 MP)             */
+
+/* One resize of a batch.  Pointers are HOST pointers for ikc_resize_batch and DEVICE pointers
+ * for ikc_batch_prepare.  Rows are `pitch` bytes apart, pixels are `channels` interleaved
+ * samples (1=Luma, 2=LumaA, 3=Rgb, 4=Rgba).  `status` and `device` are written by the library. */
+typedef struct ikc_job {
+    const void* src;
+    void* dst;
+    uint32_t sw, sh;
+    uint32_t dw, dh;
+    size_t src_pitch;
+    size_t dst_pitch;
+    int32_t channels;
+    int32_t filter;     /* enum ikc_filter */
+    int32_t status;     /* out: enum ikc_status for this job */
+    int32_t device;     /* out: index (into the ctx's device list) that ran it */
+} ikc_job;
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* Creates the process-wide context over `n` CUDA devices (device_ids == NULL or n <= 0: all
+ * visible devices).  Per device: a pool of lanes (stream + pinned staging + device scratch) and
+ * a weight-table cache.  Rust holds it in a OnceLock and shares it across all worker threads. */
+IKC_API int ikc_create(const int* device_ids, int n, ikc_ctx** out);
+IKC_API void ikc_destroy(ikc_ctx* ctx);
+IKC_API int ikc_device_count(const ikc_ctx* ctx);
+IKC_API int ikc_set_mode(ikc_ctx* ctx, int mode);          /* enum ikc_mode; default FAST */
+IKC_API int ikc_get_mode(const ikc_ctx* ctx);
+/* Number of resampling-kernel launches issued through this context so far. */
+IKC_API uint64_t ikc_kernel_launches(const ikc_ctx* ctx);
+/* Thread-local text of the last failure on the calling thread ("" if none). */
+IKC_API const char* ikc_last_error(void);
+IKC_API int ikc_version(void);                               /* major*1000 + minor */
+
+/* ---- dims rule (rows a1-a3 of the hot path) ------------------------------------------------- */
+
+/* Replaces the size arithmetic of resize_image (src/transform.rs:67-87: f32 ratio, f32::round,
+ * saturating cast, max(1)) followed by DynamicImage::resize's early-out and resize_dimensions
+ * (image 0.25.8 math/utils.rs: f64 min-ratio fit-within, round, max(1), u32::MAX branch).
+ * Returns an ikc_dims_code (>= 0) or -IKC_ERR_INVALID_ARG. Needs no context and no GPU. */
+IKC_API int ikc_target_dims(uint32_t ow, uint32_t oh, int has_w, uint32_t w, int has_h, uint32_t h,
+                            uint32_t* tw, uint32_t* th);
+
+/* Inspection of the window/weight table of one separable pass n_in -> n_out (the host-built table
+ * the kernels consume; image 0.25.8 imageops/sample.rs window + weight loop).  With weights == NULL
+ * returns the per-output stride needed; otherwise fills left[n_out], count[n_out] and
+ * weights[n_out * stride] (zero padded) and returns the stride; 0 on bad arguments.  No GPU needed. */
+IKC_API uint32_t ikc_pass_table(int filter, uint32_t n_in, uint32_t n_out, uint32_t* left, uint32_t* count,
+                                float* weights, uint32_t stride);
+
+/* ---- host-buffer entry points (the drop-in path; include H2D + D2H) -------------------------- */
+
+/* Replaces imageops::resize(&buf, dw, dh, filter) for 8-bit rasters (image 0.25.8
+ * imageops/sample.rs; reached from src/transform.rs:85-89 via resize_exact).  `src`/`dst` are
+ * host buffers owned by the caller (Rust: `buf.as_raw().as_ptr()` and a pre-sized Vec<u8>).
+ * Pinned buffers (ikc_host_alloc or cudaHostRegister'ed) are DMA'd directly; pageable ones go
+ * through the lane's pinned staging.  Returns after the result is in `dst`.
+ * Semantics kept from the crate: empty source -> zero-filled dst; same dims -> copy. */
+IKC_API int ikc_resize_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch,
+                          int channels, uint8_t* dst, uint32_t dw, uint32_t dh, size_t dst_pitch,
+                          int filter);
+
+/* Same for 16-bit samples (Luma16/LumaA16/Rgb16/Rgba16 as produced by the PNG decoder);
+ * pitches in bytes. */
+IKC_API int ikc_resize_u16(ikc_ctx* ctx, const uint16_t* src, uint32_t sw, uint32_t sh, size_t src_pitch,
+                           int channels, uint16_t* dst, uint32_t dw, uint32_t dh, size_t dst_pitch,
+                           int filter);
+
+/* Whole resize_image(img, w, h) for a tight 8-bit raster (src/transform.rs:62-90): dims rule +
+ * Lanczos3.  `dst_capacity` bytes must hold tw*th*channels (query with ikc_target_dims first).
+ * Writes the produced size to (*tw,*th) and returns an ikc_dims_code (>= 0; for codes 1..3 the
+ * source bytes are copied to dst unchanged) or -(enum ikc_status) on failure. */
+IKC_API int ikc_resize_image_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, int channels,
+                                int has_w, uint32_t w, int has_h, uint32_t h, uint8_t* dst,
+                                size_t dst_capacity, uint32_t* tw, uint32_t* th);
+
+/* Batched resize of independent images (8-bit).  Jobs are sharded round-robin over the context's
+ * devices (job i -> device i mod G); every device pipelines H2D / kernel / D2H over its lanes.
+ * No collective: images are independent.  Returns IKC_OK if every job succeeded, else the first
+ * failing status; per-job results are in jobs[i].status. */
+IKC_API int ikc_resize_batch(ikc_ctx* ctx, ikc_job* jobs, size_t n);
+
+/* Pinned host memory for callers that want zero-copy staging (decode straight into it). */
+IKC_API int ikc_host_alloc(size_t bytes, void** out);
+IKC_API void ikc_host_free(void* p);
+
+/* ---- device-resident entry points (no PCIe; what the roofline is measured on) --------------- */
+
+/* One resize between device buffers on `device_index` (index into the ctx's device list),
+ * executed on `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ * Returns once the stream has finished the resize (its descriptor staging is per call); use
+ * ikc_batch_prepare / ikc_batch_launch for fully asynchronous, replayable launches.
+ * Device buffers must span rows*pitch bytes; the fused kernel additionally wants a 16-byte
+ * aligned base and pitch (otherwise the slower generic kernels are used). */
+IKC_API int ikc_resize_u8_device(ikc_ctx* ctx, int device_index, void* stream, const uint8_t* d_src,
+                                 uint32_t sw, uint32_t sh, size_t src_pitch, int channels, uint8_t* d_dst,
+                                 uint32_t dw, uint32_t dh, size_t dst_pitch, int filter);
+
+/* Prepare `n` device-resident jobs (8-bit) as one replayable batch: plans every job, uploads the
+ * weight tables and work-item list once.  ikc_batch_launch enqueues the whole batch on `stream`
+ * (one launch per kernel family present, normally one).  jobs[i].status is set at prepare time. */
+IKC_API int ikc_batch_prepare(ikc_ctx* ctx, int device_index, ikc_job* jobs, size_t n, ikc_batch** out);
+IKC_API int ikc_batch_launch(ikc_batch* b, void* stream);
+/* Kernel launches one ikc_batch_launch issues. */
+IKC_API int ikc_batch_launch_count(const ikc_batch* b);
+IKC_API void ikc_batch_free(ikc_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMAGEKIT_CUDA_H */

@@ -1,0 +1,302 @@
+// api.cpp -- the extern "C" boundary declared in include/imagekit_cuda.h.  Nothing throws across it.
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "context.hpp"
+#include "imagekit_cuda.h"
+#include "launch.hpp"
+
+using namespace ikc;
+
+struct ikc_ctx {
+    Context impl;
+    ikc_ctx(const int* ids, int n) : impl(ids, n) {}
+};
+struct ikc_batch {
+    PreparedBatch impl;
+};
+
+namespace {
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return IKC_OK;
+    } catch (const Error& e) {
+        set_last_error(e.what);
+        return int(e.status);
+    } catch (const std::bad_alloc&) {
+        set_last_error("host allocation failed");
+        return IKC_ERR_OOM;
+    } catch (const std::exception& e) {
+        set_last_error(std::string("internal error: ") + e.what());
+        return IKC_ERR_CUDA;
+    } catch (...) {
+        set_last_error("internal error");
+        return IKC_ERR_CUDA;
+    }
+}
+
+JobDesc make_desc(const void* src, uint32_t sw, uint32_t sh, size_t sp, int ch, void* dst, uint32_t dw, uint32_t dh,
+                  size_t dp, int filter, int bps) {
+    return JobDesc{src, dst, sw, sh, dw, dh, sp, dp, ch, bps, filter};
+}
+
+}  // namespace
+
+extern "C" {
+
+int ikc_version(void) { return IKC_VERSION_MAJOR * 1000 + IKC_VERSION_MINOR; }
+const char* ikc_last_error(void) { return last_error(); }
+
+int ikc_create(const int* device_ids, int n, ikc_ctx** out) {
+    if (!out) {
+        set_last_error("out is null");
+        return IKC_ERR_INVALID_ARG;
+    }
+    *out = nullptr;
+    return guarded([&] { *out = new ikc_ctx(device_ids, n); });
+}
+
+void ikc_destroy(ikc_ctx* ctx) {
+    try {
+        delete ctx;
+    } catch (...) {
+    }
+}
+
+int ikc_device_count(const ikc_ctx* ctx) { return ctx ? ctx->impl.device_count() : 0; }
+
+int ikc_set_mode(ikc_ctx* ctx, int mode) {
+    if (!ctx || (mode != IKC_MODE_FAST && mode != IKC_MODE_EXACT)) {
+        set_last_error("bad context or mode");
+        return IKC_ERR_INVALID_ARG;
+    }
+    ctx->impl.mode.store(mode);
+    return IKC_OK;
+}
+int ikc_get_mode(const ikc_ctx* ctx) { return ctx ? ctx->impl.mode.load() : -1; }
+uint64_t ikc_kernel_launches(const ikc_ctx* ctx) { return ctx ? ctx->impl.launches.load() : 0; }
+
+int ikc_target_dims(uint32_t ow, uint32_t oh, int has_w, uint32_t w, int has_h, uint32_t h, uint32_t* tw,
+                    uint32_t* th) {
+    if (!tw || !th) {
+        set_last_error("tw/th is null");
+        return -IKC_ERR_INVALID_ARG;
+    }
+    return target_dims(ow, oh, has_w != 0, w, has_h != 0, h, tw, th);
+}
+
+uint32_t ikc_pass_table(int filter, uint32_t n_in, uint32_t n_out, uint32_t* left, uint32_t* count, float* weights,
+                        uint32_t stride) {
+    uint32_t need = 0;
+    guarded([&] {
+        auto p = build_pass(filter, n_in, n_out);
+        if (!p) return;
+        need = p->stride;
+        if (!weights) return;
+        if (!left || !count || stride < p->stride) {
+            need = 0;
+            return;
+        }
+        for (uint32_t o = 0; o < n_out; ++o) {
+            left[o] = uint32_t(p->left[o]);
+            count[o] = uint32_t(p->count[o]);
+            for (uint32_t i = 0; i < stride; ++i)
+                weights[size_t(o) * stride + i] = i < p->stride ? p->w[size_t(o) * p->stride + i] : 0.0f;
+        }
+        need = stride;
+    });
+    return need;
+}
+
+int ikc_resize_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch, int channels,
+                  uint8_t* dst, uint32_t dw, uint32_t dh, size_t dst_pitch, int filter) {
+    if (!ctx) {
+        set_last_error("ctx is null");
+        return IKC_ERR_INVALID_ARG;
+    }
+    return guarded([&] {
+        ctx->impl.resize_host(make_desc(src, sw, sh, src_pitch, channels, dst, dw, dh, dst_pitch, filter, 1), nullptr);
+    });
+}
+
+int ikc_resize_u16(ikc_ctx* ctx, const uint16_t* src, uint32_t sw, uint32_t sh, size_t src_pitch, int channels,
+                   uint16_t* dst, uint32_t dw, uint32_t dh, size_t dst_pitch, int filter) {
+    if (!ctx) {
+        set_last_error("ctx is null");
+        return IKC_ERR_INVALID_ARG;
+    }
+    return guarded([&] {
+        ctx->impl.resize_host(make_desc(src, sw, sh, src_pitch, channels, dst, dw, dh, dst_pitch, filter, 2), nullptr);
+    });
+}
+
+int ikc_resize_image_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, int channels, int has_w,
+                        uint32_t w, int has_h, uint32_t h, uint8_t* dst, size_t dst_capacity, uint32_t* tw,
+                        uint32_t* th) {
+    if (!ctx || !tw || !th) {
+        set_last_error("null argument");
+        return -IKC_ERR_INVALID_ARG;
+    }
+    int code = 0;
+    const int rc = guarded([&] {
+        if (channels < 1 || channels > 4) fail(kInvalidArg, "channels must be 1..4");
+        code = target_dims(sw, sh, has_w != 0, w, has_h != 0, h, tw, th);
+        if (*tw > IKC_MAX_DIM || *th > IKC_MAX_DIM || uint64_t(*tw) * *th > IKC_MAX_PIXELS)
+            fail(kTooLarge, "requested size exceeds IKC_MAX_DIM / IKC_MAX_PIXELS");
+        const size_t need = size_t(*tw) * *th * size_t(channels);
+        if (need > dst_capacity) fail(kInvalidArg, "dst_capacity too small for the target size");
+        if (need && !dst) fail(kInvalidArg, "dst is null");
+        if (code != IKC_DIMS_RESAMPLE) {  // passthrough / clone / copy: bytes unchanged
+            if (need) std::memcpy(dst, src, need);
+            return;
+        }
+        ctx->impl.resize_host(make_desc(src, sw, sh, size_t(sw) * channels, channels, dst, *tw, *th,
+                                        size_t(*tw) * channels, IKC_FILTER_LANCZOS3, 1),
+                              nullptr);
+    });
+    return rc == IKC_OK ? code : -rc;
+}
+
+int ikc_resize_batch(ikc_ctx* ctx, ikc_job* jobs, size_t n) {
+    if (!ctx || (!jobs && n)) {
+        set_last_error("null argument");
+        return IKC_ERR_INVALID_ARG;
+    }
+    int first_bad = IKC_OK;
+    const int rc = guarded([&] {
+        std::vector<JobDesc> d(n);
+        std::vector<int> st(n, 0), dev(n, 0);
+        for (size_t i = 0; i < n; ++i)
+            d[i] = make_desc(jobs[i].src, jobs[i].sw, jobs[i].sh, jobs[i].src_pitch, jobs[i].channels, jobs[i].dst,
+                             jobs[i].dw, jobs[i].dh, jobs[i].dst_pitch, jobs[i].filter, 1);
+        ctx->impl.resize_batch_host(d.data(), n, st.data(), dev.data());
+        for (size_t i = 0; i < n; ++i) {
+            jobs[i].status = st[i];
+            jobs[i].device = dev[i];
+            if (st[i] != IKC_OK && first_bad == IKC_OK) first_bad = st[i];
+        }
+    });
+    return rc != IKC_OK ? rc : first_bad;
+}
+
+int ikc_host_alloc(size_t bytes, void** out) {
+    if (!out) return IKC_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded([&] { check_cuda(cudaMallocHost(out, bytes ? bytes : 1), "cudaMallocHost"); });
+}
+void ikc_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int ikc_resize_u8_device(ikc_ctx* ctx, int device_index, void* stream, const uint8_t* d_src, uint32_t sw,
+                         uint32_t sh, size_t src_pitch, int channels, uint8_t* d_dst, uint32_t dw, uint32_t dh,
+                         size_t dst_pitch, int filter) {
+    if (!ctx || device_index < 0 || device_index >= ctx->impl.device_count()) {
+        set_last_error("bad context or device index");
+        return IKC_ERR_INVALID_ARG;
+    }
+    return guarded([&] {
+        Context& c = ctx->impl;
+        Device& dev = c.device(device_index);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        check_cuda(cudaSetDevice(dev.ordinal()), "cudaSetDevice");
+        JobDesc d = make_desc(d_src, sw, sh, src_pitch, channels, d_dst, dw, dh, dst_pitch, filter, 1);
+        validate_job(d);
+        const size_t row = size_t(dw) * channels;
+        if (dw == 0 || dh == 0) return;
+        if (sw == 0 || sh == 0) {
+            check_cuda(cudaMemset2DAsync(d_dst, dst_pitch, 0, row, dh, s), "memset");
+            return;
+        }
+        if (sw == dw && sh == dh) {
+            check_cuda(cudaMemcpy2DAsync(d_dst, dst_pitch, d_src, src_pitch, row, dh, cudaMemcpyDeviceToDevice, s),
+                       "copy");
+            return;
+        }
+        const bool exact = c.mode.load() == 1;
+        int status = kOk;
+        LaunchPlan lp = c.plan(dev, &d, 1, &status, exact);
+        if (status != kOk) fail(Status(status), last_error());
+        // Descriptor staging comes from a lane; the lane is held until the caller's stream has
+        // consumed the upload (the scratch of the generic path lives in the lane too).
+        Lane* l = dev.acquire_lane();
+        try {
+            c.enqueue(dev, lp, l->h_desc, l->d_desc, l->d_scratch, s, exact);
+            check_cuda(cudaStreamSynchronize(s), "resize (stream sync)");
+        } catch (...) {
+            dev.release_lane(l);
+            throw;
+        }
+        dev.release_lane(l);
+    });
+}
+
+int ikc_batch_prepare(ikc_ctx* ctx, int device_index, ikc_job* jobs, size_t n, ikc_batch** out) {
+    if (!ctx || !out || (!jobs && n) || device_index < 0 || device_index >= ctx->impl.device_count()) {
+        set_last_error("bad argument");
+        return IKC_ERR_INVALID_ARG;
+    }
+    *out = nullptr;
+    int first_bad = IKC_OK;
+    const int rc = guarded([&] {
+        Context& c = ctx->impl;
+        Device& dev = c.device(device_index);
+        check_cuda(cudaSetDevice(dev.ordinal()), "cudaSetDevice");
+        std::vector<JobDesc> d(n);
+        std::vector<int> st(n, 0);
+        for (size_t i = 0; i < n; ++i)
+            d[i] = make_desc(jobs[i].src, jobs[i].sw, jobs[i].sh, jobs[i].src_pitch, jobs[i].channels, jobs[i].dst,
+                             jobs[i].dw, jobs[i].dh, jobs[i].dst_pitch, jobs[i].filter, 1);
+        const bool exact = c.mode.load() == 1;
+        auto b = std::unique_ptr<ikc_batch>(new ikc_batch{PreparedBatch{&c, device_index, exact, {}, {}, {}}});
+        b->impl.lp = c.plan(dev, d.data(), n, st.data(), exact);
+        for (size_t i = 0; i < n; ++i) {
+            jobs[i].status = st[i];
+            jobs[i].device = device_index;
+            if (st[i] != IKC_OK && first_bad == IKC_OK) first_bad = st[i];
+        }
+        LaunchPlan& lp = b->impl.lp;
+        if (lp.scratch_floats) b->impl.d_scratch.reserve(lp.scratch_floats * sizeof(float));
+        for (int idx : lp.generic_jobs) lp.jobs[idx].tmp = static_cast<float*>(b->impl.d_scratch.p);
+        const size_t bytes = c.desc_bytes(lp);
+        std::vector<uint8_t> host(bytes);
+        c.fill_desc(lp, host.data(), static_cast<float*>(b->impl.d_scratch.p));
+        b->impl.d_desc.reserve(bytes);
+        check_cuda(cudaMemcpy(b->impl.d_desc.p, host.data(), bytes, cudaMemcpyHostToDevice), "upload descriptors");
+        *out = b.release();
+    });
+    return rc != IKC_OK ? rc : first_bad;
+}
+
+int ikc_batch_launch(ikc_batch* b, void* stream) {
+    if (!b) {
+        set_last_error("batch is null");
+        return IKC_ERR_INVALID_ARG;
+    }
+    return guarded([&] {
+        Context& c = *b->impl.ctx;
+        check_cuda(cudaSetDevice(c.device(b->impl.device_index).ordinal()), "cudaSetDevice");
+        c.launch_resident(b->impl.lp, static_cast<const uint8_t*>(b->impl.d_desc.p), static_cast<cudaStream_t>(stream),
+                          b->impl.exact);
+    });
+}
+
+int ikc_batch_launch_count(const ikc_batch* b) { return b ? b->impl.lp.launches() : 0; }
+
+void ikc_batch_free(ikc_batch* b) {
+    if (!b) return;
+    try {
+        cudaSetDevice(b->impl.ctx->device(b->impl.device_index).ordinal());
+        cudaDeviceSynchronize();
+        b->impl.d_desc.release();
+        b->impl.d_scratch.release();
+        delete b;
+    } catch (...) {
+    }
+}
+
+}  // extern "C"

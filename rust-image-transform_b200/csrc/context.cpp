@@ -1,0 +1,584 @@
+// context.cpp -- see context.hpp.
+#include "context.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <thread>
+
+#include "launch.hpp"
+
+namespace ikc {
+
+// ---- errors ---------------------------------------------------------------------------------------
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+const char* last_error() { return g_last_error.c_str(); }
+
+void fail(Status s, const std::string& what) { throw Error{s, what}; }
+void check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return;
+    const Status s = (e == cudaErrorMemoryAllocation) ? kOom : kCudaError;
+    fail(s, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+
+// ---- buffers --------------------------------------------------------------------------------------
+
+void Buffer::release() {
+    if (!p) return;
+    if (pinned_host) cudaFreeHost(p); else cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+void Buffer::reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    size_t want = std::max<size_t>(bytes, 1 << 16);
+    want = std::max(want, cap + cap / 2);
+    want = (want + 255) & ~size_t(255);
+    release();
+    if (pinned_host) check_cuda(cudaMallocHost(&p, want), "cudaMallocHost(staging)");
+    else check_cuda(cudaMalloc(&p, want), "cudaMalloc(device buffer)");
+    cap = want;
+}
+
+DevTables::~DevTables() {
+    if (base) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(device);
+        cudaFree(base);
+        cudaSetDevice(cur);
+    }
+}
+
+// ---- validation -----------------------------------------------------------------------------------
+
+static constexpr uint32_t kMaxDim = 65535u;
+static constexpr uint64_t kMaxPixels = 1ull << 28;
+
+void validate_job(const JobDesc& d) {
+    if (d.channels < 1) fail(kInvalidArg, "channels must be >= 1");
+    if (d.channels > 4) fail(kUnsupported, "more than 4 interleaved channels is not supported");
+    if (d.bps != 1 && d.bps != 2) fail(kUnsupported, "only 8- and 16-bit samples are supported");
+    if (d.filter < 0 || d.filter > 4) fail(kInvalidArg, "unknown filter");
+    if (d.sw > kMaxDim || d.sh > kMaxDim || d.dw > kMaxDim || d.dh > kMaxDim)
+        fail(kTooLarge, "image dimension exceeds IKC_MAX_DIM");
+    if (uint64_t(d.sw) * d.sh > kMaxPixels || uint64_t(d.dw) * d.dh > kMaxPixels)
+        fail(kTooLarge, "image area exceeds IKC_MAX_PIXELS");
+    if (d.dw != 0 && d.dh != 0) {
+        if (!d.dst) fail(kInvalidArg, "dst is null");
+        if (d.dst_pitch < size_t(d.dw) * d.channels * d.bps) fail(kInvalidArg, "dst_pitch smaller than a row");
+        if (d.bps == 2 && (d.dst_pitch & 1)) fail(kInvalidArg, "dst_pitch must be even for 16-bit samples");
+    }
+    if (d.sw != 0 && d.sh != 0) {
+        if (!d.src) fail(kInvalidArg, "src is null");
+        if (d.src_pitch < size_t(d.sw) * d.channels * d.bps) fail(kInvalidArg, "src_pitch smaller than a row");
+        if (d.bps == 2 && (d.src_pitch & 1)) fail(kInvalidArg, "src_pitch must be even for 16-bit samples");
+    }
+}
+
+// ---- device ---------------------------------------------------------------------------------------
+
+static constexpr int kLanesPerDevice = 4;
+static constexpr size_t kMaxCachedTables = 512;
+
+Device::Device(Context* ctx, int ordinal, int index) : ctx_(ctx), ordinal_(ordinal), index_(index) {
+    check_cuda(cudaSetDevice(ordinal), "cudaSetDevice");
+    cudaDeviceProp prop{};
+    check_cuda(cudaGetDeviceProperties(&prop, ordinal), "cudaGetDeviceProperties");
+    if (prop.major < 10)
+        fail(kCudaError, std::string("device ") + prop.name + " is not sm_100-class; this library is built for sm_100a only");
+    sm_count_ = prop.multiProcessorCount;
+    for (int i = 0; i < kLanesPerDevice; ++i) {
+        auto l = std::make_unique<Lane>();
+        check_cuda(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        free_.push_back(l.get());
+        lanes_.push_back(std::move(l));
+    }
+}
+
+Device::~Device() {
+    cudaSetDevice(ordinal_);
+    tabs_.clear();
+    for (auto& l : lanes_) {
+        if (l->stream) {
+            cudaStreamSynchronize(l->stream);
+            cudaStreamDestroy(l->stream);
+        }
+        l->h_in.release(); l->h_out.release(); l->h_desc.release();
+        l->d_in.release(); l->d_out.release(); l->d_scratch.release(); l->d_desc.release();
+    }
+}
+
+Lane* Device::acquire_lane() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return !free_.empty(); });
+    Lane* l = free_.back();
+    free_.pop_back();
+    return l;
+}
+void Device::release_lane(Lane* l) {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        free_.push_back(l);
+    }
+    cv_.notify_one();
+}
+
+std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_out) {
+    const auto key = std::make_tuple(filter, n_in, n_out);
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = tabs_.find(key);
+        if (it != tabs_.end()) return it->second;
+    }
+    auto host = ctx_->pass(filter, n_in, n_out);
+    if (!host) fail(kInvalidArg, "cannot plan pass");
+    // one allocation: left | right | w | ring (each 256-byte aligned)
+    auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+    const size_t b_idx = up(sizeof(int32_t) * n_out);
+    const size_t b_w = up(sizeof(float) * host->w.size());
+    const size_t b_ring = up(sizeof(float) * host->ring.size());
+    auto t = std::make_shared<DevTables>();
+    t->device = ordinal_;
+    t->host = host;
+    check_cuda(cudaSetDevice(ordinal_), "cudaSetDevice");
+    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + b_ring + 256), "cudaMalloc(weight tables)");
+    uint8_t* p = static_cast<uint8_t*>(t->base);
+    auto put = [&](const void* src, size_t bytes, size_t slot) {
+        uint8_t* at = p;
+        if (bytes) check_cuda(cudaMemcpy(at, src, bytes, cudaMemcpyHostToDevice), "cudaMemcpy(weight tables)");
+        p += slot;
+        return at;
+    };
+    t->pass.left = reinterpret_cast<const int32_t*>(put(host->left.data(), sizeof(int32_t) * n_out, b_idx));
+    t->pass.right = reinterpret_cast<const int32_t*>(put(host->right.data(), sizeof(int32_t) * n_out, b_idx));
+    t->pass.w = reinterpret_cast<const float*>(put(host->w.data(), sizeof(float) * host->w.size(), b_w));
+    const uint8_t* ring = put(host->ring.data(), sizeof(float) * host->ring.size(), b_ring);
+    t->pass.ring = host->ring.empty() ? nullptr : reinterpret_cast<const float*>(ring);
+    t->pass.stride = int32_t(host->stride);
+    t->pass.ring_k = host->ring_k;
+    t->pass.ring_stride = host->ring_stride;
+    t->pass.n_in = int32_t(n_in);
+    t->pass.n_out = int32_t(n_out);
+    t->pass.max_count = int32_t(host->max_count);
+
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = tabs_.find(key);
+    if (it != tabs_.end()) return it->second;  // another thread won the race; ours is freed on return
+    if (tabs_.size() >= kMaxCachedTables) {    // drop the oldest entry (holders keep theirs alive)
+        tabs_.erase(tab_order_.front());
+        tab_order_.erase(tab_order_.begin());
+    }
+    tabs_[key] = t;
+    tab_order_.push_back(key);
+    return t;
+}
+
+// ---- context --------------------------------------------------------------------------------------
+
+Context::Context(const int* ids, int n) {
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible <= 0)
+        fail(kCudaError, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                             (e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)));
+    std::vector<int> want;
+    if (ids && n > 0) want.assign(ids, ids + n);
+    else for (int i = 0; i < visible; ++i) want.push_back(i);
+    for (size_t i = 0; i < want.size(); ++i) {
+        if (want[i] < 0 || want[i] >= visible) fail(kInvalidArg, "device id out of range");
+        devs_.push_back(std::make_unique<Device>(this, want[i], int(i)));
+    }
+}
+
+Context::~Context() { devs_.clear(); }
+
+std::shared_ptr<const PassPlan> Context::pass(int filter, uint32_t n_in, uint32_t n_out) {
+    const auto key = std::make_tuple(filter, n_in, n_out);
+    {
+        std::lock_guard<std::mutex> lk(pass_mu_);
+        auto it = passes_.find(key);
+        if (it != passes_.end()) return it->second;
+    }
+    auto p = build_pass(filter, n_in, n_out);
+    std::lock_guard<std::mutex> lk(pass_mu_);
+    if (passes_.size() >= kMaxCachedTables) {
+        passes_.erase(pass_order_.front());
+        pass_order_.erase(pass_order_.begin());
+    }
+    if (passes_.emplace(key, p).second) pass_order_.push_back(key);
+    return p;
+}
+
+// ---- launch planning ------------------------------------------------------------------------------
+
+namespace {
+
+int up16(int v) { return (v + 15) & ~15; }
+
+// Source bytes a strip [a, b) of output columns needs per row (16-byte aligned at both ends).
+int strip_bytes(const PassPlan& h, int a, int b, int ch, int sw) {
+    const int xl = h.left[a], xr = h.right[b - 1];
+    const int b0 = (xl * ch) & ~15;
+    const int b1 = std::min(up16(xr * ch), up16(sw * ch));
+    return b1 - b0;
+}
+
+// Cut [0, dw) into column strips whose source footprint fits the kernel's staging row.
+bool cut_strips(const PassPlan& h, int ch, int sw, int max_src, int max_out, std::vector<std::pair<int, int>>* out) {
+    const int dw = int(h.n_out);
+    auto greedy = [&](int cap, std::vector<std::pair<int, int>>* res) {
+        res->clear();
+        int a = 0;
+        while (a < dw) {
+            if (strip_bytes(h, a, a + 1, ch, sw) > max_src) return false;
+            int b = a + 1;
+            while (b < dw && b - a < cap && strip_bytes(h, a, b + 1, ch, sw) <= max_src) ++b;
+            res->emplace_back(a, b);
+            a = b;
+        }
+        return true;
+    };
+    if (!greedy(max_out, out)) return false;
+    const int n = int(out->size());
+    std::vector<std::pair<int, int>> even;
+    if (n > 1 && greedy((dw + n - 1) / n, &even) && int(even.size()) == n) *out = even;
+    return true;
+}
+
+}  // namespace
+
+LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* status, bool exact) {
+    LaunchPlan lp;
+    struct Cand {
+        int job;
+        std::vector<std::pair<int, int>> strips;
+        int ch, kv, kh;
+    };
+    std::vector<Cand> cands;
+    lp.jobs.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        status[i] = kOk;
+        try {
+            const JobDesc& d = descs[i];
+            validate_job(d);
+            if (d.sw == 0 || d.sh == 0 || d.dw == 0 || d.dh == 0 || (d.sw == d.dw && d.sh == d.dh))
+                fail(kInvalidArg, "degenerate resize (empty or same-size) must be handled by the caller");
+            auto tv = dev.tables(d.filter, d.sh, d.dh);
+            auto th = dev.tables(d.filter, d.sw, d.dw);
+            DevJob j{};
+            j.src = static_cast<const uint8_t*>(d.src);
+            j.dst = static_cast<uint8_t*>(d.dst);
+            j.tmp = nullptr;
+            j.src_pitch = d.src_pitch;
+            j.dst_pitch = d.dst_pitch;
+            j.sw = d.sw; j.sh = d.sh; j.dw = d.dw; j.dh = d.dh;
+            j.channels = d.channels;
+            j.bps = d.bps;
+            j.v = tv->pass;
+            j.h = th->pass;
+            const int idx = int(lp.jobs.size());
+            lp.jobs.push_back(j);
+            lp.keepalive.push_back(tv);
+            lp.keepalive.push_back(th);
+
+            bool fused = !exact && d.bps == 1 && d.sh >= d.dh && d.sw >= d.dw &&
+                         fused_supported(d.channels, tv->pass.ring_k, th->pass.ring_k) &&
+                         (reinterpret_cast<uintptr_t>(d.src) & 15) == 0 && (d.src_pitch & 15) == 0;
+            Cand c{idx, {}, d.channels, tv->pass.ring_k, th->pass.ring_k};
+            if (fused) {
+                const int max_out = 1024 / d.channels;  // out-stage row <= 1 KB
+                fused = cut_strips(*th->host, d.channels, int(d.sw), fused_max_src_bytes(d.channels), max_out,
+                                   &c.strips);
+            }
+            if (fused) cands.push_back(std::move(c));
+            else {
+                lp.generic_jobs.push_back(idx);
+                lp.scratch_floats = std::max(lp.scratch_floats, size_t(d.sw) * d.channels * d.dh);
+            }
+        } catch (const Error& e) {
+            status[i] = e.status;
+            set_last_error(e.what);
+        }
+    }
+    if (cands.empty()) return lp;
+
+    // Row chunks: enough CTAs to fill every SM twice over (two CTAs are resident per SM), but
+    // no chunk so short that the vertical halo (taps - ratio rows per chunk) dominates.
+    size_t total_strips = 0;
+    for (auto& c : cands) total_strips += c.strips.size();
+    const size_t slots = size_t(dev.sm_count()) * 2;
+    const int group_rows = fused_group_rows();
+    for (auto& c : cands) {
+        const DevJob& j = lp.jobs[c.job];
+        // Pick the chunk count that minimises (tail-wave waste) x (vertical halo recompute), assuming
+        // the other jobs of the batch are cut the same way.
+        const PassPlan& vp = *lp.keepalive[size_t(c.job) * 2]->host;
+        const double ratio_v = double(j.sh) / double(j.dh);
+        const double halo_rows = std::max(0.0, double(vp.max_count) - ratio_v);
+        const int max_chunks = std::max(1, std::min(64, int(j.dh) / (2 * group_rows)));
+        int n_chunks = 1;
+        double best = 1e30;
+        for (int nc = 1; nc <= max_chunks; ++nc) {
+            const double items = double(total_strips) * nc;
+            const double waves = items / double(slots);
+            const double tail = std::ceil(waves) / waves;
+            const double halo = 1.0 + halo_rows / (double(j.sh) / nc);
+            const double cost = tail * halo;
+            if (cost < best - 1e-9) { best = cost; n_chunks = nc; }
+        }
+        FusedGroup* g = nullptr;
+        for (auto& gg : lp.groups)
+            if (gg.channels == c.ch && gg.kv == c.kv && gg.kh == c.kh) g = &gg;
+        if (!g) {
+            lp.groups.push_back(FusedGroup{c.ch, c.kv, c.kh, {}, {}});
+            g = &lp.groups.back();
+        }
+        const PassPlan& hp = *lp.keepalive[size_t(c.job) * 2 + 1]->host;
+        for (int k = 0; k < n_chunks; ++k) {
+            const int oy0 = int(int64_t(j.dh) * k / n_chunks);
+            const int oy1 = int(int64_t(j.dh) * (k + 1) / n_chunks);
+            if (oy1 <= oy0) continue;
+            for (auto& s : c.strips) {
+                g->items.push_back(WorkItem{c.job, s.first, s.second, oy0, oy1});
+                const int xl = hp.left[s.first], xr = hp.right[s.second - 1];
+                const int pxb = ((xl * c.ch) & ~15) / c.ch;
+                g->geom.tmp_px = std::max(g->geom.tmp_px, xr - pxb + 1);
+                g->geom.out_pitch_w = std::max(g->geom.out_pitch_w, ((s.second - s.first) * c.ch + 3) / 4 + 2);
+            }
+        }
+    }
+    for (auto& g : lp.groups) {
+        g.geom.tmp_px |= 1;        // odd pixel pitch: conflict-free float4 column walks
+        g.geom.out_pitch_w |= 1;   // odd word pitch: conflict-free per-row pixel stores
+        g.geom.n_items = int(g.items.size());
+        if (fused_smem_bytes(g.channels, g.geom) > 113 * 1024)
+            fail(kUnsupported, "internal: fused kernel shared-memory budget exceeded");
+    }
+    return lp;
+}
+
+size_t Context::desc_bytes(const LaunchPlan& lp) const {
+    size_t b = (sizeof(DevJob) * lp.jobs.size() + 15) & ~size_t(15);
+    for (auto& g : lp.groups) b += (sizeof(WorkItem) * g.items.size() + 15) & ~size_t(15);
+    return std::max<size_t>(b, 16);
+}
+
+void Context::fill_desc(const LaunchPlan& lp, uint8_t* host, float* scratch) const {
+    DevJob* jobs = reinterpret_cast<DevJob*>(host);
+    for (size_t i = 0; i < lp.jobs.size(); ++i) jobs[i] = lp.jobs[i];
+    for (int idx : lp.generic_jobs) jobs[idx].tmp = scratch;
+    size_t off = (sizeof(DevJob) * lp.jobs.size() + 15) & ~size_t(15);
+    for (auto& g : lp.groups) {
+        std::memcpy(host + off, g.items.data(), sizeof(WorkItem) * g.items.size());
+        off += (sizeof(WorkItem) * g.items.size() + 15) & ~size_t(15);
+    }
+}
+
+void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, cudaStream_t stream, bool exact) {
+    const DevJob* d_jobs = reinterpret_cast<const DevJob*>(d_desc_base);
+    size_t off = (sizeof(DevJob) * lp.jobs.size() + 15) & ~size_t(15);
+    for (auto& g : lp.groups) {
+        const WorkItem* d_items = reinterpret_cast<const WorkItem*>(d_desc_base + off);
+        check_cuda(launch_fused(g.channels, g.kv, g.kh, d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");
+        off += (sizeof(WorkItem) * g.items.size() + 15) & ~size_t(15);
+        launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    for (int idx : lp.generic_jobs) {
+        check_cuda(launch_generic(lp.jobs[idx], exact, stream), "launch generic kernels");
+        launches.fetch_add(2, std::memory_order_relaxed);
+    }
+}
+
+void Context::enqueue(Device& dev, LaunchPlan& lp, Buffer& h_desc, Buffer& d_desc, Buffer& d_scratch,
+                      cudaStream_t stream, bool exact) {
+    (void)dev;
+    if (lp.jobs.empty()) return;
+    if (lp.scratch_floats) d_scratch.reserve(lp.scratch_floats * sizeof(float));
+    for (int idx : lp.generic_jobs) lp.jobs[idx].tmp = static_cast<float*>(d_scratch.p);
+    const size_t bytes = desc_bytes(lp);
+    h_desc.reserve(bytes);
+    d_desc.reserve(bytes);
+    fill_desc(lp, static_cast<uint8_t*>(h_desc.p), static_cast<float*>(d_scratch.p));
+    check_cuda(cudaMemcpyAsync(d_desc.p, h_desc.p, bytes, cudaMemcpyHostToDevice, stream), "upload descriptors");
+    launch_resident(lp, static_cast<const uint8_t*>(d_desc.p), stream, exact);
+}
+
+// ---- host-buffer path -----------------------------------------------------------------------------
+
+namespace {
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+size_t device_pitch(size_t row_bytes) { return (row_bytes + 255) & ~size_t(255); }
+
+struct HostJobState {  // one in-flight host job on a lane
+    JobDesc d;
+    size_t in_pitch = 0, out_pitch = 0;
+    bool out_staged = false;
+};
+
+// Stage + H2D + kernels + D2H for one job on one lane; everything asynchronous on the lane stream
+// except the pageable staging memcpy.  finish_host_job() completes it.
+void start_host_job(Context& ctx, Device& dev, Lane& l, const JobDesc& d, HostJobState* st, bool exact) {
+    const size_t in_row = size_t(d.sw) * d.channels * d.bps;
+    const size_t out_row = size_t(d.dw) * d.channels * d.bps;
+    st->d = d;
+    st->in_pitch = device_pitch(in_row);
+    st->out_pitch = device_pitch(out_row);
+    l.d_in.reserve(st->in_pitch * d.sh);
+    l.d_out.reserve(st->out_pitch * d.dh);
+    const void* src = d.src;
+    size_t src_pitch = d.src_pitch;
+    if (!is_pinned(d.src)) {  // pageable: pack rows tightly into the lane's pinned staging
+        l.h_in.reserve(in_row * d.sh);
+        uint8_t* hp = static_cast<uint8_t*>(l.h_in.p);
+        if (d.src_pitch == in_row) std::memcpy(hp, d.src, in_row * d.sh);
+        else for (uint32_t y = 0; y < d.sh; ++y)
+            std::memcpy(hp + size_t(y) * in_row, static_cast<const uint8_t*>(d.src) + size_t(y) * d.src_pitch, in_row);
+        src = hp;
+        src_pitch = in_row;
+    }
+    check_cuda(cudaMemcpy2DAsync(l.d_in.p, st->in_pitch, src, src_pitch, in_row, d.sh, cudaMemcpyHostToDevice, l.stream),
+               "H2D copy");
+    JobDesc dj = d;
+    dj.src = l.d_in.p;
+    dj.dst = l.d_out.p;
+    dj.src_pitch = st->in_pitch;
+    dj.dst_pitch = st->out_pitch;
+    int status = kOk;
+    LaunchPlan lp = ctx.plan(dev, &dj, 1, &status, exact);
+    if (status != kOk) fail(Status(status), last_error());
+    ctx.enqueue(dev, lp, l.h_desc, l.d_desc, l.d_scratch, l.stream, exact);
+    st->out_staged = !is_pinned(d.dst);
+    void* dst = d.dst;
+    size_t dst_pitch = d.dst_pitch;
+    if (st->out_staged) {
+        l.h_out.reserve(out_row * d.dh);
+        dst = l.h_out.p;
+        dst_pitch = out_row;
+    }
+    check_cuda(cudaMemcpy2DAsync(dst, dst_pitch, l.d_out.p, st->out_pitch, out_row, d.dh, cudaMemcpyDeviceToHost, l.stream),
+               "D2H copy");
+    // `lp` (and the table references it keeps alive) may go away now: the cache still holds the
+    // tables, and kernels already enqueued only need the device memory, which eviction frees with a
+    // synchronising cudaFree.
+}
+
+void finish_host_job(Lane& l, const HostJobState& st) {
+    check_cuda(cudaStreamSynchronize(l.stream), "resize (stream sync)");
+    if (st.out_staged) {
+        const JobDesc& d = st.d;
+        const size_t out_row = size_t(d.dw) * d.channels * d.bps;
+        const uint8_t* hp = static_cast<const uint8_t*>(l.h_out.p);
+        if (d.dst_pitch == out_row) std::memcpy(d.dst, hp, out_row * d.dh);
+        else for (uint32_t y = 0; y < d.dh; ++y)
+            std::memcpy(static_cast<uint8_t*>(d.dst) + size_t(y) * d.dst_pitch, hp + size_t(y) * out_row, out_row);
+    }
+}
+
+// Cases imageops::resize answers without resampling.  Returns true if handled.
+bool trivial_resize(const JobDesc& d) {
+    if (d.dw == 0 || d.dh == 0) return true;
+    const size_t out_row = size_t(d.dw) * d.channels * d.bps;
+    if (d.sw == 0 || d.sh == 0) {  // nothing to sample from: zeroed ImageBuffer::new(nw, nh)
+        for (uint32_t y = 0; y < d.dh; ++y) std::memset(static_cast<uint8_t*>(d.dst) + size_t(y) * d.dst_pitch, 0, out_row);
+        return true;
+    }
+    if (d.sw == d.dw && d.sh == d.dh) {  // same dimensions: plain copy
+        for (uint32_t y = 0; y < d.dh; ++y)
+            std::memcpy(static_cast<uint8_t*>(d.dst) + size_t(y) * d.dst_pitch,
+                        static_cast<const uint8_t*>(d.src) + size_t(y) * d.src_pitch, out_row);
+        return true;
+    }
+    return false;
+}
+
+}  // namespace
+
+void Context::resize_host(const JobDesc& d, int* device_index_out) {
+    validate_job(d);
+    if (trivial_resize(d)) return;
+    Device& dev = device(next_device());
+    if (device_index_out) *device_index_out = dev.index();
+    check_cuda(cudaSetDevice(dev.ordinal()), "cudaSetDevice");
+    Lane* l = dev.acquire_lane();
+    try {
+        HostJobState st;
+        start_host_job(*this, dev, *l, d, &st, mode.load() == 1);
+        finish_host_job(*l, st);
+    } catch (...) {
+        cudaStreamSynchronize(l->stream);
+        dev.release_lane(l);
+        throw;
+    }
+    dev.release_lane(l);
+}
+
+void Context::resize_batch_host(JobDesc* descs, size_t n, int* status, int* device_out) {
+    const int G = device_count();
+    const bool exact = mode.load() == 1;
+    std::vector<std::string> errors{size_t(G), std::string()};
+    auto worker = [&](int g) {
+        Device& dev = device(g);
+        if (cudaSetDevice(dev.ordinal()) != cudaSuccess) {
+            for (size_t i = size_t(g); i < n; i += size_t(G)) status[i] = kCudaError;
+            return;
+        }
+        // software pipeline over the device's lanes: while lane k waits for its DMA, the next jobs
+        // are staged and enqueued on the other lanes
+        std::lock_guard<std::mutex> batch_lock(dev.batch_mu);  // one batch at a time owns all lanes
+        const int L = dev.lane_count();
+        std::vector<Lane*> lanes;
+        for (int k = 0; k < L; ++k) lanes.push_back(dev.acquire_lane());
+        std::vector<HostJobState> st(size_t(L), HostJobState{});
+        std::vector<long> inflight(size_t(L), -1);
+        auto drain = [&](int k) {
+            if (inflight[size_t(k)] < 0) return;
+            const size_t i = size_t(inflight[size_t(k)]);
+            try {
+                finish_host_job(*lanes[size_t(k)], st[size_t(k)]);
+            } catch (const Error& e) {
+                status[i] = e.status;
+                errors[size_t(g)] = e.what;
+            }
+            inflight[size_t(k)] = -1;
+        };
+        int k = 0;
+        for (size_t i = size_t(g); i < n; i += size_t(G)) {
+            status[i] = kOk;
+            device_out[i] = g;
+            try {
+                validate_job(descs[i]);
+                if (trivial_resize(descs[i])) continue;
+                drain(k);
+                start_host_job(*this, dev, *lanes[size_t(k)], descs[i], &st[size_t(k)], exact);
+                inflight[size_t(k)] = long(i);
+                k = (k + 1) % L;
+            } catch (const Error& e) {
+                status[i] = e.status;
+                errors[size_t(g)] = e.what;
+                cudaStreamSynchronize(lanes[size_t(k)]->stream);
+            }
+        }
+        for (int q = 0; q < L; ++q) drain(q);
+        for (Lane* l : lanes) dev.release_lane(l);
+    };
+    if (G == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g) th.emplace_back(worker, g);
+        for (auto& t : th) t.join();
+    }
+    for (auto& e : errors) if (!e.empty()) set_last_error(e);
+}
+
+}  // namespace ikc

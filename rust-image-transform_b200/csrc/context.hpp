@@ -1,0 +1,158 @@
+// context.hpp -- process-wide context behind the C ABI: devices, lanes (stream + pinned staging +
+// device buffers), weight-table caches, launch planning.  Product code.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "device_types.hpp"
+#include "plan.hpp"
+
+namespace ikc {
+
+// Status codes mirror enum ikc_status in include/imagekit_cuda.h.
+enum Status : int { kOk = 0, kInvalidArg = 1, kUnsupported = 2, kTooLarge = 3, kCudaError = 4, kOom = 5 };
+
+struct Error {
+    Status status;
+    std::string what;
+};
+[[noreturn]] void fail(Status s, const std::string& what);
+void check_cuda(cudaError_t e, const char* what);
+
+void set_last_error(const std::string& s);
+const char* last_error();
+
+// A host- or device-resident resize request (pointers are interpreted by the caller of plan).
+struct JobDesc {
+    const void* src;
+    void* dst;
+    uint32_t sw, sh, dw, dh;
+    size_t src_pitch, dst_pitch;
+    int channels;
+    int bps;  // bytes per sample
+    int filter;
+};
+
+// Device copy of one PassPlan; frees its memory when the last holder lets go.
+struct DevTables {
+    int device = -1;
+    void* base = nullptr;  // single allocation holding left | right | w | ring
+    DevPass pass{};
+    std::shared_ptr<const PassPlan> host;
+    ~DevTables();
+};
+
+struct FusedGroup {
+    int channels, kv, kh;
+    std::vector<WorkItem> items;
+    FusedGeom geom{};
+};
+
+// Everything needed to enqueue a set of device-resident jobs.
+struct LaunchPlan {
+    std::vector<DevJob> jobs;               // tmp pointers are patched at enqueue time
+    std::vector<FusedGroup> groups;         // fused launches (jobs referenced by index)
+    std::vector<int> generic_jobs;          // indices that take the two-launch path
+    std::vector<std::shared_ptr<DevTables>> keepalive;
+    size_t scratch_floats = 0;              // max f32 intermediate any generic job needs
+    int launches() const { return int(groups.size()) + 2 * int(generic_jobs.size()); }
+};
+
+struct Buffer {  // grow-only device or pinned-host buffer
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned_host = false;
+    void reserve(size_t bytes);
+    void release();
+};
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    Buffer h_in{nullptr, 0, true}, h_out{nullptr, 0, true}, h_desc{nullptr, 0, true};
+    Buffer d_in, d_out, d_scratch, d_desc;
+};
+
+class Context;
+
+class Device {
+public:
+    Device(Context* ctx, int ordinal, int index);
+    ~Device();
+    int ordinal() const { return ordinal_; }
+    int index() const { return index_; }
+    int sm_count() const { return sm_count_; }
+
+    std::shared_ptr<DevTables> tables(int filter, uint32_t n_in, uint32_t n_out);
+    Lane* acquire_lane();
+    void release_lane(Lane* l);
+    int lane_count() const { return int(lanes_.size()); }
+    std::mutex batch_mu;  // serialises batch workers, which take every lane of the device
+
+private:
+    Context* ctx_;
+    int ordinal_, index_, sm_count_ = 148;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<std::unique_ptr<Lane>> lanes_;
+    std::vector<Lane*> free_;
+    std::map<std::tuple<int, uint32_t, uint32_t>, std::shared_ptr<DevTables>> tabs_;
+    std::vector<std::tuple<int, uint32_t, uint32_t>> tab_order_;
+};
+
+class Context {
+public:
+    Context(const int* ids, int n);
+    ~Context();
+    int device_count() const { return int(devs_.size()); }
+    Device& device(int i) { return *devs_[i]; }
+    int next_device() { return int(rr_.fetch_add(1, std::memory_order_relaxed) % devs_.size()); }
+
+    std::shared_ptr<const PassPlan> pass(int filter, uint32_t n_in, uint32_t n_out);
+
+    std::atomic<int> mode{0};
+    std::atomic<uint64_t> launches{0};
+
+    // Plan device-resident jobs for `dev` (device pointers in descs).  Per-job failures are
+    // reported through `status` (size n) and leave that job out of the plan.
+    LaunchPlan plan(Device& dev, const JobDesc* descs, size_t n, int* status, bool exact);
+    // Upload descriptors into `d_desc` (via pinned `h_desc`) and enqueue every launch on `stream`.
+    void enqueue(Device& dev, LaunchPlan& lp, Buffer& h_desc, Buffer& d_desc, Buffer& d_scratch,
+                 cudaStream_t stream, bool exact);
+    // Enqueue only (descriptors already resident at `d_desc_base`).
+    void launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, cudaStream_t stream, bool exact);
+    size_t desc_bytes(const LaunchPlan& lp) const;
+    void fill_desc(const LaunchPlan& lp, uint8_t* host, float* scratch) const;
+
+    // Host-buffer resize of one image through a lane of some device.
+    void resize_host(const JobDesc& d, int* device_index_out);
+    void resize_batch_host(JobDesc* descs, size_t n, int* status, int* device_out);
+
+private:
+    std::vector<std::unique_ptr<Device>> devs_;
+    std::atomic<uint64_t> rr_{0};
+    std::mutex pass_mu_;
+    std::map<std::tuple<int, uint32_t, uint32_t>, std::shared_ptr<const PassPlan>> passes_;
+    std::vector<std::tuple<int, uint32_t, uint32_t>> pass_order_;
+};
+
+// Validation shared by every entry point; throws Error.
+void validate_job(const JobDesc& d);
+
+struct PreparedBatch {
+    Context* ctx;
+    int device_index;
+    bool exact;  // arithmetic mode the batch was planned for
+    LaunchPlan lp;
+    Buffer d_desc, d_scratch;
+};
+
+}  // namespace ikc

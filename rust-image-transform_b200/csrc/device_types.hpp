@@ -1,0 +1,49 @@
+// device_types.hpp -- plain structs shared by the host planner and the CUDA kernels.
+#pragma once
+#include <cstdint>
+
+namespace ikc {
+
+// Device-resident tables of one separable pass (see plan.hpp for the host form).
+struct DevPass {
+    const int32_t* left;   // [n_out]
+    const int32_t* right;  // [n_out]
+    const float* w;        // [n_out * stride]
+    const float* ring;     // [n_in * ring_stride * 2] duplicated ring weights, or nullptr
+    int32_t stride;
+    int32_t ring_k;        // windows covering any source index (ring size)
+    int32_t ring_stride;   // ring_k rounded up to even (row stride of `ring`, in weight pairs)
+    int32_t n_in, n_out;
+    int32_t max_count;
+};
+
+// One image resize, device pointers.
+struct DevJob {
+    const uint8_t* src;
+    uint8_t* dst;
+    float* tmp;            // generic path only: f32 intermediate [dh][sw*channels]
+    uint64_t src_pitch;    // bytes
+    uint64_t dst_pitch;    // bytes
+    uint32_t sw, sh, dw, dh;
+    int32_t channels;
+    int32_t bps;           // bytes per sample: 1 or 2
+    DevPass v, h;
+};
+
+// One CTA's share of a job in the fused kernel: output columns [ox0,ox1) x rows [oy0,oy1).
+struct WorkItem {
+    int32_t job;
+    int32_t ox0, ox1;
+    int32_t oy0, oy1;
+};
+
+// Launch-wide shared-memory geometry of the fused kernel (max over the batch's items).
+struct FusedGeom {
+    int32_t tmp_px;        // tmp row capacity in pixels (float4 each); odd
+    int32_t src_stage_b;   // bytes per staged source row (multiple of 16)
+    int32_t n_stage_rows;  // rows in the source ring (multiple of kRowsPerStage)
+    int32_t out_pitch_w;   // out-stage row pitch in 32-bit words; odd
+    int32_t n_items;
+};
+
+}  // namespace ikc

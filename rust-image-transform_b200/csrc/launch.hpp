@@ -1,0 +1,23 @@
+// launch.hpp -- host-callable launchers implemented in kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+#include "device_types.hpp"
+
+namespace ikc {
+
+// Generic two-launch path (vertical -> f32 tmp in HBM -> horizontal).  `job` holds device pointers.
+cudaError_t launch_generic(const DevJob& job, bool exact, cudaStream_t stream);
+
+// Fused ring kernel over a list of work items (device arrays `jobs`, `items`).
+bool fused_supported(int channels, int ring_k_v, int ring_k_h);
+int fused_max_src_bytes(int channels);   // source bytes of one strip row the kernel can stage
+int fused_group_rows();                  // intermediate rows per group
+int fused_max_segments();                // x segments of a strip in the horizontal phase
+size_t fused_smem_bytes(int channels, const FusedGeom& geom);
+cudaError_t launch_fused(int channels, int ring_k_v, int ring_k_h, const DevJob* jobs, const WorkItem* items,
+                         const FusedGeom& geom, cudaStream_t stream);
+
+}  // namespace ikc

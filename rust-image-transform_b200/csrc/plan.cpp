@@ -1,0 +1,202 @@
+// plan.cpp -- dims rule + window/weight tables (see plan.hpp).  Must be compiled with
+// -ffp-contract=off and without fast-math: every float operation below is meant to round
+// exactly once, as the Rust reference does.
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+namespace ikc {
+namespace {
+
+// Rust `as` casts from float saturate and send NaN to zero.
+template <typename Int, typename Flt>
+Int saturating_cast(Flt v) {
+    if (std::isnan(v)) return Int(0);
+    const Flt lo = static_cast<Flt>(std::numeric_limits<Int>::min());
+    // max() of a 32/64-bit integer is not representable; 2^bits (or 2^(bits-1)) is.
+    const Flt hi_excl = std::ldexp(Flt(1), std::numeric_limits<Int>::digits);
+    if (v <= lo) return std::numeric_limits<Int>::min();
+    if (v >= hi_excl) return std::numeric_limits<Int>::max();
+    return static_cast<Int>(v);
+}
+
+// image 0.25.8 math/utils.rs: resize_dimensions(width, height, nwidth, nheight, fill = false)
+void fit_within(uint32_t width, uint32_t height, uint32_t nwidth, uint32_t nheight, uint32_t* rw,
+                uint32_t* rh) {
+    const double wratio = double(nwidth) / double(width);
+    const double hratio = double(nheight) / double(height);
+    const double ratio = std::fmin(wratio, hratio);
+    const uint64_t nw = std::max<uint64_t>(saturating_cast<uint64_t>(std::round(double(width) * ratio)), 1);
+    const uint64_t nh = std::max<uint64_t>(saturating_cast<uint64_t>(std::round(double(height) * ratio)), 1);
+    constexpr uint64_t kU32Max = std::numeric_limits<uint32_t>::max();
+    if (nw > kU32Max) {
+        const double r = double(kU32Max) / double(width);
+        *rw = uint32_t(kU32Max);
+        *rh = std::max<uint32_t>(saturating_cast<uint32_t>(std::round(double(height) * r)), 1);
+    } else if (nh > kU32Max) {
+        const double r = double(kU32Max) / double(height);
+        *rw = std::max<uint32_t>(saturating_cast<uint32_t>(std::round(double(width) * r)), 1);
+        *rh = uint32_t(kU32Max);
+    } else {
+        *rw = uint32_t(nw);
+        *rh = uint32_t(nh);
+    }
+}
+
+constexpr float kPi = 3.14159274101257324f;  // f32::consts::PI
+
+struct FilterDef {
+    float support;
+    float (*eval)(float);
+};
+
+float eval_box(float) { return 1.0f; }
+float eval_triangle(float x) {
+    const float a = std::fabs(x);
+    return a < 1.0f ? 1.0f - a : 0.0f;
+}
+float eval_sinc(float t) {
+    const float a = t * kPi;
+    return t == 0.0f ? 1.0f : sinf(a) / a;
+}
+float eval_lanczos3(float x) {
+    constexpr float t = 3.0f;
+    return std::fabs(x) < t ? eval_sinc(x) * eval_sinc(x / t) : 0.0f;
+}
+// bc_cubic_spline with the b, c parameters kept symbolic so the constant sub-expressions round
+// exactly as the crate's f32 code does; CatmullRom is (b, c) = (0, 1/2).
+float eval_bc_spline(float x, float b, float c) {
+    const float a = std::fabs(x);
+    const float a2 = a * a;   // powi(2)
+    const float a3 = a * a2;  // powi(3)
+    float k = 0.0f;
+    if (a < 1.0f) {
+        k = (12.0f - 9.0f * b - 6.0f * c) * a3 + (-18.0f + 12.0f * b + 6.0f * c) * a2 + (6.0f - 2.0f * b);
+    } else if (a < 2.0f) {
+        k = (-b - 6.0f * c) * a3 + (6.0f * b + 30.0f * c) * a2 + (-12.0f * b - 48.0f * c) * a +
+            (8.0f * b + 24.0f * c);
+    }
+    return k / 6.0f;
+}
+float eval_catmullrom(float x) { return eval_bc_spline(x, 0.0f, 0.5f); }
+float eval_gaussian(float x) {
+    constexpr float r = 0.5f;
+    const float norm = 1.0f / (std::sqrt(2.0f * kPi) * r);
+    return norm * expf(-(x * x) / (2.0f * (r * r)));
+}
+
+bool lookup_filter(int filter, FilterDef* out) {
+    switch (filter) {
+        case kNearest: *out = {0.0f, eval_box}; return true;
+        case kTriangle: *out = {1.0f, eval_triangle}; return true;
+        case kCatmullRom: *out = {2.0f, eval_catmullrom}; return true;
+        case kGaussian: *out = {3.0f, eval_gaussian}; return true;
+        case kLanczos3: *out = {3.0f, eval_lanczos3}; return true;
+        default: return false;
+    }
+}
+
+}  // namespace
+
+float filter_support(int filter) {
+    FilterDef f;
+    return lookup_filter(filter, &f) ? f.support : -1.0f;
+}
+
+int target_dims(uint32_t ow, uint32_t oh, bool has_w, uint32_t w, bool has_h, uint32_t h, uint32_t* tw,
+                uint32_t* th) {
+    if (!has_w && !has_h) {  // transform.rs:67-69
+        *tw = ow;
+        *th = oh;
+        return 1;
+    }
+    // transform.rs:74-82: the missing side follows the other one's scale, in f32.
+    uint32_t want_w = w, want_h = h;
+    if (!has_w) want_w = saturating_cast<uint32_t>(std::round(float(ow) * (float(h) / float(oh))));
+    if (!has_h) want_h = saturating_cast<uint32_t>(std::round(float(oh) * (float(w) / float(ow))));
+    want_w = std::max<uint32_t>(want_w, 1);  // transform.rs:86-87
+    want_h = std::max<uint32_t>(want_h, 1);
+    if (want_w == ow && want_h == oh) {  // DynamicImage::resize: same size -> clone
+        *tw = ow;
+        *th = oh;
+        return 2;
+    }
+    fit_within(ow, oh, want_w, want_h, tw, th);
+    if (*tw == ow && *th == oh) return 3;  // imageops::resize: same size -> copy
+    return 0;
+}
+
+std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n_out) {
+    FilterDef f;
+    if (!lookup_filter(filter, &f) || n_in == 0 || n_out == 0) return nullptr;
+    auto plan = std::make_shared<PassPlan>();
+    PassPlan& p = *plan;
+    p.filter = filter;
+    p.n_in = n_in;
+    p.n_out = n_out;
+    p.left.resize(n_out);
+    p.count.resize(n_out);
+    p.right.resize(n_out);
+
+    const float ratio = float(n_in) / float(n_out);
+    const float sratio = ratio < 1.0f ? 1.0f : ratio;
+    const float reach = f.support * sratio;
+
+    // Pass 1: windows + raw weights (ragged), exactly the crate's loop.
+    std::vector<std::vector<float>> ragged(n_out);
+    for (uint32_t o = 0; o < n_out; ++o) {
+        float centre = (float(o) + 0.5f) * ratio;
+        int64_t lo = saturating_cast<int64_t>(std::floor(centre - reach));
+        lo = std::clamp<int64_t>(lo, 0, int64_t(n_in) - 1);
+        int64_t hi = saturating_cast<int64_t>(std::ceil(centre + reach));
+        hi = std::clamp<int64_t>(hi, lo + 1, int64_t(n_in));
+        centre = centre - 0.5f;
+        std::vector<float>& ws = ragged[o];
+        ws.reserve(size_t(hi - lo));
+        float total = 0.0f;
+        for (int64_t i = lo; i < hi; ++i) {
+            const float wi = f.eval((float(uint32_t(i)) - centre) / sratio);
+            ws.push_back(wi);
+            total += wi;
+        }
+        for (float& wi : ws) wi /= total;
+        p.left[o] = int32_t(lo);
+        p.count[o] = int32_t(hi - lo);
+        p.right[o] = int32_t(hi);
+        p.max_count = std::max<uint32_t>(p.max_count, uint32_t(hi - lo));
+    }
+    p.stride = p.max_count;
+    p.w.assign(size_t(n_out) * p.stride, 0.0f);
+    for (uint32_t o = 0; o < n_out; ++o)
+        std::copy(ragged[o].begin(), ragged[o].end(), p.w.begin() + size_t(o) * p.stride);
+
+    // Ring form: how many windows cover each source index (windows are monotone, so the
+    // covering outputs are a contiguous run and get distinct residues mod ring_k).
+    std::vector<int32_t> cover(size_t(n_in) + 1, 0);
+    for (uint32_t o = 0; o < n_out; ++o) {
+        cover[p.left[o]] += 1;
+        cover[p.right[o]] -= 1;
+    }
+    int run = 0, k = 0;
+    for (uint32_t y = 0; y < n_in; ++y) {
+        run += cover[y];
+        k = std::max(k, run);
+    }
+    p.ring_k = k;
+    if (k >= 1 && k <= 8) {  // only the fused kernels use it; they handle ring_k <= 8
+        p.ring_stride = (k + 1) & ~1;  // even: every ring row is a whole number of 16-byte loads
+        p.ring.assign(size_t(n_in) * p.ring_stride * 2, 0.0f);
+        for (uint32_t o = 0; o < n_out; ++o) {
+            const int j = int(o % uint32_t(k));
+            for (int32_t i = 0; i < p.count[o]; ++i) {
+                const size_t at = (size_t(p.left[o] + i) * p.ring_stride + j) * 2;
+                p.ring[at] = p.ring[at + 1] = ragged[o][i];
+            }
+        }
+    }
+    return plan;
+}
+
+}  // namespace ikc

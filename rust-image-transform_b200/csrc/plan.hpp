@@ -1,0 +1,45 @@
+// plan.hpp -- host-side planning for the resize hot path: the dims rule and the per-pass
+// window/weight tables.  Product code (compiled into libimagekit_cuda.so).
+//
+// Follows /root/reference/src/transform.rs:62-90 (target size in f32) and the published
+// algorithm of crate image 0.25.8 (math/utils.rs resize_dimensions; imageops/sample.rs
+// window + weight generation and filter kernels).  Weights are built on the host with glibc
+// sinf/expf -- the same libm calls Rust's f32::sin/f32::exp lower to on linux-gnu -- so the
+// tables are bit-identical to what the reference computes; the GPU only consumes them.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+namespace ikc {
+
+enum Filter : int { kNearest = 0, kTriangle = 1, kCatmullRom = 2, kGaussian = 3, kLanczos3 = 4 };
+
+// a1-a3: returns an ikc_dims_code (0 resample, 1 passthrough, 2 clone, 3 copy).
+int target_dims(uint32_t ow, uint32_t oh, bool has_w, uint32_t w, bool has_h, uint32_t h,
+                uint32_t* tw, uint32_t* th);
+
+// One separable pass n_in -> n_out with a given filter.
+struct PassPlan {
+    int filter = 0;
+    uint32_t n_in = 0, n_out = 0;
+    uint32_t stride = 0;                // taps slots per output in `w` (>= max count)
+    std::vector<int32_t> left;          // [n_out] first source index of the window
+    std::vector<int32_t> count;         // [n_out] taps in the window (right - left)
+    std::vector<float> w;               // [n_out * stride] normalised weights, zero padded
+    // Ring form, used by the fused kernels.  ring_k = max number of windows that contain any
+    // one source index.  ring[(y * ring_stride + j) * 2 + {0,1}] = weight of source index y for the
+    // output o (o mod ring_k == j) whose window contains y, else 0; each weight is stored twice
+    // so that one 64-bit load feeds a packed fma.rn.f32x2.
+    int ring_k = 0;
+    int ring_stride = 0;                // ring_k rounded up to even
+    std::vector<float> ring;            // [n_in * ring_stride * 2]
+    std::vector<int32_t> right;         // [n_out] left + count
+    uint32_t max_count = 0;
+};
+
+std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n_out);
+
+float filter_support(int filter);
+
+}  // namespace ikc

@@ -1,0 +1,229 @@
+"""Thin object layer over the C ABI: context, pinned host buffers, prepared device batches."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import Job
+
+
+class ImageKitError(Exception):
+    """Mirror of ImageKitError::TransformError(String) (/root/reference/src/lib.rs:38-39)."""
+
+    def __init__(self, status: int, message: str):
+        self.status = status
+        name = _lib.STATUS_NAMES[status] if 0 <= status < len(_lib.STATUS_NAMES) else str(status)
+        super().__init__(f"Transformation error: {message} [{name}]")
+
+
+def _check(rc: int) -> None:
+    if rc != _lib.OK:
+        raise ImageKitError(rc, _lib.last_error())
+
+
+def target_dims(ow: int, oh: int, w: int | None, h: int | None):
+    """(tw, th, code) -- the dims rule of resize_image (transform.rs:62-90 + image 0.25.8)."""
+    tw, th = C.c_uint32(), C.c_uint32()
+    code = _lib.load().ikc_target_dims(ow, oh, w is not None, w or 0, h is not None, h or 0,
+                                       C.byref(tw), C.byref(th))
+    if code < 0:
+        raise ImageKitError(-code, _lib.last_error())
+    return tw.value, th.value, code
+
+
+def pass_table(filt: int, n_in: int, n_out: int):
+    """(left, count, weights[n_out, stride]) of one pass, as the kernels consume it."""
+    L = _lib.load()
+    stride = L.ikc_pass_table(filt, n_in, n_out, None, None, None, 0)
+    if stride == 0:
+        raise ImageKitError(_lib.ERR_INVALID_ARG, "cannot plan pass")
+    left = np.zeros(n_out, np.uint32)
+    cnt = np.zeros(n_out, np.uint32)
+    w = np.zeros((n_out, stride), np.float32)
+    pu32 = C.POINTER(C.c_uint32)
+    L.ikc_pass_table(filt, n_in, n_out, left.ctypes.data_as(pu32), cnt.ctypes.data_as(pu32),
+                     w.ctypes.data_as(C.POINTER(C.c_float)), stride)
+    return left, cnt, w
+
+
+class PinnedArray:
+    """A numpy view over cudaMallocHost memory obtained through ikc_host_alloc."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        _check(_lib.load().ikc_host_alloc(max(n, 1), C.byref(p)))
+        self.ptr = p.value
+        buf = (C.c_uint8 * max(n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            _lib.load().ikc_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """ikc_ctx: one per process (the Rust side keeps it in a OnceLock)."""
+
+    def __init__(self, device_ids=None):
+        L = _lib.load()
+        self._h = C.c_void_p()
+        if device_ids:
+            arr = (C.c_int * len(device_ids))(*device_ids)
+            rc = L.ikc_create(arr, len(device_ids), C.byref(self._h))
+        else:
+            rc = L.ikc_create(None, 0, C.byref(self._h))
+        _check(rc)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            _lib.load().ikc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_count(self) -> int:
+        return _lib.load().ikc_device_count(self._h)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(_lib.load().ikc_kernel_launches(self._h))
+
+    def set_mode(self, mode: int) -> None:
+        _check(_lib.load().ikc_set_mode(self._h, mode))
+
+    # ---- host-buffer entry points -------------------------------------------------------------
+    def resize(self, src: np.ndarray, dw: int, dh: int, filt: int = _lib.FILTER_LANCZOS3,
+               out: np.ndarray | None = None) -> np.ndarray:
+        """imageops::resize(src, dw, dh, filt) on HxWxC (or HxW) u8/u16 host arrays."""
+        squeeze = src.ndim == 2
+        s = src[:, :, None] if squeeze else src
+        if s.ndim != 3:
+            raise ImageKitError(_lib.ERR_INVALID_ARG, "expected HxWxC or HxW array")
+        if not (s.strides[2] == s.itemsize and s.strides[1] == s.itemsize * s.shape[2]):
+            s = np.ascontiguousarray(s)
+        sh, sw, ch = s.shape
+        dst = out if out is not None else np.empty((dh, dw, ch), s.dtype)
+        d3 = dst[:, :, None] if dst.ndim == 2 else dst
+        assert d3.shape == (dh, dw, ch) and d3.dtype == s.dtype
+        L = _lib.load()
+        fn = {1: L.ikc_resize_u8, 2: L.ikc_resize_u16}.get(s.itemsize)
+        if fn is None:
+            raise ImageKitError(_lib.ERR_UNSUPPORTED, f"unsupported sample type {s.dtype}")
+        src_pitch = s.strides[0] if sh > 1 else sw * ch * s.itemsize
+        dst_pitch = d3.strides[0] if dh > 1 else dw * ch * s.itemsize
+        _check(fn(self._h, s.ctypes.data, sw, sh, src_pitch, ch, d3.ctypes.data, dw, dh, dst_pitch, filt))
+        if out is not None:
+            return out
+        return dst[:, :, 0] if squeeze else dst
+
+    def resize_image(self, src: np.ndarray, w: int | None, h: int | None) -> np.ndarray:
+        """resize_image(img, w, h) for a tight 8-bit raster through ikc_resize_image_u8."""
+        squeeze = src.ndim == 2
+        s = np.ascontiguousarray(src[:, :, None] if squeeze else src)
+        sh, sw, ch = s.shape
+        tw, th, _ = target_dims(sw, sh, w, h)
+        dst = np.empty((th, tw, ch), np.uint8)
+        otw, oth = C.c_uint32(), C.c_uint32()
+        code = _lib.load().ikc_resize_image_u8(self._h, s.ctypes.data, sw, sh, ch, w is not None, w or 0,
+                                               h is not None, h or 0, dst.ctypes.data, dst.nbytes,
+                                               C.byref(otw), C.byref(oth))
+        if code < 0:
+            raise ImageKitError(-code, _lib.last_error())
+        assert (otw.value, oth.value) == (tw, th)
+        return dst[:, :, 0] if squeeze else dst
+
+    def resize_batch(self, srcs, sizes, filt: int = _lib.FILTER_LANCZOS3, outs=None):
+        """ikc_resize_batch over host arrays; sizes = [(dw, dh)]. Returns (outputs, jobs)."""
+        n = len(srcs)
+        jobs = (Job * n)()
+        keep = []
+        results = []
+        for i, (s, (dw, dh)) in enumerate(zip(srcs, sizes)):
+            s3 = s[:, :, None] if s.ndim == 2 else s
+            if not s3.flags.c_contiguous:
+                s3 = np.ascontiguousarray(s3)
+            sh, sw, ch = s3.shape
+            d = outs[i] if outs is not None else np.empty((dh, dw, ch), np.uint8)
+            keep.append((s3, d))
+            results.append(d)
+            jobs[i] = Job(s3.ctypes.data, d.ctypes.data, sw, sh, dw, dh, sw * ch, dw * ch, ch, filt, 0, 0)
+        rc = _lib.load().ikc_resize_batch(self._h, jobs, n)
+        _check(rc)
+        return results, jobs
+
+    # ---- device-resident entry points ----------------------------------------------------------
+    def resize_device(self, device_index: int, stream: int, d_src: int, sw: int, sh: int, src_pitch: int,
+                      ch: int, d_dst: int, dw: int, dh: int, dst_pitch: int, filt: int = _lib.FILTER_LANCZOS3):
+        _check(_lib.load().ikc_resize_u8_device(self._h, device_index, stream, d_src, sw, sh, src_pitch, ch,
+                                                d_dst, dw, dh, dst_pitch, filt))
+
+    def prepare_batch(self, device_index: int, jobs) -> "PreparedBatch":
+        """jobs: list of (d_src, sw, sh, src_pitch, d_dst, dw, dh, dst_pitch, channels, filter)."""
+        n = len(jobs)
+        arr = (Job * n)()
+        for i, (d_src, sw, sh, sp, d_dst, dw, dh, dp, ch, filt) in enumerate(jobs):
+            arr[i] = Job(d_src, d_dst, sw, sh, dw, dh, sp, dp, ch, filt, 0, 0)
+        h = C.c_void_p()
+        _check(_lib.load().ikc_batch_prepare(self._h, device_index, arr, n, C.byref(h)))
+        return PreparedBatch(self, h, arr)
+
+
+class PreparedBatch:
+    def __init__(self, ctx: Context, handle, jobs):
+        self._ctx = ctx
+        self._h = handle
+        self.jobs = jobs
+
+    @property
+    def launch_count(self) -> int:
+        return _lib.load().ikc_batch_launch_count(self._h)
+
+    def launch(self, stream: int = 0) -> None:
+        _check(_lib.load().ikc_batch_launch(self._h, stream))
+
+    def free(self):
+        if self._h:
+            _lib.load().ikc_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+_default = None
+_default_lock = threading.Lock()
+
+
+def default_context() -> Context:
+    """Process-wide context (lazy), like the Rust wrapper's OnceLock<Context>."""
+    global _default
+    with _default_lock:
+        if _default is None:
+            _default = Context()
+        return _default

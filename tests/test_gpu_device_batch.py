@@ -1,0 +1,61 @@
+"""Device-resident entry points (what the roofline bench times): prepared batches replayed on a
+torch stream, checked against the oracle; plus full-size size-independent properties."""
+import numpy as np
+import pytest
+
+from conftest import delta_histogram, splitmix_noise
+
+pytestmark = pytest.mark.gpu
+
+
+def test_prepared_batch_on_torch_stream(ctx, ik, oracle):
+    import torch
+    ctx.set_mode(ik.MODE_FAST)
+    dev = torch.device("cuda:0")
+    shapes = [(480, 640, 3, 200, 150), (600, 800, 4, 400, 300), (1080, 1920, 3, 400, 225), (96, 128, 4, 61, 47)]
+    srcs, dsts, jobs = [], [], []
+    for i, (h, w, c, dw, dh) in enumerate(shapes):
+        s = splitmix_noise((h, w, c), image_id=i)
+        ts = torch.from_numpy(s).to(dev)
+        td = torch.zeros((dh, dw, c), dtype=torch.uint8, device=dev)
+        srcs.append((s, ts)); dsts.append(td)
+        jobs.append((ts.data_ptr(), w, h, w * c, td.data_ptr(), dw, dh, dw * c, c, ik.FILTER_LANCZOS3))
+    batch = ctx.prepare_batch(0, jobs)
+    assert all(j.status == 0 for j in batch.jobs)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        batch.launch(stream.cuda_stream)
+        batch.launch(stream.cuda_stream)                 # replayable
+    stream.synchronize()
+    for (s, _), td, (h, w, c, dw, dh) in zip(srcs, dsts, shapes):
+        got = td.cpu().numpy()
+        hist = delta_histogram(got, oracle.resize_exact(s, dw, dh, oracle.LANCZOS3))
+        assert max(abs(k) for k in hist) <= 1, hist
+    batch.free()
+
+
+def test_device_entry_point(ctx, ik, oracle):
+    import torch
+    ctx.set_mode(ik.MODE_FAST)
+    s = splitmix_noise((600, 800, 4))
+    ts = torch.from_numpy(s).cuda()
+    td = torch.zeros((300, 400, 4), dtype=torch.uint8, device="cuda")
+    ctx.resize_device(0, torch.cuda.current_stream().cuda_stream, ts.data_ptr(), 800, 600, 3200, 4, td.data_ptr(),
+                      400, 300, 1600)
+    torch.cuda.synchronize()
+    hist = delta_histogram(td.cpu().numpy(), oracle.resize_exact(s, 400, 300, oracle.LANCZOS3))
+    assert max(abs(k) for k in hist) <= 1, hist
+
+
+def test_full_size_properties_4k(ctx, ik):
+    """BASELINE config 2 at full size through size-independent properties: a constant image stays
+    constant, and resizing is linear up to rounding: resize(a) + resize(255 - a) ~= 255."""
+    ctx.set_mode(ik.MODE_FAST)
+    c = np.full((2160, 3840, 4), 201, np.uint8)
+    assert (ctx.resize(c, 1920, 1080) == 201).all()
+    a = splitmix_noise((2160, 3840, 4))
+    ra = ctx.resize(a, 1920, 1080).astype(np.int32)
+    rb = ctx.resize(255 - a, 1920, 1080).astype(np.int32)
+    s = ra + rb
+    inner = (ra > 0) & (ra < 255) & (rb > 0) & (rb < 255)   # unclamped samples
+    assert np.abs(s[inner] - 255).max() <= 1

@@ -1,0 +1,192 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+Bars: EXACT mode (two-launch generic kernels) is bit-equal; FAST mode (fused ring kernel, FMA) is
+within max |delta| <= 1 per u8 sample (north-star tolerance), with the delta histogram checked."""
+import numpy as np
+import pytest
+
+from conftest import checker, delta_histogram, photo_like, splitmix_noise
+
+pytestmark = pytest.mark.gpu
+TOL = 1  # max |delta| per u8 channel, BASELINE.json north_star
+
+
+def _fast(ctx, ik):
+    ctx.set_mode(ik.MODE_FAST)
+
+
+def _check_fast(got, want, label):
+    hist = delta_histogram(got, want)
+    assert max(abs(k) for k in hist) <= TOL, (label, hist)
+    off = sum(v for k, v in hist.items() if k != 0) / got.size
+    assert off < 0.002, (label, hist)   # FMA vs mul+add only flips values sitting on a .5 boundary
+    return hist
+
+
+SMALL_SHAPES = [  # (h, w, c, dw, dh)
+    (60, 80, 3, 40, 30), (64, 96, 4, 48, 32), (121, 161, 3, 16, 12), (24, 32, 3, 64, 48), (70, 70, 3, 33, 33),
+    (33, 47, 2, 19, 13), (45, 45, 1, 20, 17), (30, 40, 3, 1, 1), (2, 2, 3, 200, 200), (333, 1000, 3, 99, 33),
+    (17, 1, 3, 1, 5), (1, 19, 4, 7, 1), (600, 800, 3, 400, 300),
+]
+
+
+@pytest.mark.parametrize("shape", SMALL_SHAPES)
+@pytest.mark.parametrize("filt", [0, 1, 2, 3, 4])
+def test_exact_mode_bit_equal(ctx, ik, oracle, shape, filt):
+    h, w, c, dw, dh = shape
+    src = splitmix_noise((h, w, c), image_id=filt)
+    ctx.set_mode(ik.MODE_EXACT)
+    got = ctx.resize(src, dw, dh, filt)
+    want = oracle.resize_exact(src, dw, dh, filt)
+    assert np.array_equal(got, want), delta_histogram(got, want)
+
+
+@pytest.mark.parametrize("shape", SMALL_SHAPES)
+@pytest.mark.parametrize("filt", [0, 1, 2, 3, 4])
+def test_fast_mode_within_one_lsb(ctx, ik, oracle, shape, filt):
+    h, w, c, dw, dh = shape
+    src = splitmix_noise((h, w, c), image_id=10 + filt)
+    _fast(ctx, ik)
+    got = ctx.resize(src, dw, dh, filt)
+    want = oracle.resize_exact(src, dw, dh, filt)
+    _check_fast(got, want, (shape, filt))
+
+
+FUSED_SHAPES = [  # Lanczos3 downscales that take the fused ring kernel: (h, w, c, dw, dh)
+    (480, 640, 3, 200, 150), (480, 640, 4, 320, 240), (1080, 1920, 3, 400, 225), (1000, 1504, 4, 752, 500),
+    (777, 1031, 3, 515, 388), (901, 1200, 4, 411, 309), (2160, 3840, 4, 1920, 1080), (3024, 4032, 3, 400, 300),
+    (512, 512, 4, 511, 511), (300, 5000, 3, 2500, 150), (4000, 304, 4, 152, 2000), (768, 1024, 3, 1000, 750),
+]
+
+
+@pytest.mark.parametrize("shape", FUSED_SHAPES)
+@pytest.mark.parametrize("content", ["noise", "edges", "photo"])
+def test_fused_kernel_parity(ctx, ik, oracle, shape, content):
+    h, w, c, dw, dh = shape
+    if content != "noise" and h * w > 2_000_000:
+        pytest.skip("large shapes run on noise only")
+    src = {"noise": splitmix_noise, "edges": checker, "photo": photo_like}[content]((h, w, c))
+    _fast(ctx, ik)
+    before = ctx.kernel_launches
+    got = ctx.resize(src, dw, dh, ik.FILTER_LANCZOS3)
+    assert ctx.kernel_launches - before == 1, "expected the single-launch fused kernel"
+    want = oracle.resize_exact(src, dw, dh, oracle.LANCZOS3)
+    _check_fast(got, want, (shape, content))
+
+
+def test_fused_gaussian_downscale(ctx, ik, oracle):
+    src = splitmix_noise((700, 900, 4))
+    _fast(ctx, ik)
+    got = ctx.resize(src, 450, 350, ik.FILTER_GAUSSIAN)
+    _check_fast(got, oracle.resize_exact(src, 450, 350, oracle.GAUSSIAN), "gaussian")
+
+
+def test_constants_and_zero(ctx, ik, oracle):
+    _fast(ctx, ik)
+    for v in (0, 37, 255):
+        src = np.full((480, 640, 3), v, np.uint8)
+        assert (ctx.resize(src, 200, 150) == v).all()
+        src4 = np.full((300, 400, 4), v, np.uint8)
+        assert (ctx.resize(src4, 800, 600, ik.FILTER_CATMULLROM) == v).all()
+
+
+def test_reference_semantics_empty_and_same_size(ctx, ik):
+    _fast(ctx, ik)
+    out = ctx.resize(np.zeros((0, 0, 3), np.uint8), 5, 4)
+    assert out.shape == (4, 5, 3) and not out.any()
+    n = splitmix_noise((40, 50, 3))
+    assert np.array_equal(ctx.resize(n, 50, 40), n)
+
+
+def test_channel_independence_on_gpu(ctx, ik):
+    _fast(ctx, ik)
+    rgba = splitmix_noise((480, 640, 4))
+    full = ctx.resize(rgba, 320, 240)
+    rgb = ctx.resize(np.ascontiguousarray(rgba[:, :, :3]), 320, 240)
+    assert np.abs(full[:, :, :3].astype(int) - rgb.astype(int)).max() <= 1
+
+
+def test_pitched_host_buffers(ctx, ik, oracle):
+    _fast(ctx, ik)
+    big = splitmix_noise((500, 700, 3))
+    view = big[10:490, 20:660, :]                      # non-contiguous rows (pitch > row bytes)
+    out_big = np.zeros((200, 300, 3), np.uint8)
+    out_view = out_big[5:155, 7:207, :]
+    ctx.resize(view, 200, 150, ik.FILTER_LANCZOS3, out=out_view)
+    want = oracle.resize_exact(np.ascontiguousarray(view), 200, 150, oracle.LANCZOS3)
+    _check_fast(out_view, want, "pitched")
+    assert not out_big[:5].any() and not out_big[:, :7].any() and not out_big[155:].any()
+
+
+def test_u16_samples(ctx, ik, oracle):
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 65536, (90, 120, 3), dtype=np.uint16)
+    ctx.set_mode(ik.MODE_EXACT)
+    assert np.array_equal(ctx.resize(src, 50, 41), oracle.resize_exact(src, 50, 41, oracle.LANCZOS3))
+    _fast(ctx, ik)
+    got = ctx.resize(src, 50, 41)
+    assert np.abs(got.astype(int) - oracle.resize_exact(src, 50, 41, oracle.LANCZOS3).astype(int)).max() <= 1
+
+
+def test_resize_image_matches_reference_tests(ctx, ik, oracle):
+    """The reference's own resize tests (tests/transform.rs:11-96, 239-257), run on the GPU path."""
+    _fast(ctx, ik)
+    cases = [((800, 600), (400, None), (400, 300)), ((800, 600), (None, 300), (400, 300)),
+             ((800, 600), (400, 300), (400, 300)), ((1920, 1080), (960, None), (960, 540)),
+             ((800, 600), (None, None), (800, 600)), ((100, 100), (200, 200), (200, 200)),
+             ((800, 600), (1, 1), (1, 1)), ((2, 2), (200, 200), (200, 200)), ((1920, 1080), (640, 480), (640, 360))]
+    for (ow, oh), (w, h), expect in cases:
+        img = ik.DynamicImage.new_rgb8(ow, oh)
+        out = ik.resize_image(img, w, h, ctx=ctx)
+        assert out.dimensions() == expect
+        assert not out.pixels.any()                       # zero image stays zero
+    noise = ik.DynamicImage(splitmix_noise((333, 1000, 3)))
+    out = ik.resize_image(noise, 100, None, ctx=ctx)
+    assert out.dimensions() == (99, 33)
+    _check_fast(out.pixels, oracle.resize_image(noise.pixels, 100, None), "99x33")
+    got = ctx.resize_image(noise.pixels, 100, None)      # same through ikc_resize_image_u8
+    assert np.array_equal(got, out.pixels)
+
+
+def test_host_batch(ctx, ik, oracle):
+    _fast(ctx, ik)
+    srcs = [splitmix_noise((480 + 16 * i, 640, 3), image_id=i) for i in range(9)]
+    sizes = [(200, 150 + 5 * i) for i in range(9)]
+    outs, jobs = ctx.resize_batch(srcs, sizes)
+    for s, (dw, dh), o_, j in zip(srcs, sizes, outs, jobs):
+        assert j.status == 0
+        _check_fast(o_, oracle.resize_exact(s, dw, dh, oracle.LANCZOS3), "batch")
+
+
+def test_error_codes(ctx, ik):
+    L = ik._lib.load()
+    src = np.zeros((8, 8, 3), np.uint8)
+    dst = np.zeros((4, 4, 3), np.uint8)
+    h = ctx.handle
+    assert L.ikc_resize_u8(h, src.ctypes.data, 8, 8, 24, 3, dst.ctypes.data, 4, 4, 12, 9) == ik._lib.ERR_INVALID_ARG
+    assert L.ikc_resize_u8(h, src.ctypes.data, 8, 8, 24, 5, dst.ctypes.data, 4, 4, 20, 4) == ik._lib.ERR_UNSUPPORTED
+    assert L.ikc_resize_u8(h, src.ctypes.data, 8, 8, 24, 3, dst.ctypes.data, 70000, 4, 210000, 4) == ik._lib.ERR_TOO_LARGE
+    assert L.ikc_resize_u8(h, src.ctypes.data, 8, 8, 10, 3, dst.ctypes.data, 4, 4, 12, 4) == ik._lib.ERR_INVALID_ARG
+    assert L.ikc_resize_u8(h, None, 8, 8, 24, 3, dst.ctypes.data, 4, 4, 12, 4) == ik._lib.ERR_INVALID_ARG
+    with pytest.raises(ik.ImageKitError):
+        ik.resize_image(ik.DynamicImage.new_rgb8(10, 10), 4_000_000_000, None, ctx=ctx)  # reference would allocate
+
+
+def test_threads_share_one_context(ctx, ik, oracle):
+    """The reference calls resize_image concurrently from its tokio workers (src/lib.rs:180,286)."""
+    import threading
+    _fast(ctx, ik)
+    src = splitmix_noise((480, 640, 3))
+    want = oracle.resize_exact(src, 200, 150, oracle.LANCZOS3)
+    errs = []
+
+    def work():
+        try:
+            for _ in range(5):
+                _check_fast(ctx.resize(src, 200, 150), want, "thread")
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work) for _ in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
