@@ -267,6 +267,7 @@ int ikc_batch_prepare(ikc_ctx* ctx, int device_index, ikc_job* jobs, size_t n, i
         c.fill_desc(lp, host.data(), static_cast<float*>(b->impl.d_scratch.p));
         b->impl.d_desc.reserve(bytes);
         check_cuda(cudaMemcpy(b->impl.d_desc.p, host.data(), bytes, cudaMemcpyHostToDevice), "upload descriptors");
+        check_cuda(cudaDeviceSynchronize(), "upload descriptors (sync)");  // pageable source: wait for the DMA
         *out = b.release();
     });
     return rc != IKC_OK ? rc : first_bad;

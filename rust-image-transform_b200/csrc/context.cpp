@@ -151,6 +151,9 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
         p += slot;
         return at;
     };
+    struct SyncOnExit {  // pageable-source cudaMemcpy may return before the DMA lands, and the lanes'
+        ~SyncOnExit() { cudaDeviceSynchronize(); }  // non-blocking streams do not order against it
+    } sync_on_exit;
     t->pass.left = reinterpret_cast<const int32_t*>(put(host->left.data(), sizeof(int32_t) * n_out, b_idx));
     t->pass.right = reinterpret_cast<const int32_t*>(put(host->right.data(), sizeof(int32_t) * n_out, b_idx));
     t->pass.w = reinterpret_cast<const float*>(put(host->w.data(), sizeof(float) * host->w.size(), b_w));
@@ -288,7 +291,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
                          (reinterpret_cast<uintptr_t>(d.src) & 15) == 0 && (d.src_pitch & 15) == 0;
             Cand c{idx, {}, d.channels, tv->pass.ring_k, th->pass.ring_k};
             if (fused) {
-                const int max_out = 1024 / d.channels;  // out-stage row <= 1 KB
+                const int max_out = 256;  // outputs per strip (bounds the kernel's left/right table)
                 fused = cut_strips(*th->host, d.channels, int(d.sw), fused_max_src_bytes(d.channels), max_out,
                                    &c.strips);
             }
@@ -342,18 +345,19 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
             if (oy1 <= oy0) continue;
             for (auto& s : c.strips) {
                 g->items.push_back(WorkItem{c.job, s.first, s.second, oy0, oy1});
-                const int xl = hp.left[s.first], xr = hp.right[s.second - 1];
-                const int pxb = ((xl * c.ch) & ~15) / c.ch;
-                g->geom.tmp_px = std::max(g->geom.tmp_px, xr - pxb + 1);
-                g->geom.out_pitch_w = std::max(g->geom.out_pitch_w, ((s.second - s.first) * c.ch + 3) / 4 + 2);
+                // tmp row capacity: every staged source byte of the strip lands in some pixel slot
+                const int xl = hp.left[s.first];
+                const int b0 = (xl * c.ch) & ~15;
+                const int nb = strip_bytes(hp, s.first, s.second, c.ch, int(j.sw));
+                const int pxb = b0 / c.ch;
+                g->geom.tmp_px = std::max(g->geom.tmp_px, (b0 + nb - 1) / c.ch - pxb + 2);
             }
         }
     }
     for (auto& g : lp.groups) {
         g.geom.tmp_px |= 1;        // odd pixel pitch: conflict-free float4 column walks
-        g.geom.out_pitch_w |= 1;   // odd word pitch: conflict-free per-row pixel stores
         g.geom.n_items = int(g.items.size());
-        if (fused_smem_bytes(g.channels, g.geom) > 113 * 1024)
+        if (fused_smem_bytes(g.channels, g.kv, g.kh, g.geom) > 113 * 1024)
             fail(kUnsupported, "internal: fused kernel shared-memory budget exceeded");
     }
     return lp;

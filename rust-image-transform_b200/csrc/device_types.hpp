@@ -40,9 +40,6 @@ struct WorkItem {
 // Launch-wide shared-memory geometry of the fused kernel (max over the batch's items).
 struct FusedGeom {
     int32_t tmp_px;        // tmp row capacity in pixels (float4 each); odd
-    int32_t src_stage_b;   // bytes per staged source row (multiple of 16)
-    int32_t n_stage_rows;  // rows in the source ring (multiple of kRowsPerStage)
-    int32_t out_pitch_w;   // out-stage row pitch in 32-bit words; odd
     int32_t n_items;
 };
 

@@ -33,6 +33,7 @@ constexpr int kTmpRows = 16;                    // f32 intermediate rows per gro
 constexpr int kMaxSegs = 2 * kComputeWarps;     // horizontal segments: one per half warp
 constexpr int kHeaderBytes = 256;               // mbarriers
 constexpr int kMaxStages = 8;
+constexpr int kMaxStripOut = 272;                // outputs of one strip (256) + ring pre-roll, in the left/right table
 
 template <int C>
 struct Layout;
@@ -44,7 +45,7 @@ struct Layout<4> {
 template <>
 struct Layout<3> {
     static constexpr int kMaxSrcBytes = 864;
-    static constexpr int kRingRows = 20;
+    static constexpr int kRingRows = 16;
 };
 template <>
 struct Layout<2> {
@@ -99,40 +100,54 @@ __device__ __forceinline__ float byte_to_float(uint32_t word) {
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440u + BYTE)) - 8388608.0f;
 }
 
-// clamp to [0,255] and round half away from zero (f32::round), exact for every float
+// clamp to [0,255] and round half away from zero (f32::round).  trunc(v + 0.5) equals round(v) for
+// every non-negative float except v = 0.5 - 2^-25 (the add rounds up to 1.0); this path's sums differ
+// from the reference's by FMA/association rounding anyway, and the EXACT path (generic.cu) has no such case.
 __device__ __forceinline__ uint32_t quantize_u8(float v) {
     v = fminf(fmaxf(v, 0.0f), 255.0f);
-    const float t = truncf(v);
-    return uint32_t((v - t >= 0.5f) ? t + 1.0f : t);
+    return __float2uint_rz(v + 0.5f);
 }
 
+// Quantise one finished pixel and store it straight to the destination raster.  Lanes of a half
+// warp hold 16 different rows of the same column, so these are scattered 4-byte (or 1-byte) stores;
+// the sectors are completed in L2 by the same thread's next pixels before they reach HBM.
 template <int C>
-__device__ __forceinline__ void store_pixel(uint32_t* out_row, int op, float4 v) {
-    if (C == 4) {
-        out_row[op] = quantize_u8(v.x) | (quantize_u8(v.y) << 8) | (quantize_u8(v.z) << 16) |
-                      (quantize_u8(v.w) << 24);
+__device__ __forceinline__ void store_pixel(uint8_t* dst_px, bool word_ok, float4 v) {
+    const uint32_t r = quantize_u8(v.x), g = quantize_u8(v.y), b = quantize_u8(v.z), a = quantize_u8(v.w);
+    if (C == 4 && word_ok) {
+        *reinterpret_cast<uint32_t*>(dst_px) = r | (g << 8) | (b << 16) | (a << 24);
     } else {
-        uint8_t* ob = reinterpret_cast<uint8_t*>(out_row) + op * C;
-        ob[0] = uint8_t(quantize_u8(v.x));
-        if (C > 1) ob[1] = uint8_t(quantize_u8(v.y));
-        if (C > 2) ob[2] = uint8_t(quantize_u8(v.z));
+        dst_px[0] = uint8_t(r);
+        if (C > 1) dst_px[1] = uint8_t(g);
+        if (C > 2) dst_px[2] = uint8_t(b);
+        if (C > 3) dst_px[3] = uint8_t(a);
     }
+}
+
+// shared-memory atomic add issued by one lane (kept as inline PTX so the compiler does not wrap it
+// in its warp-aggregation sequence)
+__device__ __forceinline__ int smem_atomic_inc(int* p) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_addr(p)) : "memory");
+    return old;
 }
 
 }  // namespace
 
 // Block = 4 warps; two CTAs are resident per SM.
 //
-// Shared memory: [mbarriers][source ring: kRingRows x 1024 B][tmp: 16 rows x tmp_px x float4]
-//                [out stage: 16 rows x out_pitch_w words].
+// Shared memory: [mbarriers][source ring: kRingRows x 1024 B][vertical weight ring: kRingRows x KSV
+//                pairs][horizontal weights of the strip: tmp_px x KSH pairs][(left,right) of the
+//                strip's outputs][tmp: 16 rows x tmp_px x float4].  Weights travel with TMA bulk
+//                copies too, so the hot loops only read shared memory.
 //
-// Vertical phase: compute thread t owns source byte columns [4t,4t+4) and [512+4t,512+4t+4) of the
-// strip and marches down the source rows; its KV ring slots hold the partial sums of the <= KV
-// output rows currently open.  A finished row goes to tmp as one float4 per pixel (fewer than 4
-// channels are padded to 4 lanes).  Horizontal phase (per group of 16 tmp rows): lane & 15 = tmp
-// row, half warp = x segment of the strip; the same ring march along x.  Outputs whose window
-// straddles a segment boundary are completed from head/tail partial sums parked in tmp columns the
-// thread has already consumed.
+// Vertical phase: thread t owns source byte columns [4t,4t+4) and [512+4t,512+4t+4) of the strip and
+// marches down the source rows; its KV ring slots hold the partial sums of the <= KV output rows
+// currently open (slot = output row mod KV).  A finished row goes to tmp as one float4 per pixel
+// (fewer than 4 channels are padded to 4 lanes).  Every 16 finished rows the horizontal phase runs:
+// lane & 15 = tmp row, half warp = x segment of the strip; the same ring march along x.  Outputs whose
+// window straddles a segment boundary are completed from head/tail partial sums parked in tmp columns
+// the thread has already consumed.  Finished pixels are quantised and stored straight to HBM.
 template <int C, int KV, int KH>
 __global__ void __launch_bounds__(kThreads, 2)
 fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, const FusedGeom geom) {
@@ -145,9 +160,12 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
 
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
     int* rel_count = reinterpret_cast<int*>(full_bar + kMaxStages);  // warps done with each stage
+    uint64_t* hw_bar = full_bar + kMaxStages + kMaxStages / 2;       // after full_bar[8], rel_count[8]
     uint8_t* src_ring = smem + kHeaderBytes;
-    float4* tmp = reinterpret_cast<float4*>(src_ring + kRingRows * kSrcRowBytes);
-    uint32_t* out_stage = reinterpret_cast<uint32_t*>(tmp + size_t(kTmpRows) * geom.tmp_px);
+    float4* vw_ring = reinterpret_cast<float4*>(src_ring + kRingRows * kSrcRowBytes);  // [row][KSV/2]
+    float4* hw_smem = vw_ring + kRingRows * (KSV / 2);                                 // [px][KSH/2]
+    int2* hlr = reinterpret_cast<int2*>(hw_smem + size_t(geom.tmp_px) * (KSH / 2));    // (left, right)
+    float4* tmp = reinterpret_cast<float4*>(hlr + kMaxStripOut);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -177,30 +195,72 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     const int y_last = __ldg(vright + oy1 - 1);
     const int nrows = y_last - y_first;
 
-    // The source ring is refilled by whichever warp is last to finish a stage (see the vertical
-    // loop); the first fill of every stage is issued here.
+    // The source ring is refilled by whichever warp is last to finish a stage (see the row loop);
+    // the first fill of every stage is issued here.
     const uint8_t* const gsrc = J->src + size_t(y_first) * J->src_pitch + b0;
     const size_t src_pitch = J->src_pitch;
     auto issue_fill = [&](int stage, int r0) {  // rows [r0, r0 + kStageRows) of the chunk -> stage
         const int n = min(kStageRows, nrows - r0);
-        mbar_expect_tx(full_bar + stage, uint32_t(n) * uint32_t(nb));
+        const uint32_t wbytes = uint32_t(n) * (KSV * 8);
+        mbar_expect_tx(full_bar + stage, uint32_t(n) * uint32_t(nb) + wbytes);
         for (int i = 0; i < n; ++i)
             bulk_load(src_ring + (stage * kStageRows + i) * kSrcRowBytes, gsrc + size_t(r0 + i) * src_pitch,
                       uint32_t(nb), full_bar + stage);
+        bulk_load(vw_ring + stage * kStageRows * (KSV / 2), vring + size_t(y_first + r0) * (KSV / 2), wbytes,
+                  full_bar + stage);
     };
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_bar + s, 1);
             rel_count[s] = 0;
         }
+        mbar_init(hw_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (int s = 0; s < kStages && s * kStageRows < nrows; ++s) issue_fill(s, s * kStageRows);
+        // horizontal ring weights of the strip's source pixels [xl, xr): one bulk copy, used by every group
+        const uint32_t hbytes = uint32_t(xr - xl) * (KSH * 8);
+        mbar_expect_tx(hw_bar, hbytes);
+        bulk_load(hw_smem, hring + size_t(xl) * (KSH / 2), hbytes, hw_bar);
     }
+    // (left, right) of the strip's outputs (plus the few before ox0 whose windows reach into the strip)
+    const int o_lo = max(0, ox0 - KH + 1);
+    for (int i = tid; i < ox1 - o_lo; i += kThreads) hlr[i] = make_int2(__ldg(hleft + o_lo + i), __ldg(hright + o_lo + i));
     __syncthreads();
+    const int2* const lr_tab = hlr - o_lo;  // indexed by absolute output column
 
-    // ------------------------------------------------------------------ compute warps
-    // ---- vertical state (lives across groups)
+    // ---------------------------------------------------------------- horizontal segmentation
+    // The strip's outputs [ox0, ox1) are cut into n_seg runs of `per` outputs (a multiple of KH, so
+    // every segment starts on the same ring slot and the half warps of a warp walk the unrolled slot
+    // code in lock step).  Segment s owns outputs [os, oe) and the source pixels [seg_lo, seg_hi)
+    // between the end of the previous segment's last window and the end of its own last window.
+    const int span = xr - xl;
+    const int n_out = ox1 - ox0;
+    const int want_seg = max(1, min(kMaxSegs, span / (int(J->h.max_count) + 2 * KH + 2)));
+    const int per = ((n_out + want_seg - 1) / want_seg + KH - 1) / KH * KH;
+    const int hrow = lane & 15;
+    const int sidx = 2 * warp + (lane >> 4);
+    // A short last run (< KH outputs) is merged into the run before it: near the right edge several
+    // windows end on the same (clamped) pixel, and a segment must own at least one pixel per head.
+    int n_act = (n_out + per - 1) / per;
+    if (n_act > 1 && n_out - (n_act - 1) * per < KH) --n_act;
+    const int os = ox0 + sidx * per;
+    const bool h_active = sidx < n_act;
+    const bool has_next_seg = sidx + 1 < n_act;
+    const int oe = has_next_seg ? os + per : ox1;
+    int seg_lo = xr, seg_hi = xr;
+    if (h_active) {
+        seg_lo = (sidx == 0) ? xl : lr_tab[os - 1].y;
+        seg_hi = lr_tab[oe - 1].y;
+    }
+    const int h_slot0 = ox0 % KH;  // ring slot of every segment's first output
+    float4* const my_row = tmp + size_t(hrow) * geom.tmp_px - pxb;  // indexed by absolute source pixel
+    uint8_t* const dst_base = J->dst;
+    const size_t dst_pitch = J->dst_pitch;
+    const bool word_ok = C == 4 && ((reinterpret_cast<uintptr_t>(dst_base) | dst_pitch) & 3) == 0;
+    bool hw_ready = false;
+
+    // ---------------------------------------------------------------- vertical state
     float2 vacc[KV][4];  // [slot][byte pair]: bytes 0-1, 2-3 of the first word; 0-1, 2-3 of the second
 #pragma unroll
     for (int j = 0; j < KV; ++j)
@@ -209,17 +269,6 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     const bool v_active0 = 4 * tid < nb;
     const bool v_active1 = kHalfRowBytes + 4 * tid < nb;
     const uint8_t* my_src = src_ring + 4 * tid;
-    const float4* wv = vring + size_t(y_first) * (KSV / 2);  // ring weights of the prefetched row
-    int y = y_first;         // next source row to consume (its data is in the nxt_* registers)
-    int ready = y_first;     // rows below `ready` have landed in the ring
-    int fill_stage = 0;      // next stage to wait for
-    uint32_t fill_phase = 0;
-    int rel_stage = 0;       // stage being drained
-    int rel_base = 0;        // chunk-relative index of the first row held by that stage
-    int rows_in_stage = 0;   // rows consumed from the stage being drained
-    int ring_row = 0;        // ring row of source row y
-    uint32_t nxt0 = 0, nxt1 = 0;
-    float4 nxtw[KSV / 2];
 
     // Where this thread's eight vertical results land in a tmp row (float index within the row).
     int emit_off[8];
@@ -229,63 +278,51 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
         emit_off[i] = (byte / C - pxb) * 4 + (byte % C);
     }
 
-    // prefetch row y_first
-    if (nrows > 0) {
-        mbar_wait(full_bar + 0, 0);
-        fill_stage = (kStages > 1) ? 1 : 0;
-        fill_phase = (kStages > 1) ? 0 : 1;
-        ready = min(y_first + kStageRows, y_last);
-        nxt0 = *reinterpret_cast<const uint32_t*>(my_src);
-        nxt1 = *reinterpret_cast<const uint32_t*>(my_src + kHalfRowBytes);
-#pragma unroll
-        for (int jj = 0; jj < KSV / 2; ++jj) nxtw[jj] = __ldg(wv + jj);
-    }
-
-    // ---- horizontal segmentation of the strip: segment sidx owns source pixels [seg_lo, seg_hi)
-    const int span = xr - xl;
-    const int max_count_h = J->h.max_count;
-    const int n_seg = max(1, min(kMaxSegs, span / (max_count_h + 2 * KH + 2)));
-    const int seg_len = (span + n_seg - 1) / n_seg;
-    const int hrow = lane & 15;
-    const int sidx = 2 * warp + (lane >> 4);
-    const bool h_active = sidx < n_seg;
-    const int seg_lo = min(xl + sidx * seg_len, xr);
-    const int seg_hi = min(seg_lo + seg_len, xr);
-    // First output whose window ends after seg_lo (binary search over the monotone `right`).
-    int o_first = max(0, ox0 - KH + 1);
-    if (h_active) {
-        int lo = o_first, hi = ox1;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(hright + mid) > seg_lo) hi = mid; else lo = mid + 1;
-        }
-        o_first = lo;
-    }
-    const int o_ring0 = (o_first / KH) * KH;  // ring slot of output o is o % KH
-
-    const int out_bytes = (ox1 - ox0) * C;
-    float4* const my_row = tmp + size_t(hrow) * geom.tmp_px - pxb;  // indexed by absolute source pixel
-    uint32_t* const my_out = out_stage + size_t(hrow) * geom.out_pitch_w;
-
-    // Advance to the next source row and start loading it (data word pair + ring weights).
-    auto v_prefetch = [&](uint32_t& d0, uint32_t& d1, float4 (&w)[KSV / 2]) {
-        ++y;
-        ring_row = (ring_row + 1 == kRingRows) ? 0 : ring_row + 1;
-        wv += KSV / 2;
-        if (y < y_last) {
-            if (y == ready) {  // the next ring stage must have landed
-                mbar_wait(full_bar + fill_stage, fill_phase);
-                if (++fill_stage == kStages) { fill_stage = 0; fill_phase ^= 1; }
-                ready = min(ready + kStageRows, y_last);
-            }
-            d0 = *reinterpret_cast<const uint32_t*>(my_src + ring_row * kSrcRowBytes);
-            d1 = *reinterpret_cast<const uint32_t*>(my_src + ring_row * kSrcRowBytes + kHalfRowBytes);
-#pragma unroll
-            for (int jj = 0; jj < KSV / 2; ++jj) w[jj] = __ldg(wv + jj);
-        }
+    // `right` of 32 consecutive outputs lives one per lane and is broadcast with a shuffle one output
+    // ahead of its use, so no global load sits on the row loop's critical path.
+    int vr_base = max(0, oy0 - KV);
+    auto vr_load = [&](int base) {
+        const int o = base + lane;
+        return (o < oy1) ? __ldg(vright + o) : 0x7fffffff;
     };
-    // Accumulate one source row (8 byte columns) into every open ring slot.
-    auto v_accumulate = [&](uint32_t d0, uint32_t d1, const float4 (&w)[KSV / 2]) {
+    int vr_val = vr_load(vr_base);
+    auto v_end_of = [&](int o) {  // right[o] for o >= vr_base (uniform)
+        while (o - vr_base >= 32) {
+            vr_base += 32;
+            vr_val = vr_load(vr_base);
+        }
+        return __shfl_sync(0xffffffffu, vr_val, o - vr_base);
+    };
+    // Ring order starts at the first output whose window reaches row y_first: outputs above the chunk
+    // that are still open there hold ring slots until they close (their sums are never emitted).
+    int ov = vr_base;
+    int yend_next = v_end_of(ov);
+    while (yend_next <= y_first) yend_next = v_end_of(++ov);
+    int c_start = ov % KV;  // slot of output ov is ov mod KV; the unrolled slot loop is entered here
+
+    int y = y_first;        // next source row to consume
+    int ready = y_first;    // rows below `ready` have landed in the ring
+    int fill_stage = 0;     // next stage to wait for
+    uint32_t fill_phase = 0;
+    int rel_stage = 0;      // stage being drained
+    int rel_base = 0;       // chunk-relative index of the first row held by that stage
+    int rows_in_stage = 0;  // rows consumed from the stage being drained
+    int ring_row = 0;       // ring row of source row y
+    int g0 = oy0;           // first output row of the group being assembled in tmp
+    int emitted = 0;        // rows of that group already in tmp
+
+    // One source row into every open ring slot.
+    auto consume_row = [&]() {
+        if (y == ready) {  // the next ring stage must have landed
+            mbar_wait(full_bar + fill_stage, fill_phase);
+            if (++fill_stage == kStages) { fill_stage = 0; fill_phase ^= 1; }
+            ready = min(ready + kStageRows, y_last);
+        }
+        const uint32_t d0 = *reinterpret_cast<const uint32_t*>(my_src + ring_row * kSrcRowBytes);
+        const uint32_t d1 = *reinterpret_cast<const uint32_t*>(my_src + ring_row * kSrcRowBytes + kHalfRowBytes);
+        float4 w[KSV / 2];
+#pragma unroll
+        for (int jj = 0; jj < KSV / 2; ++jj) w[jj] = vw_ring[ring_row * (KSV / 2) + jj];
         const float2 s0 = make_float2(byte_to_float<0>(d0), byte_to_float<1>(d0));
         const float2 s1 = make_float2(byte_to_float<2>(d0), byte_to_float<3>(d0));
         const float2 s2 = make_float2(byte_to_float<0>(d1), byte_to_float<1>(d1));
@@ -299,16 +336,17 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             vacc[j][2] = __ffma2_rn(wj, s2, vacc[j][2]);
             vacc[j][3] = __ffma2_rn(wj, s3, vacc[j][3]);
         }
+        ++y;
+        ring_row = (ring_row + 1 == kRingRows) ? 0 : ring_row + 1;
         if (++rows_in_stage == kStageRows) {
             // This warp is done with the stage; the last of the 4 warps refills it with the rows one
-            // ring revolution further down (TMA bulk copies).
+            // ring revolution further down (TMA bulk copies).  Every lane's loads of the stage have
+            // returned (their values were consumed above), so the count alone orders the refill.
             rows_in_stage = 0;
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
-                if (atomicAdd(rel_count + rel_stage, 1) == kComputeWarps - 1) {
+                if (smem_atomic_inc(rel_count + rel_stage) == kComputeWarps - 1) {
                     rel_count[rel_stage] = 0;
-                    __threadfence_block();
                     if (rel_base + kRingRows < nrows) issue_fill(rel_stage, rel_base + kRingRows);
                 }
             }
@@ -317,43 +355,17 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
         }
     };
 
-    // Ring order starts KV outputs above the chunk: rows from y_first on also belong to those
-    // outputs; they are consumed but never emitted, and their slots clear as their windows close.
-    int ov = oy0 - KV;
-    int c_start = ((ov % KV) + KV) % KV;  // slot of output ov is ov mod KV
-
-    for (int g0 = oy0; g0 < oy1; g0 += kTmpRows) {
-        const int n_rows = min(kTmpRows, oy1 - g0);
-        int remaining = n_rows;
-
-        // ============================ vertical phase: fill tmp rows [0, n_rows)
+    while (ov < oy1) {
+        // ============================ vertical phase: fill tmp until the group is complete
         for (;;) {
 #pragma unroll
             for (int c = 0; c < KV; ++c) {
-                if (c >= c_start) {
-                    const int yend = (ov >= 0) ? __ldg(vright + ov) : y;
-                    while (y < yend) {
-                        // Two rows per trip, ping-ponging between the nxt_* registers and a second
-                        // set, so each row's loads are issued one row ahead without register copies.
-                        uint32_t alt0, alt1;
-                        float4 altw[KSV / 2];
-                        if (y + 1 < yend) {
-                            v_prefetch(alt0, alt1, altw);
-                            v_accumulate(nxt0, nxt1, nxtw);
-                            v_prefetch(nxt0, nxt1, nxtw);
-                            v_accumulate(alt0, alt1, altw);
-                        } else {
-                            v_prefetch(alt0, alt1, altw);
-                            v_accumulate(nxt0, nxt1, nxtw);
-                            nxt0 = alt0;
-                            nxt1 = alt1;
-#pragma unroll
-                            for (int jj = 0; jj < KSV / 2; ++jj) nxtw[jj] = altw[jj];
-                        }
-                    }
-                    const bool live = ov >= oy0;
-                    if (live) {
-                        float* trow = reinterpret_cast<float*>(tmp + size_t(ov - g0) * geom.tmp_px);
+                if (c >= c_start) {  // output ov accumulates in slot c
+                    const int yend = yend_next;
+                    yend_next = (ov + 1 < oy1) ? v_end_of(ov + 1) : 0x7fffffff;
+                    while (y < yend) consume_row();
+                    if (ov >= oy0) {
+                        float* trow = reinterpret_cast<float*>(tmp + size_t(emitted) * geom.tmp_px);
                         if (C == 4) {
                             if (v_active0)
                                 *reinterpret_cast<float4*>(trow + emit_off[0]) =
@@ -363,23 +375,19 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                                     make_float4(vacc[c][2].x, vacc[c][2].y, vacc[c][3].x, vacc[c][3].y);
                         } else {
                             if (v_active0) {
-                                trow[emit_off[0]] = vacc[c][0].x;
-                                trow[emit_off[1]] = vacc[c][0].y;
-                                trow[emit_off[2]] = vacc[c][1].x;
-                                trow[emit_off[3]] = vacc[c][1].y;
+                                trow[emit_off[0]] = vacc[c][0].x; trow[emit_off[1]] = vacc[c][0].y;
+                                trow[emit_off[2]] = vacc[c][1].x; trow[emit_off[3]] = vacc[c][1].y;
                             }
                             if (v_active1) {
-                                trow[emit_off[4]] = vacc[c][2].x;
-                                trow[emit_off[5]] = vacc[c][2].y;
-                                trow[emit_off[6]] = vacc[c][3].x;
-                                trow[emit_off[7]] = vacc[c][3].y;
+                                trow[emit_off[4]] = vacc[c][2].x; trow[emit_off[5]] = vacc[c][2].y;
+                                trow[emit_off[6]] = vacc[c][3].x; trow[emit_off[7]] = vacc[c][3].y;
                             }
                         }
+                        ++emitted;
                     }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) vacc[c][q] = make_float2(0.0f, 0.0f);
+                    vacc[c][0] = vacc[c][1] = vacc[c][2] = vacc[c][3] = make_float2(0.0f, 0.0f);
                     ++ov;
-                    if (live && --remaining == 0) {
+                    if (emitted == kTmpRows || ov == oy1) {
                         c_start = (c + 1) % KV;
                         goto vertical_done;
                     }
@@ -388,36 +396,33 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             c_start = 0;
         }
     vertical_done:
-        compute_barrier();
+        __syncthreads();  // tmp rows [0, emitted) are complete
 
         // ============================ horizontal phase
+        if (!hw_ready) {  // the strip's horizontal weights were requested at kernel start
+            mbar_wait(hw_bar, 0);
+            hw_ready = true;
+        }
+        uint8_t* const my_dst = dst_base + size_t(g0 + hrow) * dst_pitch;  // this lane's output row
+        const bool row_live = hrow < emitted;
         int n_heads = 0;
-        int head0 = 0;
         if (h_active) {
             float2 hacc[KH][2];
 #pragma unroll
             for (int j = 0; j < KH; ++j) hacc[j][0] = hacc[j][1] = make_float2(0.0f, 0.0f);
             int x = seg_lo;
             const float4* px = my_row + seg_lo;
-            const float4* wh = hring + size_t(seg_lo) * (KSH / 2);
-            float4 nxtp = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 nxth[KSH / 2];
-            if (x < seg_hi) {
-                nxtp = *px;
-#pragma unroll
-                for (int jj = 0; jj < KSH / 2; ++jj) nxth[jj] = __ldg(wh + jj);
-            }
-            auto h_prefetch = [&](float4& p, float4 (&w)[KSH / 2]) {
-                ++x;
-                ++px;
-                wh += KSH / 2;
-                if (x < seg_hi) {
-                    p = *px;
-#pragma unroll
-                    for (int jj = 0; jj < KSH / 2; ++jj) w[jj] = __ldg(wh + jj);
-                }
-            };
-            auto h_accumulate = [&](const float4& p, const float4 (&w)[KSH / 2]) {
+            const float4* wh = hw_smem + size_t(seg_lo - xl) * (KSH / 2);
+            // Start one ring revolution early: outputs before `os` that are still open at seg_lo (only
+            // possible for the strip's first segment) hold their slots until their windows close; they
+            // are walked like any other output but never emitted.  Every segment pre-rolls the same KH
+            // outputs so that all half warps stay on the same unrolled slot.
+            int oh = os - KH;
+            int hc_start = h_slot0;
+            auto window_of = [&](int o) { return (o >= o_lo && o < oe) ? lr_tab[o] : make_int2(0, 0); };
+            int2 lr_next = window_of(oh);
+
+            auto accumulate = [&](const float4& p, const float4* w) {
                 const float2 plo = make_float2(p.x, p.y), phi = make_float2(p.z, p.w);
 #pragma unroll
                 for (int j = 0; j < KH; ++j) {
@@ -427,87 +432,73 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                     hacc[j][1] = __ffma2_rn(wj, phi, hacc[j][1]);
                 }
             };
-            bool seg_done = false;
-            for (int oh0 = o_ring0; oh0 < ox1 && !seg_done; oh0 += KH) {
+            for (;;) {
 #pragma unroll
                 for (int c = 0; c < KH; ++c) {
-                    const int oh = oh0 + c;
-                    if (oh >= ox1) { seg_done = true; break; }
-                    const int r_end = __ldg(hright + oh);
-                    const int xend = min(r_end, seg_hi);
-                    while (x < xend) {
-                        float4 altp;
-                        float4 alth[KSH / 2];
-                        if (x + 1 < xend) {
-                            h_prefetch(altp, alth);
-                            h_accumulate(nxtp, nxth);
-                            h_prefetch(nxtp, nxth);
-                            h_accumulate(altp, alth);
-                        } else {
-                            h_prefetch(altp, alth);
-                            h_accumulate(nxtp, nxth);
-                            nxtp = altp;
+                    if (c >= hc_start) {  // output oh accumulates in slot c
+                        if (oh >= oe) goto horizontal_done;
+                        const int2 lr = lr_next;
+                        lr_next = window_of(oh + 1);
+                        const int xend = lr.y;  // <= seg_hi: every owned window ends inside the segment
+                        while (x + 1 < xend) {  // two pixels per trip: all loads are issued first
+                            const float4 p0 = px[0], p1 = px[1];
+                            float4 w0[KSH / 2], w1[KSH / 2];
 #pragma unroll
-                            for (int jj = 0; jj < KSH / 2; ++jj) nxth[jj] = alth[jj];
+                            for (int jj = 0; jj < KSH / 2; ++jj) { w0[jj] = wh[jj]; w1[jj] = wh[KSH / 2 + jj]; }
+                            accumulate(p0, w0);
+                            accumulate(p1, w1);
+                            x += 2; px += 2; wh += KSH;
                         }
-                    }
-                    if (r_end > seg_hi) { seg_done = true; break; }  // window continues in the next segment
-                    if (r_end > seg_lo && oh >= ox0) {
+                        if (x < xend) {
+                            const float4 p0 = px[0];
+                            float4 w0[KSH / 2];
+#pragma unroll
+                            for (int jj = 0; jj < KSH / 2; ++jj) w0[jj] = wh[jj];
+                            accumulate(p0, w0);
+                            x += 1; px += 1; wh += KSH / 2;
+                        }
                         const float4 v = make_float4(hacc[c][0].x, hacc[c][0].y, hacc[c][1].x, hacc[c][1].y);
-                        if (__ldg(hleft + oh) >= seg_lo) {
-                            store_pixel<C>(my_out, oh - ox0, v);  // complete inside this segment
-                        } else {
-                            // head: the window started in an earlier segment; park the partial sum in a
-                            // tmp column this thread has already consumed
-                            if (n_heads == 0) head0 = oh;
-                            my_row[seg_lo + n_heads] = v;
-                            ++n_heads;
+                        if (oh >= os) {
+                            if (lr.x >= seg_lo) {  // the whole window lies in this segment: finished pixel
+                                if (row_live) store_pixel<C>(my_dst + size_t(oh) * C, word_ok, v);
+                            } else {               // head: the window started in an earlier segment; park the
+                                my_row[seg_lo + n_heads] = v;  // partial sum in a tmp column already consumed
+                                ++n_heads;
+                            }
                         }
+                        hacc[c][0] = hacc[c][1] = make_float2(0.0f, 0.0f);
+                        ++oh;
                     }
-                    hacc[c][0] = hacc[c][1] = make_float2(0.0f, 0.0f);
                 }
+                hc_start = 0;
             }
+        horizontal_done:
             // tails: partial sums of the windows still open at seg_hi (slot = output index mod KH)
-            if (sidx + 1 < n_seg) {
+            if (has_next_seg) {
 #pragma unroll
                 for (int j = 0; j < KH; ++j)
                     my_row[seg_lo + KH + j] = make_float4(hacc[j][0].x, hacc[j][0].y, hacc[j][1].x, hacc[j][1].y);
             }
         }
-        compute_barrier();
-
-        // ============================ fix-up: heads + tails of earlier segments -> finished outputs
+        __syncthreads();
+        // fix-up: heads (the first n_heads outputs of the segment) + tails of earlier segments
         for (int i = 0; i < n_heads; ++i) {
-            const int oh = head0 + i;
+            const int oh = os + i;
             float4 v = my_row[seg_lo + i];
-            const int first = __ldg(hleft + oh);
+            const int first = lr_tab[oh].x;
             const int slot = oh % KH;
             for (int sg = sidx - 1; sg >= 0; --sg) {
-                const int sg_lo = xl + sg * seg_len;
-                if (sg_lo + seg_len <= first) break;  // the window starts after that segment
+                const int sg_hi = lr_tab[ox0 + (sg + 1) * per - 1].y;
+                if (sg_hi <= first) break;  // the window starts after that segment
+                const int sg_lo = (sg == 0) ? xl : lr_tab[ox0 + sg * per - 1].y;
                 const float4 t = my_row[sg_lo + KH + slot];
                 v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
             }
-            store_pixel<C>(my_out, oh - ox0, v);
+            if (row_live) store_pixel<C>(my_dst + size_t(oh) * C, word_ok, v);
         }
-        compute_barrier();
-
-        // ============================ store the finished rows (coalesced, any alignment)
-        for (int row = warp; row < n_rows; row += kComputeWarps) {
-            const uint32_t* srow = out_stage + size_t(row) * geom.out_pitch_w;
-            const uint8_t* sbytes = reinterpret_cast<const uint8_t*>(srow);
-            uint8_t* g = J->dst + size_t(g0 + row) * J->dst_pitch + size_t(ox0) * C;
-            const int head = min(out_bytes, int((4 - (reinterpret_cast<uintptr_t>(g) & 3)) & 3));
-            const int nwords = (out_bytes - head) >> 2;
-            if (lane < head) g[lane] = sbytes[lane];
-            uint32_t* gw = reinterpret_cast<uint32_t*>(g + head);
-            const int sh8 = head * 8;
-            for (int k = lane; k < nwords; k += 32) gw[k] = __funnelshift_r(srow[k], srow[k + 1], sh8);
-            const int done = head + nwords * 4;
-            if (lane < out_bytes - done) g[done + lane] = sbytes[done + lane];
-        }
-        // No barrier needed here: the next vertical phase only writes tmp (all reads of tmp finished
-        // before the barrier above) and ends in a barrier before out_stage is written again.
+        __syncthreads();  // tmp (incl. parked partial sums) is free for the next vertical rows
+        g0 += emitted;
+        emitted = 0;
     }
 }
 
@@ -522,9 +513,11 @@ static int ring_rows_for(int channels) {
     }
 }
 
-size_t fused_smem_bytes(int channels, const FusedGeom& g) {
-    return size_t(kHeaderBytes) + size_t(ring_rows_for(channels)) * kSrcRowBytes +
-           size_t(kTmpRows) * g.tmp_px * sizeof(float4) + size_t(kTmpRows) * g.out_pitch_w * 4;
+size_t fused_smem_bytes(int channels, int kv, int kh, const FusedGeom& g) {
+    const size_t ksv = size_t((kv + 1) & ~1), ksh = size_t((kh + 1) & ~1);
+    const size_t ring = size_t(ring_rows_for(channels));
+    return size_t(kHeaderBytes) + ring * kSrcRowBytes + ring * ksv * 8 + size_t(g.tmp_px) * ksh * 8 +
+           size_t(kMaxStripOut) * sizeof(int2) + size_t(kTmpRows) * g.tmp_px * sizeof(float4);
 }
 
 int fused_max_src_bytes(int channels) {
@@ -547,7 +540,7 @@ bool fused_supported(int channels, int kv, int kh) {
 template <int C, int KV, int KH>
 static cudaError_t launch_one(const DevJob* jobs, const WorkItem* items, const FusedGeom& geom,
                               cudaStream_t stream) {
-    const size_t smem = fused_smem_bytes(C, geom);
+    const size_t smem = fused_smem_bytes(C, KV, KH, geom);
     // Opt in to > 48 KB dynamic shared memory (per device; cheap, so done on every launch).
     cudaError_t e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          int(smem));

@@ -16,7 +16,7 @@ bool fused_supported(int channels, int ring_k_v, int ring_k_h);
 int fused_max_src_bytes(int channels);   // source bytes of one strip row the kernel can stage
 int fused_group_rows();                  // intermediate rows per group
 int fused_max_segments();                // x segments of a strip in the horizontal phase
-size_t fused_smem_bytes(int channels, const FusedGeom& geom);
+size_t fused_smem_bytes(int channels, int ring_k_v, int ring_k_h, const FusedGeom& geom);
 cudaError_t launch_fused(int channels, int ring_k_v, int ring_k_h, const DevJob* jobs, const WorkItem* items,
                          const FusedGeom& geom, cudaStream_t stream);
 

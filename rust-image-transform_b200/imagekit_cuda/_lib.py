@@ -17,6 +17,7 @@ STATUS_NAMES = ["ok", "invalid-arg", "unsupported-layout", "too-large", "cuda-er
 FILTER_NEAREST, FILTER_TRIANGLE, FILTER_CATMULLROM, FILTER_GAUSSIAN, FILTER_LANCZOS3 = range(5)
 MODE_FAST, MODE_EXACT = 0, 1
 DIMS_RESAMPLE, DIMS_PASSTHROUGH, DIMS_CLONE, DIMS_COPY = range(4)
+MAX_DIM, MAX_PIXELS = 65535, 1 << 28  # IKC_MAX_DIM, IKC_MAX_PIXELS
 
 # every symbol include/imagekit_cuda.h declares
 EXPORTS = [

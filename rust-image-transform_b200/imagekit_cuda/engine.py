@@ -125,6 +125,9 @@ class Context:
         if not (s.strides[2] == s.itemsize and s.strides[1] == s.itemsize * s.shape[2]):
             s = np.ascontiguousarray(s)
         sh, sw, ch = s.shape
+        if out is None and (dw > _lib.MAX_DIM or dh > _lib.MAX_DIM or dw * dh > _lib.MAX_PIXELS):
+            # same bound the library enforces (IKC_ERR_TOO_LARGE); checked here before allocating the result
+            raise ImageKitError(_lib.ERR_TOO_LARGE, "requested size exceeds IKC_MAX_DIM / IKC_MAX_PIXELS")
         dst = out if out is not None else np.empty((dh, dw, ch), s.dtype)
         d3 = dst[:, :, None] if dst.ndim == 2 else dst
         assert d3.shape == (dh, dw, ch) and d3.dtype == s.dtype
