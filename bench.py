@@ -260,13 +260,11 @@ def main():
                 prepared.launch(stream.cuda_stream)
                 stream.synchronize()
     barrier()
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t.item())
-    ms_per_step = ms_total_max / args.steps
+    from imagekit_cuda.sharding import aggregate_throughput
     out_mp_step = batch * dw * dh / 1e6
-    value = world * out_mp_step / (ms_per_step * 1e-3)
+    # units all ranks processed / max-over-ranks device time
+    total_mp, ms_total_max, value = aggregate_throughput(out_mp_step * args.steps, ms_total, dist, dev)
+    ms_per_step = ms_total_max / args.steps
 
     algo_bytes = batch * (sw * sh * ch + dw * dh * ch)
     kernel_ms = (ms_total / args.steps) / max(1, launches_per_step)  # this rank's average launch duration
@@ -292,10 +290,7 @@ def main():
         ctx.resize_batch(srcs, sizes, filt, outs=outs)   # synchronous: returns with results in host memory
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * eb * e2e_steps * dw * dh / 1e6 / float(te.item())
+    _, _, e2e_value = aggregate_throughput(eb * e2e_steps * dw * dh / 1e6, e2e_s * 1e3, dist, dev)
 
     if rank != 0:
         if dist is not None:

@@ -1,0 +1,96 @@
+//! imagekit-cuda: `resize_image` with the reference's exact signature
+//! (imagekit src/transform.rs:62-66), executed on B200 GPUs through libimagekit_cuda.so.
+//!
+//! Drop-in: in imagekit's src/transform.rs replace the body of `resize_image` with
+//! `imagekit_cuda::resize_image(img, w, h).map_err(ImageKitError::TransformError)`; the handlers
+//! (src/lib.rs:180, :286), DiskCache and the signing path are untouched.
+pub mod ffi;
+
+use image::{DynamicImage, GenericImageView, ImageBuffer};
+use std::ffi::CStr;
+use std::sync::OnceLock;
+
+struct Ctx(*mut ffi::ikc_ctx);
+unsafe impl Send for Ctx {} // the C ABI is thread-safe and re-entrant
+unsafe impl Sync for Ctx {}
+
+static CTX: OnceLock<Result<Ctx, String>> = OnceLock::new();
+
+fn last_error() -> String {
+    unsafe { CStr::from_ptr(ffi::ikc_last_error()).to_string_lossy().into_owned() }
+}
+
+fn ctx() -> Result<*mut ffi::ikc_ctx, String> {
+    CTX.get_or_init(|| {
+        let mut p = std::ptr::null_mut();
+        // all visible devices; single-image calls are spread round-robin, batches are sharded
+        let rc = unsafe { ffi::ikc_create(std::ptr::null(), 0, &mut p) };
+        if rc == ffi::IKC_OK { Ok(Ctx(p)) } else { Err(last_error()) }
+    })
+    .as_ref()
+    .map(|c| c.0)
+    .map_err(|e| e.clone())
+}
+
+fn resize_u8(raw: &[u8], sw: u32, sh: u32, ch: u32, dw: u32, dh: u32) -> Result<Vec<u8>, String> {
+    let mut out = vec![0u8; dw as usize * dh as usize * ch as usize];
+    let rc = unsafe {
+        ffi::ikc_resize_u8(ctx()?, raw.as_ptr(), sw, sh, (sw * ch) as usize, ch as i32, out.as_mut_ptr(), dw, dh,
+                           (dw * ch) as usize, ffi::IKC_FILTER_LANCZOS3)
+    };
+    if rc == ffi::IKC_OK { Ok(out) } else { Err(last_error()) }
+}
+
+fn resize_u16(raw: &[u16], sw: u32, sh: u32, ch: u32, dw: u32, dh: u32) -> Result<Vec<u16>, String> {
+    let mut out = vec![0u16; dw as usize * dh as usize * ch as usize];
+    let rc = unsafe {
+        ffi::ikc_resize_u16(ctx()?, raw.as_ptr(), sw, sh, (sw * ch * 2) as usize, ch as i32, out.as_mut_ptr(), dw, dh,
+                            (dw * ch * 2) as usize, ffi::IKC_FILTER_LANCZOS3)
+    };
+    if rc == ffi::IKC_OK { Ok(out) } else { Err(last_error()) }
+}
+
+/// Same contract as imagekit's `resize_image` (src/transform.rs:62-90): `(None, None)` returns the
+/// image untouched; otherwise the target size follows the reference's f32 rule, is fitted within
+/// (aspect preserved, `DynamicImage::resize`) and the raster is resampled with Lanczos3.
+/// The error string becomes `ImageKitError::TransformError` at the call site.
+pub fn resize_image(img: DynamicImage, w: Option<u32>, h: Option<u32>) -> Result<DynamicImage, String> {
+    if w.is_none() && h.is_none() {
+        return Ok(img);
+    }
+    let (ow, oh) = img.dimensions();
+    let (mut tw, mut th) = (0u32, 0u32);
+    let code = unsafe {
+        ffi::ikc_target_dims(ow, oh, w.is_some() as i32, w.unwrap_or(0), h.is_some() as i32, h.unwrap_or(0), &mut tw, &mut th)
+    };
+    if code < 0 {
+        return Err(last_error());
+    }
+    if code != ffi::IKC_DIMS_RESAMPLE {
+        return Ok(img); // clone / copy cases: pixels unchanged
+    }
+    macro_rules! run8 {
+        ($buf:expr, $ch:expr, $variant:path) => {{
+            let v = resize_u8($buf.as_raw(), ow, oh, $ch, tw, th)?;
+            Ok($variant(ImageBuffer::from_raw(tw, th, v).expect("size matches")))
+        }};
+    }
+    macro_rules! run16 {
+        ($buf:expr, $ch:expr, $variant:path) => {{
+            let v = resize_u16($buf.as_raw(), ow, oh, $ch, tw, th)?;
+            Ok($variant(ImageBuffer::from_raw(tw, th, v).expect("size matches")))
+        }};
+    }
+    match &img {
+        DynamicImage::ImageLuma8(b) => run8!(b, 1, DynamicImage::ImageLuma8),
+        DynamicImage::ImageLumaA8(b) => run8!(b, 2, DynamicImage::ImageLumaA8),
+        DynamicImage::ImageRgb8(b) => run8!(b, 3, DynamicImage::ImageRgb8),
+        DynamicImage::ImageRgba8(b) => run8!(b, 4, DynamicImage::ImageRgba8),
+        DynamicImage::ImageLuma16(b) => run16!(b, 1, DynamicImage::ImageLuma16),
+        DynamicImage::ImageLumaA16(b) => run16!(b, 2, DynamicImage::ImageLumaA16),
+        DynamicImage::ImageRgb16(b) => run16!(b, 3, DynamicImage::ImageRgb16),
+        DynamicImage::ImageRgba16(b) => run16!(b, 4, DynamicImage::ImageRgba16),
+        // 32F variants never come out of the reference's decoders (jpeg/png/webp); no CPU fallback.
+        _ => Err("unsupported pixel format (f32 rasters)".to_string()),
+    }
+}
