@@ -40,7 +40,7 @@ struct Layout;
 template <>
 struct Layout<4> {
     static constexpr int kMaxSrcBytes = 1024;
-    static constexpr int kRingRows = 24;
+    static constexpr int kRingRows = 16;
 };
 template <>
 struct Layout<3> {
@@ -50,12 +50,12 @@ struct Layout<3> {
 template <>
 struct Layout<2> {
     static constexpr int kMaxSrcBytes = 512;
-    static constexpr int kRingRows = 24;
+    static constexpr int kRingRows = 16;
 };
 template <>
 struct Layout<1> {
     static constexpr int kMaxSrcBytes = 256;
-    static constexpr int kRingRows = 24;
+    static constexpr int kRingRows = 16;
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
@@ -156,11 +156,11 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     constexpr int KSH = (KH + 1) & ~1;
     constexpr int kRingRows = Layout<C>::kRingRows;
     constexpr int kStages = kRingRows / kStageRows;
-    static_assert(kStages <= kMaxStages && kRingRows % kStageRows == 0, "ring geometry");
+    static_assert(kStages == kComputeWarps && kStageRows == 4 && kRingRows == 16, "ring geometry: one stage per warp");
 
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
-    int* rel_count = reinterpret_cast<int*>(full_bar + kMaxStages);  // warps done with each stage
-    uint64_t* hw_bar = full_bar + kMaxStages + kMaxStages / 2;       // after full_bar[8], rel_count[8]
+    uint64_t* empty_bar = full_bar + kMaxStages;   // one arrival per warp that has drained the stage
+    uint64_t* hw_bar = empty_bar + kMaxStages;
     uint8_t* src_ring = smem + kHeaderBytes;
     float4* vw_ring = reinterpret_cast<float4*>(src_ring + kRingRows * kSrcRowBytes);  // [row][KSV/2]
     float4* hw_smem = vw_ring + kRingRows * (KSV / 2);                                 // [px][KSH/2]
@@ -212,7 +212,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_bar + s, 1);
-            rel_count[s] = 0;
+            mbar_init(empty_bar + s, kComputeWarps);
         }
         mbar_init(hw_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -300,24 +300,17 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     while (yend_next <= y_first) yend_next = v_end_of(++ov);
     int c_start = ov % KV;  // slot of output ov is ov mod KV; the unrolled slot loop is entered here
 
-    int y = y_first;        // next source row to consume
-    int ready = y_first;    // rows below `ready` have landed in the ring
-    int fill_stage = 0;     // next stage to wait for
-    uint32_t fill_phase = 0;
-    int rel_stage = 0;      // stage being drained
-    int rel_base = 0;       // chunk-relative index of the first row held by that stage
-    int rows_in_stage = 0;  // rows consumed from the stage being drained
-    int ring_row = 0;       // ring row of source row y
+    // All ring bookkeeping derives from r = rows of the chunk consumed so far: ring row r % 16, stage
+    // (r / 4) % 4, fill parity (r / 16) & 1.
+    uint32_t r = 0;
     int g0 = oy0;           // first output row of the group being assembled in tmp
     int emitted = 0;        // rows of that group already in tmp
 
     // One source row into every open ring slot.
     auto consume_row = [&]() {
-        if (y == ready) {  // the next ring stage must have landed
-            mbar_wait(full_bar + fill_stage, fill_phase);
-            if (++fill_stage == kStages) { fill_stage = 0; fill_phase ^= 1; }
-            ready = min(ready + kStageRows, y_last);
-        }
+        const uint32_t stage = (r / kStageRows) % kStages;
+        if (r % kStageRows == 0) mbar_wait(full_bar + stage, (r / kRingRows) & 1);  // the stage has landed
+        const uint32_t ring_row = r % kRingRows;
         const uint32_t d0 = *reinterpret_cast<const uint32_t*>(my_src + ring_row * kSrcRowBytes);
         const uint32_t d1 = *reinterpret_cast<const uint32_t*>(my_src + ring_row * kSrcRowBytes + kHalfRowBytes);
         float4 w[KSV / 2];
@@ -336,23 +329,24 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             vacc[j][2] = __ffma2_rn(wj, s2, vacc[j][2]);
             vacc[j][3] = __ffma2_rn(wj, s3, vacc[j][3]);
         }
-        ++y;
-        ring_row = (ring_row + 1 == kRingRows) ? 0 : ring_row + 1;
-        if (++rows_in_stage == kStageRows) {
-            // This warp is done with the stage; the last of the 4 warps refills it with the rows one
-            // ring revolution further down (TMA bulk copies).  Every lane's loads of the stage have
-            // returned (their values were consumed above), so the count alone orders the refill.
-            rows_in_stage = 0;
+        if (r % kStageRows == kStageRows - 1) {
+            // This warp has drained `stage` (all its loads have returned: their values were consumed
+            // above).  Warp w refills stage w, one stage late: by then the other warps have drained it
+            // too, so the wait below normally falls through and nobody stalls on the slowest warp.
             __syncwarp();
             if (lane == 0) {
-                if (smem_atomic_inc(rel_count + rel_stage) == kComputeWarps - 1) {
-                    rel_count[rel_stage] = 0;
-                    if (rel_base + kRingRows < nrows) issue_fill(rel_stage, rel_base + kRingRows);
+                mbar_arrive(empty_bar + stage);
+                const uint32_t prev = (stage + kStages - 1) % kStages;
+                if (uint32_t(warp) == prev && r >= 2 * kStageRows - 1) {
+                    const uint32_t prev_r0 = r - (2 * kStageRows - 1);   // first row the previous stage held
+                    if (prev_r0 + kRingRows < uint32_t(nrows)) {
+                        mbar_wait(empty_bar + prev, (prev_r0 / kRingRows) & 1);
+                        issue_fill(int(prev), int(prev_r0 + kRingRows));
+                    }
                 }
             }
-            rel_base += kStageRows;
-            if (++rel_stage == kStages) rel_stage = 0;
         }
+        ++r;
     };
 
     while (ov < oy1) {
@@ -361,9 +355,9 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
 #pragma unroll
             for (int c = 0; c < KV; ++c) {
                 if (c >= c_start) {  // output ov accumulates in slot c
-                    const int yend = yend_next;
+                    const uint32_t rend = uint32_t(yend_next - y_first);  // rows of the chunk output ov needs
                     yend_next = (ov + 1 < oy1) ? v_end_of(ov + 1) : 0x7fffffff;
-                    while (y < yend) consume_row();
+                    while (r < rend) consume_row();
                     if (ov >= oy0) {
                         float* trow = reinterpret_cast<float*>(tmp + size_t(emitted) * geom.tmp_px);
                         if (C == 4) {
