@@ -306,16 +306,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     int g0 = oy0;           // first output row of the group being assembled in tmp
     int emitted = 0;        // rows of that group already in tmp
 
-    // One source row into every open ring slot.
-    auto consume_row = [&]() {
-        const uint32_t stage = (r / kStageRows) % kStages;
-        if (r % kStageRows == 0) mbar_wait(full_bar + stage, (r / kRingRows) & 1);  // the stage has landed
-        const uint32_t ring_row = r % kRingRows;
-        const uint32_t d0 = *reinterpret_cast<const uint32_t*>(my_src + ring_row * kSrcRowBytes);
-        const uint32_t d1 = *reinterpret_cast<const uint32_t*>(my_src + ring_row * kSrcRowBytes + kHalfRowBytes);
-        float4 w[KSV / 2];
-#pragma unroll
-        for (int jj = 0; jj < KSV / 2; ++jj) w[jj] = vw_ring[ring_row * (KSV / 2) + jj];
+    auto fma_row = [&](uint32_t d0, uint32_t d1, const float4 (&w)[KSV / 2]) {
         const float2 s0 = make_float2(byte_to_float<0>(d0), byte_to_float<1>(d0));
         const float2 s1 = make_float2(byte_to_float<2>(d0), byte_to_float<3>(d0));
         const float2 s2 = make_float2(byte_to_float<0>(d1), byte_to_float<1>(d1));
@@ -329,24 +320,57 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             vacc[j][2] = __ffma2_rn(wj, s2, vacc[j][2]);
             vacc[j][3] = __ffma2_rn(wj, s3, vacc[j][3]);
         }
-        if (r % kStageRows == kStageRows - 1) {
-            // This warp has drained `stage` (all its loads have returned: their values were consumed
-            // above).  Warp w refills stage w, one stage late: by then the other warps have drained it
-            // too, so the wait below normally falls through and nobody stalls on the slowest warp.
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(empty_bar + stage);
-                const uint32_t prev = (stage + kStages - 1) % kStages;
-                if (uint32_t(warp) == prev && r >= 2 * kStageRows - 1) {
-                    const uint32_t prev_r0 = r - (2 * kStageRows - 1);   // first row the previous stage held
-                    if (prev_r0 + kRingRows < uint32_t(nrows)) {
-                        mbar_wait(empty_bar + prev, (prev_r0 / kRingRows) & 1);
-                        issue_fill(int(prev), int(prev_r0 + kRingRows));
-                    }
+    };
+    // Called after the row that closes a stage: this warp has drained `stage` (all its loads have
+    // returned: their values were consumed).  Warp w refills stage w, one stage late: by then the other
+    // warps have drained it too, so the wait normally falls through and nobody stalls on the slowest warp.
+    auto stage_drained = [&](uint32_t stage, uint32_t r_last) {
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(empty_bar + stage);
+            const uint32_t prev = (stage + kStages - 1) % kStages;
+            if (uint32_t(warp) == prev && r_last >= 2 * kStageRows - 1) {
+                const uint32_t prev_r0 = r_last - (2 * kStageRows - 1);  // first row the previous stage held
+                if (prev_r0 + kRingRows < uint32_t(nrows)) {
+                    mbar_wait(empty_bar + prev, (prev_r0 / kRingRows) & 1);
+                    issue_fill(int(prev), int(prev_r0 + kRingRows));
                 }
             }
         }
-        ++r;
+    };
+    // Source rows [r, rend) of the chunk into every open ring slot; two rows per trip when both lie in
+    // the same ring stage (all loads first, then both rows' conversions and FMAs), otherwise one.
+    auto consume_rows = [&](uint32_t rend) {
+        while (r < rend) {
+            const uint32_t stage = (r / kStageRows) % kStages;
+            const uint32_t in_stage = r % kStageRows;
+            if (in_stage == 0) mbar_wait(full_bar + stage, (r / kRingRows) & 1);  // the stage has landed
+            const uint32_t ring_row = r % kRingRows;
+            const uint8_t* src = my_src + ring_row * kSrcRowBytes;
+            const float4* wrow = vw_ring + ring_row * (KSV / 2);
+            if (r + 1 < rend && in_stage != kStageRows - 1) {
+                const uint32_t a0 = *reinterpret_cast<const uint32_t*>(src);
+                const uint32_t a1 = *reinterpret_cast<const uint32_t*>(src + kHalfRowBytes);
+                const uint32_t c0 = *reinterpret_cast<const uint32_t*>(src + kSrcRowBytes);
+                const uint32_t c1 = *reinterpret_cast<const uint32_t*>(src + kSrcRowBytes + kHalfRowBytes);
+                float4 wa[KSV / 2], wc[KSV / 2];
+#pragma unroll
+                for (int jj = 0; jj < KSV / 2; ++jj) { wa[jj] = wrow[jj]; wc[jj] = wrow[KSV / 2 + jj]; }
+                fma_row(a0, a1, wa);
+                fma_row(c0, c1, wc);
+                if (in_stage == kStageRows - 2) stage_drained(stage, r + 1);
+                r += 2;
+            } else {
+                const uint32_t a0 = *reinterpret_cast<const uint32_t*>(src);
+                const uint32_t a1 = *reinterpret_cast<const uint32_t*>(src + kHalfRowBytes);
+                float4 wa[KSV / 2];
+#pragma unroll
+                for (int jj = 0; jj < KSV / 2; ++jj) wa[jj] = wrow[jj];
+                fma_row(a0, a1, wa);
+                if (in_stage == kStageRows - 1) stage_drained(stage, r);
+                r += 1;
+            }
+        }
     };
 
     while (ov < oy1) {
@@ -357,7 +381,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                 if (c >= c_start) {  // output ov accumulates in slot c
                     const uint32_t rend = uint32_t(yend_next - y_first);  // rows of the chunk output ov needs
                     yend_next = (ov + 1 < oy1) ? v_end_of(ov + 1) : 0x7fffffff;
-                    while (r < rend) consume_row();
+                    consume_rows(rend);
                     if (ov >= oy0) {
                         float* trow = reinterpret_cast<float*>(tmp + size_t(emitted) * geom.tmp_px);
                         if (C == 4) {
