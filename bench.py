@@ -323,7 +323,7 @@ def main():
                    "timing": "CUDA events on the launch stream, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": recorded_traffic(args.workload, batch), "peak_source": peak_src,
-                     "kernel": "fused_ring_kernel" if launches_per_step == 1 else "generic two-launch path",
+                     "kernel": prepared.describe(),
                      "algorithmic_bytes_per_launch": algo_bytes // max(1, launches_per_step),
                      "kernel_ms": kernel_ms},
         "cpu_baseline": cpu,

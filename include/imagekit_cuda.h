@@ -190,6 +190,8 @@ IKC_API int ikc_batch_prepare(ikc_ctx* ctx, int device_index, ikc_job* jobs, siz
 IKC_API int ikc_batch_launch(ikc_batch* b, void* stream);
 /* Kernel launches one ikc_batch_launch issues. */
 IKC_API int ikc_batch_launch_count(const ikc_batch* b);
+/* Human-readable list of the kernels (and CTA counts) one ikc_batch_launch issues. */
+IKC_API int ikc_batch_describe(const ikc_batch* b, char* out, size_t cap);
 IKC_API void ikc_batch_free(ikc_batch* b);
 
 #ifdef __cplusplus

@@ -1,5 +1,7 @@
 // api.cpp -- the extern "C" boundary declared in include/imagekit_cuda.h.  Nothing throws across it.
+#include <cstdio>
 #include <cstring>
+#include <string>
 #include <new>
 #include <vector>
 
@@ -287,6 +289,23 @@ int ikc_batch_launch(ikc_batch* b, void* stream) {
 }
 
 int ikc_batch_launch_count(const ikc_batch* b) { return b ? b->impl.lp.launches() : 0; }
+
+int ikc_batch_describe(const ikc_batch* b, char* out, size_t cap) {
+    if (!b || !out || cap == 0) return IKC_ERR_INVALID_ARG;
+    std::string s;
+    for (auto& g : b->impl.lp.groups) {
+        if (!s.empty()) s += "; ";
+        if (g.kv == 0) s += "tile_kernel";
+        else s += "fused_ring_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.kv) + "," + std::to_string(g.kh) + ">";
+        s += " x " + std::to_string(g.items.size()) + " CTAs";
+    }
+    if (!b->impl.lp.generic_jobs.empty()) {
+        if (!s.empty()) s += "; ";
+        s += "vertical_generic+horizontal_generic x " + std::to_string(b->impl.lp.generic_jobs.size()) + " jobs";
+    }
+    std::snprintf(out, cap, "%s", s.c_str());
+    return IKC_OK;
+}
 
 void ikc_batch_free(ikc_batch* b) {
     if (!b) return;

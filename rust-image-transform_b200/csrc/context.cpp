@@ -250,6 +250,57 @@ bool cut_strips(const PassPlan& h, int ch, int sw, int max_src, int max_out, std
     return true;
 }
 
+
+// Cut a job into output tiles for the tile kernel and grow `geom` to cover their source footprints.
+// Returns false (and leaves the outputs untouched) when no tile shape fits the shared-memory budget.
+bool plan_tiles(const PassPlan& v, const PassPlan& h, int ch, int job, std::vector<WorkItem>* items, TileGeom* geom) {
+    const int dw = int(h.n_out), dh = int(v.n_out);
+    auto footprint = [](const PassPlan& p, int n_out, int t) {  // widest source span of any tile of t outputs
+        int worst = 0;
+        for (int a = 0; a < n_out; a += t) {
+            const int b = std::min(n_out, a + t);
+            worst = std::max(worst, p.right[b - 1] - p.left[a]);
+        }
+        return worst;
+    };
+    const int ths[] = {32, 16, 8, 4, 2, 1}, tws[] = {64, 32, 16, 8};
+    int best_tw = 0, best_th = 0, best_rows = 0, best_pitch = 0;
+    for (size_t limit : {size_t(40) << 10, size_t(110) << 10}) {
+        for (int t_h : ths) {
+            for (int t_w : tws) {
+                const int rows = footprint(v, dh, t_h);
+                const int pitch = (footprint(h, dw, t_w) * ch + 3) & ~3;
+                TileGeom probe{};
+                probe.pitch_f = pitch; probe.max_src_rows = rows; probe.max_tile_rows = t_h; probe.max_tile_cols = t_w;
+                probe.vstride = int(v.stride); probe.hstride = int(h.stride);
+                probe.out_pitch_b = ((t_w * ch + 3) & ~3) + 4;
+                const size_t smem = tile_smem_bytes(probe);
+                if (smem <= limit) { best_tw = t_w; best_th = t_h; best_rows = rows; best_pitch = pitch; break; }
+            }
+            if (best_tw) break;
+        }
+        if (best_tw) break;
+    }
+    if (!best_tw) return false;
+    // the launch uses one geometry for every tile of every job: check the merged one still fits
+    TileGeom merged = *geom;
+    merged.pitch_f = std::max(merged.pitch_f, best_pitch);
+    merged.max_src_rows = std::max(merged.max_src_rows, best_rows);
+    merged.max_tile_rows = std::max(merged.max_tile_rows, best_th);
+    merged.max_tile_cols = std::max(merged.max_tile_cols, best_tw);
+    // one launch shares one geometry: jobs whose weight-table strides differ go to another path
+    if (geom->pitch_f != 0 && (geom->vstride != int(v.stride) || geom->hstride != int(h.stride))) return false;
+    merged.vstride = int(v.stride);
+    merged.hstride = int(h.stride);
+    merged.out_pitch_b = std::max(merged.out_pitch_b, ((best_tw * ch + 3) & ~3) + 4);
+    if (tile_smem_bytes(merged) > (size_t(110) << 10)) return false;
+    *geom = merged;
+    for (int oy = 0; oy < dh; oy += best_th)
+        for (int ox = 0; ox < dw; ox += best_tw)
+            items->push_back(WorkItem{job, ox, std::min(dw, ox + best_tw), oy, std::min(dh, oy + best_th)});
+    return true;
+}
+
 }  // namespace
 
 LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* status, bool exact) {
@@ -260,6 +311,8 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         int ch, kv, kh;
     };
     std::vector<Cand> cands;
+    std::vector<WorkItem> tile_items;
+    TileGeom tile_geom{};
     lp.jobs.reserve(n);
     for (size_t i = 0; i < n; ++i) {
         status[i] = kOk;
@@ -296,7 +349,9 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
                                    &c.strips);
             }
             if (fused) cands.push_back(std::move(c));
-            else {
+            else if (!exact && d.bps == 1 && plan_tiles(*tv->host, *th->host, d.channels, idx, &tile_items, &tile_geom)) {
+                // taken by the tile kernel
+            } else {
                 lp.generic_jobs.push_back(idx);
                 lp.scratch_floats = std::max(lp.scratch_floats, size_t(d.sw) * d.channels * d.dh);
             }
@@ -304,6 +359,11 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
             status[i] = e.status;
             set_last_error(e.what);
         }
+    }
+    if (!tile_items.empty()) {
+        FusedGroup g{0, 0, 0, std::move(tile_items), {}, tile_geom};
+        g.tgeom.n_items = int(g.items.size());
+        lp.groups.push_back(std::move(g));
     }
     if (cands.empty()) return lp;
 
@@ -335,7 +395,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         for (auto& gg : lp.groups)
             if (gg.channels == c.ch && gg.kv == c.kv && gg.kh == c.kh) g = &gg;
         if (!g) {
-            lp.groups.push_back(FusedGroup{c.ch, c.kv, c.kh, {}, {}});
+            lp.groups.push_back(FusedGroup{c.ch, c.kv, c.kh, {}, {}, {}});
             g = &lp.groups.back();
         }
         const PassPlan& hp = *lp.keepalive[size_t(c.job) * 2 + 1]->host;
@@ -355,6 +415,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         }
     }
     for (auto& g : lp.groups) {
+        if (g.kv == 0) continue;   // tile-kernel launch: geometry already final
         g.geom.tmp_px |= 1;        // odd pixel pitch: conflict-free float4 column walks
         g.geom.n_items = int(g.items.size());
         if (fused_smem_bytes(g.channels, g.kv, g.kh, g.geom) > 113 * 1024)
@@ -385,7 +446,8 @@ void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, 
     size_t off = (sizeof(DevJob) * lp.jobs.size() + 15) & ~size_t(15);
     for (auto& g : lp.groups) {
         const WorkItem* d_items = reinterpret_cast<const WorkItem*>(d_desc_base + off);
-        check_cuda(launch_fused(g.channels, g.kv, g.kh, d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");
+        if (g.kv == 0) check_cuda(launch_tile(d_jobs, d_items, g.tgeom, stream), "launch tile_kernel");
+        else check_cuda(launch_fused(g.channels, g.kv, g.kh, d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");
         off += (sizeof(WorkItem) * g.items.size() + 15) & ~size_t(15);
         launches.fetch_add(1, std::memory_order_relaxed);
     }

@@ -51,10 +51,11 @@ struct DevTables {
     ~DevTables();
 };
 
-struct FusedGroup {
-    int channels, kv, kh;
+struct FusedGroup {  // one kernel launch over a list of work items
+    int channels, kv, kh;  // ring kernel variant; kv == 0 marks a tile-kernel launch
     std::vector<WorkItem> items;
     FusedGeom geom{};
+    TileGeom tgeom{};
 };
 
 // Everything needed to enqueue a set of device-resident jobs.

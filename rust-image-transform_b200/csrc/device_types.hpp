@@ -43,4 +43,16 @@ struct FusedGeom {
     int32_t n_items;
 };
 
+// Launch-wide shared-memory geometry of the tile kernel (max over the batch's tiles).
+struct TileGeom {
+    int32_t pitch_f;        // floats per staged row: footprint columns * channels, rounded up to 4
+    int32_t max_src_rows;   // source rows of the largest tile footprint
+    int32_t max_tile_rows;  // output rows of the tallest tile
+    int32_t max_tile_cols;  // output columns of the widest tile
+    int32_t vstride;        // taps per output row in the staged vertical weights
+    int32_t hstride;        // taps per output column in the staged horizontal weights
+    int32_t out_pitch_b;    // bytes per row of the staged output tile (multiple of 4, + one spare word)
+    int32_t n_items;
+};
+
 }  // namespace ikc

@@ -20,4 +20,8 @@ size_t fused_smem_bytes(int channels, int ring_k_v, int ring_k_h, const FusedGeo
 cudaError_t launch_fused(int channels, int ring_k_v, int ring_k_h, const DevJob* jobs, const WorkItem* items,
                          const FusedGeom& geom, cudaStream_t stream);
 
+// Tile kernel (tile.cu): output-stationary fused passes over shared-memory tiles.
+size_t tile_smem_bytes(const TileGeom& geom);
+cudaError_t launch_tile(const DevJob* jobs, const WorkItem* items, const TileGeom& geom, cudaStream_t stream);
+
 }  // namespace ikc

@@ -24,7 +24,7 @@ EXPORTS = [
     "ikc_create", "ikc_destroy", "ikc_device_count", "ikc_set_mode", "ikc_get_mode", "ikc_kernel_launches",
     "ikc_last_error", "ikc_version", "ikc_target_dims", "ikc_pass_table", "ikc_resize_u8", "ikc_resize_u16",
     "ikc_resize_image_u8", "ikc_resize_batch", "ikc_host_alloc", "ikc_host_free", "ikc_resize_u8_device",
-    "ikc_batch_prepare", "ikc_batch_launch", "ikc_batch_launch_count", "ikc_batch_free",
+    "ikc_batch_prepare", "ikc_batch_launch", "ikc_batch_launch_count", "ikc_batch_describe", "ikc_batch_free",
 ]
 
 
@@ -92,6 +92,8 @@ def load() -> C.CDLL:
     L.ikc_batch_launch.restype = i32
     L.ikc_batch_launch_count.argtypes = [vp]
     L.ikc_batch_launch_count.restype = i32
+    L.ikc_batch_describe.argtypes = [vp, C.c_char_p, sz]
+    L.ikc_batch_describe.restype = i32
     L.ikc_batch_free.argtypes = [vp]
     L.ikc_batch_free.restype = None
     _lib = L

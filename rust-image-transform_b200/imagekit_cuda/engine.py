@@ -204,6 +204,11 @@ class PreparedBatch:
     def launch_count(self) -> int:
         return _lib.load().ikc_batch_launch_count(self._h)
 
+    def describe(self) -> str:
+        buf = C.create_string_buffer(512)
+        _check(_lib.load().ikc_batch_describe(self._h, buf, 512))
+        return buf.value.decode()
+
     def launch(self, stream: int = 0) -> None:
         _check(_lib.load().ikc_batch_launch(self._h, stream))
 

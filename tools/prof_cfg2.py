@@ -6,7 +6,8 @@ import torch
 import imagekit_cuda as ik
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-shapes = {"cfg2": (3840, 2160, 4, 1920, 1080, 4), "cfg3": (4032, 3024, 3, 400, 300, 4), "cfg1": (1920, 1080, 3, 400, 225, 4)}
+shapes = {"cfg2": (3840, 2160, 4, 1920, 1080, 4), "cfg3": (4032, 3024, 3, 400, 300, 4), "cfg1": (1920, 1080, 3, 400, 225, 4),
+          "cfg4": (1920, 1080, 3, 3840, 2160, 2)}
 sw, sh, ch, dw, dh, filt = shapes[wl]
 ctx = ik.Context([0])
 src = torch.randint(0, 256, (batch, sh, sw, ch), dtype=torch.uint8, device="cuda")
