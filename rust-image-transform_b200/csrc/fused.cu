@@ -22,15 +22,13 @@
 namespace ikc {
 namespace {
 
-constexpr int kComputeWarps = 4;
-constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kThreads = kComputeThreads;       // no dedicated producer warp: 8 warps/SM stay balanced
+// A CTA has 8 / WPT warps (WPT = 32-bit source words per thread per row); no dedicated producer warp, so
+// the resident warps stay balanced over the 4 SMSPs.
                                                 // over the 4 SMSPs and keep a 255-register budget
 constexpr int kStageRows = 4;                   // source rows per ring stage (one mbarrier pair)
-constexpr int kSrcRowBytes = 1024;              // staged bytes per source row: 128 threads x 2 x 4
-constexpr int kHalfRowBytes = kSrcRowBytes / 2;
+constexpr int kSrcRowBytes = 1024;              // staged bytes per source row
+constexpr int kHalfRowBytes = kSrcRowBytes / 2; // offset of a thread's second word (WPT == 2)
 constexpr int kTmpRows = 16;                    // f32 intermediate rows per group
-constexpr int kMaxSegs = 2 * kComputeWarps;     // horizontal segments: one per half warp
 constexpr int kHeaderBytes = 256;               // mbarriers
 constexpr int kMaxStages = 8;
 constexpr int kMaxStripOut = 272;                // outputs of one strip (256) + ring pre-roll, in the left/right table
@@ -148,15 +146,18 @@ __device__ __forceinline__ int smem_atomic_inc(int* p) {
 // lane & 15 = tmp row, half warp = x segment of the strip; the same ring march along x.  Outputs whose
 // window straddles a segment boundary are completed from head/tail partial sums parked in tmp columns
 // the thread has already consumed.  Finished pixels are quantised and stored straight to HBM.
-template <int C, int KV, int KH>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int C, int KV, int KH, int WPT>
+__global__ void __launch_bounds__(256 / WPT, 2)
 fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, const FusedGeom geom) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int KSV = (KV + 1) & ~1;  // ring row stride (weight pairs), even
     constexpr int KSH = (KH + 1) & ~1;
     constexpr int kRingRows = Layout<C>::kRingRows;
+    constexpr int kComputeWarps = 8 / WPT;
+    constexpr int kThreads = 32 * kComputeWarps;
+    constexpr int kMaxSegs = 2 * kComputeWarps;      // horizontal segments: one per half warp
     constexpr int kStages = kRingRows / kStageRows;
-    static_assert(kStages == kComputeWarps && kStageRows == 4 && kRingRows == 16, "ring geometry: one stage per warp");
+    static_assert(kStages <= kComputeWarps && kStageRows == 4 && kRingRows == 16, "ring geometry: warp s refills stage s");
 
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty_bar = full_bar + kMaxStages;   // one arrival per warp that has drained the stage
@@ -236,8 +237,11 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     // between the end of the previous segment's last window and the end of its own last window.
     const int span = xr - xl;
     const int n_out = ox1 - ox0;
-    const int want_seg = max(1, min(kMaxSegs, span / (int(J->h.max_count) + 2 * KH + 2)));
-    const int per = ((n_out + want_seg - 1) / want_seg + KH - 1) / KH * KH;
+    // A segment only needs 2*KH consumed pixels to park its head and tail partial sums in; windows may
+    // span several segments (the fix-up pass adds the tails of all earlier segments they touch).
+    const int want_seg = max(1, min(kMaxSegs, span / (2 * KH + 2)));
+    const int per_min = (2 * KH * n_out + span - 1) / span + 1;  // outputs that cover >= 2*KH source pixels
+    const int per = (max((n_out + want_seg - 1) / want_seg, per_min) + KH - 1) / KH * KH;
     const int hrow = lane & 15;
     const int sidx = 2 * warp + (lane >> 4);
     // A short last run (< KH outputs) is merged into the run before it: near the right edge several
@@ -259,21 +263,41 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     const size_t dst_pitch = J->dst_pitch;
     const bool word_ok = C == 4 && ((reinterpret_cast<uintptr_t>(dst_base) | dst_pitch) & 3) == 0;
     bool hw_ready = false;
+    // Uniform stretch of this segment's outputs: whole ring revolutions [fast_lo, fast_hi) of outputs
+    // whose windows lie inside the segment and end exactly fast_s pixels after the previous one (every
+    // interior output of an integer-ratio resize).  The horizontal loop walks them without any per-output
+    // window lookups or branches.
+    int fast_lo = 0, fast_hi = 0, fast_s = 0;
+    if (h_active) {
+        auto prev_end = [&](int o) { return o > os ? lr_tab[o - 1].y : seg_lo; };
+        int o = os;
+        while (o < oe && lr_tab[o].x < seg_lo) ++o;  // heads are finished in the fix-up pass
+        for (int cand = (o + KH - 1) / KH * KH; cand + KH <= oe; cand += KH) {
+            const int s_px = lr_tab[cand].y - prev_end(cand);
+            int hi = cand;
+            while (hi < oe && lr_tab[hi].y - prev_end(hi) == s_px) ++hi;
+            hi = cand + (hi - cand) / KH * KH;
+            if (hi > cand && s_px >= 1) {
+                fast_lo = cand; fast_hi = hi; fast_s = s_px;
+                break;
+            }
+        }
+    }
 
     // ---------------------------------------------------------------- vertical state
-    float2 vacc[KV][4];  // [slot][byte pair]: bytes 0-1, 2-3 of the first word; 0-1, 2-3 of the second
+    float2 vacc[KV][2 * WPT];  // [slot][byte pair]: bytes 0-1, 2-3 of the first word (and of the second)
 #pragma unroll
     for (int j = 0; j < KV; ++j)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) vacc[j][q] = make_float2(0.0f, 0.0f);
+        for (int q = 0; q < 2 * WPT; ++q) vacc[j][q] = make_float2(0.0f, 0.0f);
     const bool v_active0 = 4 * tid < nb;
-    const bool v_active1 = kHalfRowBytes + 4 * tid < nb;
+    const bool v_active1 = WPT == 2 && kHalfRowBytes + 4 * tid < nb;
     const uint8_t* my_src = src_ring + 4 * tid;
 
     // Where this thread's eight vertical results land in a tmp row (float index within the row).
-    int emit_off[8];
+    int emit_off[4 * WPT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4 * WPT; ++i) {
         const int byte = b0 + (i >> 2) * kHalfRowBytes + 4 * tid + (i & 3);
         emit_off[i] = (byte / C - pxb) * 4 + (byte % C);
     }
@@ -317,8 +341,10 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             const float2 wj = (j & 1) ? make_float2(ww.z, ww.w) : make_float2(ww.x, ww.y);
             vacc[j][0] = __ffma2_rn(wj, s0, vacc[j][0]);
             vacc[j][1] = __ffma2_rn(wj, s1, vacc[j][1]);
-            vacc[j][2] = __ffma2_rn(wj, s2, vacc[j][2]);
-            vacc[j][3] = __ffma2_rn(wj, s3, vacc[j][3]);
+            if (WPT == 2) {
+                vacc[j][2 * WPT - 2] = __ffma2_rn(wj, s2, vacc[j][2 * WPT - 2]);
+                vacc[j][2 * WPT - 1] = __ffma2_rn(wj, s3, vacc[j][2 * WPT - 1]);
+            }
         }
     };
     // Called after the row that closes a stage: this warp has drained `stage` (all its loads have
@@ -350,9 +376,9 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             const float4* wrow = vw_ring + ring_row * (KSV / 2);
             if (r + 1 < rend && in_stage != kStageRows - 1) {
                 const uint32_t a0 = *reinterpret_cast<const uint32_t*>(src);
-                const uint32_t a1 = *reinterpret_cast<const uint32_t*>(src + kHalfRowBytes);
+                const uint32_t a1 = WPT == 2 ? *reinterpret_cast<const uint32_t*>(src + kHalfRowBytes) : 0u;
                 const uint32_t c0 = *reinterpret_cast<const uint32_t*>(src + kSrcRowBytes);
-                const uint32_t c1 = *reinterpret_cast<const uint32_t*>(src + kSrcRowBytes + kHalfRowBytes);
+                const uint32_t c1 = WPT == 2 ? *reinterpret_cast<const uint32_t*>(src + kSrcRowBytes + kHalfRowBytes) : 0u;
                 float4 wa[KSV / 2], wc[KSV / 2];
 #pragma unroll
                 for (int jj = 0; jj < KSV / 2; ++jj) { wa[jj] = wrow[jj]; wc[jj] = wrow[KSV / 2 + jj]; }
@@ -362,7 +388,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                 r += 2;
             } else {
                 const uint32_t a0 = *reinterpret_cast<const uint32_t*>(src);
-                const uint32_t a1 = *reinterpret_cast<const uint32_t*>(src + kHalfRowBytes);
+                const uint32_t a1 = WPT == 2 ? *reinterpret_cast<const uint32_t*>(src + kHalfRowBytes) : 0u;
                 float4 wa[KSV / 2];
 #pragma unroll
                 for (int jj = 0; jj < KSV / 2; ++jj) wa[jj] = wrow[jj];
@@ -388,22 +414,24 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                             if (v_active0)
                                 *reinterpret_cast<float4*>(trow + emit_off[0]) =
                                     make_float4(vacc[c][0].x, vacc[c][0].y, vacc[c][1].x, vacc[c][1].y);
-                            if (v_active1)
-                                *reinterpret_cast<float4*>(trow + emit_off[4]) =
-                                    make_float4(vacc[c][2].x, vacc[c][2].y, vacc[c][3].x, vacc[c][3].y);
+                            if (WPT == 2 && v_active1)
+                                *reinterpret_cast<float4*>(trow + emit_off[4 * WPT - 4]) =
+                                    make_float4(vacc[c][2 * WPT - 2].x, vacc[c][2 * WPT - 2].y, vacc[c][2 * WPT - 1].x,
+                                                vacc[c][2 * WPT - 1].y);
                         } else {
                             if (v_active0) {
                                 trow[emit_off[0]] = vacc[c][0].x; trow[emit_off[1]] = vacc[c][0].y;
                                 trow[emit_off[2]] = vacc[c][1].x; trow[emit_off[3]] = vacc[c][1].y;
                             }
-                            if (v_active1) {
-                                trow[emit_off[4]] = vacc[c][2].x; trow[emit_off[5]] = vacc[c][2].y;
-                                trow[emit_off[6]] = vacc[c][3].x; trow[emit_off[7]] = vacc[c][3].y;
+                            if (WPT == 2 && v_active1) {
+                                trow[emit_off[4 * WPT - 4]] = vacc[c][2 * WPT - 2].x; trow[emit_off[4 * WPT - 3]] = vacc[c][2 * WPT - 2].y;
+                                trow[emit_off[4 * WPT - 2]] = vacc[c][2 * WPT - 1].x; trow[emit_off[4 * WPT - 1]] = vacc[c][2 * WPT - 1].y;
                             }
                         }
                         ++emitted;
                     }
-                    vacc[c][0] = vacc[c][1] = vacc[c][2] = vacc[c][3] = make_float2(0.0f, 0.0f);
+#pragma unroll
+                    for (int q = 0; q < 2 * WPT; ++q) vacc[c][q] = make_float2(0.0f, 0.0f);
                     ++ov;
                     if (emitted == kTmpRows || ov == oy1) {
                         c_start = (c + 1) % KV;
@@ -451,6 +479,38 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                 }
             };
             for (;;) {
+                if (hc_start == 0 && oh >= fast_lo && oh + KH <= fast_hi) {
+                    // ---- uniform stretch: slot c finishes after exactly fast_s more pixels
+                    do {
+#pragma unroll
+                        for (int c = 0; c < KH; ++c) {
+                            int left_px = fast_s;
+                            for (; left_px >= 2; left_px -= 2) {  // two pixels per trip: all loads first
+                                const float4 p0 = px[0], p1 = px[1];
+                                float4 w0[KSH / 2], w1[KSH / 2];
+#pragma unroll
+                                for (int jj = 0; jj < KSH / 2; ++jj) { w0[jj] = wh[jj]; w1[jj] = wh[KSH / 2 + jj]; }
+                                accumulate(p0, w0);
+                                accumulate(p1, w1);
+                                px += 2; wh += KSH;
+                            }
+                            if (left_px) {
+                                const float4 p0 = px[0];
+                                float4 w0[KSH / 2];
+#pragma unroll
+                                for (int jj = 0; jj < KSH / 2; ++jj) w0[jj] = wh[jj];
+                                accumulate(p0, w0);
+                                px += 1; wh += KSH / 2;
+                            }
+                            const float4 v = make_float4(hacc[c][0].x, hacc[c][0].y, hacc[c][1].x, hacc[c][1].y);
+                            if (row_live) store_pixel<C>(my_dst + size_t(oh + c) * C, word_ok, v);
+                            hacc[c][0] = hacc[c][1] = make_float2(0.0f, 0.0f);
+                        }
+                        oh += KH;
+                        x += KH * fast_s;
+                    } while (oh + KH <= fast_hi);
+                    lr_next = window_of(oh);
+                }
 #pragma unroll
                 for (int c = 0; c < KH; ++c) {
                     if (c >= hc_start) {  // output oh accumulates in slot c
@@ -549,31 +609,32 @@ int fused_max_src_bytes(int channels) {
 }
 
 int fused_group_rows() { return kTmpRows; }
-int fused_max_segments() { return kMaxSegs; }
 
 bool fused_supported(int channels, int kv, int kh) {
     return (channels == 3 || channels == 4) && kv >= 6 && kv <= 7 && kh >= 6 && kh <= 7;
 }
 
-template <int C, int KV, int KH>
+template <int C, int KV, int KH, int WPT>
 static cudaError_t launch_one(const DevJob* jobs, const WorkItem* items, const FusedGeom& geom,
                               cudaStream_t stream) {
     const size_t smem = fused_smem_bytes(C, KV, KH, geom);
     // Opt in to > 48 KB dynamic shared memory (per device; cheap, so done on every launch).
-    cudaError_t e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH, WPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          int(smem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH, WPT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    fused_ring_kernel<C, KV, KH><<<geom.n_items, kThreads, smem, stream>>>(jobs, items, geom);
+    fused_ring_kernel<C, KV, KH, WPT><<<geom.n_items, 256 / WPT, smem, stream>>>(jobs, items, geom);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fused(int channels, int kv, int kh, const DevJob* jobs, const WorkItem* items,
+cudaError_t launch_fused(int channels, int kv, int kh, int wpt, const DevJob* jobs, const WorkItem* items,
                          const FusedGeom& geom, cudaStream_t stream) {
-#define IKC_CASE(C_, KV_, KH_) \
-    if (channels == C_ && kv == KV_ && kh == KH_) return launch_one<C_, KV_, KH_>(jobs, items, geom, stream);
+#define IKC_CASE(C_, KV_, KH_)                                                                              \
+    if (channels == C_ && kv == KV_ && kh == KH_)                                                           \
+        return wpt == 1 ? launch_one<C_, KV_, KH_, 1>(jobs, items, geom, stream)                            \
+                        : launch_one<C_, KV_, KH_, 2>(jobs, items, geom, stream);
     IKC_CASE(4, 6, 6) IKC_CASE(4, 6, 7) IKC_CASE(4, 7, 6) IKC_CASE(4, 7, 7)
     IKC_CASE(3, 6, 6) IKC_CASE(3, 6, 7) IKC_CASE(3, 7, 6) IKC_CASE(3, 7, 7)
 #undef IKC_CASE

@@ -15,9 +15,9 @@ cudaError_t launch_generic(const DevJob& job, bool exact, cudaStream_t stream);
 bool fused_supported(int channels, int ring_k_v, int ring_k_h);
 int fused_max_src_bytes(int channels);   // source bytes of one strip row the kernel can stage
 int fused_group_rows();                  // intermediate rows per group
-int fused_max_segments();                // x segments of a strip in the horizontal phase
 size_t fused_smem_bytes(int channels, int ring_k_v, int ring_k_h, const FusedGeom& geom);
-cudaError_t launch_fused(int channels, int ring_k_v, int ring_k_h, const DevJob* jobs, const WorkItem* items,
+// words_per_thread: 1 = 8 warps per CTA (one source word per thread per row), 2 = 4 warps per CTA
+cudaError_t launch_fused(int channels, int ring_k_v, int ring_k_h, int words_per_thread, const DevJob* jobs, const WorkItem* items,
                          const FusedGeom& geom, cudaStream_t stream);
 
 // Tile kernel (tile.cu): output-stationary fused passes over shared-memory tiles.
