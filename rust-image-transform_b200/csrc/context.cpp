@@ -2,7 +2,6 @@
 #include "context.hpp"
 
 #include <algorithm>
-#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -166,6 +165,9 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     t->pass.n_in = int32_t(n_in);
     t->pass.n_out = int32_t(n_out);
     t->pass.max_count = int32_t(host->max_count);
+    t->pass.uni_step = host->uni_step;
+    t->pass.uni_lo = host->uni_lo;
+    t->pass.uni_hi = host->uni_hi;
 
     std::lock_guard<std::mutex> lk(mu_);
     auto it = tabs_.find(key);
@@ -218,13 +220,6 @@ std::shared_ptr<const PassPlan> Context::pass(int filter, uint32_t n_in, uint32_
 // ---- launch planning ------------------------------------------------------------------------------
 
 namespace {
-
-// CTA shape of the ring kernel: 2 = 4 warps per CTA, two source words per thread and row (default; measured
-// 3-9 % faster on B200), 1 = 8 warps per CTA, one word per thread (IKC_RING_WPT=1, kept for A/B runs).
-int fused_words_per_thread() {
-    static const int wpt = [] { const char* e = std::getenv("IKC_RING_WPT"); return (e && std::atoi(e) == 1) ? 1 : 2; }();
-    return wpt;
-}
 
 int up16(int v) { return (v + 15) & ~15; }
 
@@ -317,6 +312,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         int job;
         std::vector<std::pair<int, int>> strips;
         int ch, kv, kh;
+        int sv, sh;  // uniform steps the ring kernel has a specialised loop for, else 0
     };
     std::vector<Cand> cands;
     std::vector<WorkItem> tile_items;
@@ -350,7 +346,11 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
             bool fused = !exact && d.bps == 1 && d.sh >= d.dh && d.sw >= d.dw &&
                          fused_supported(d.channels, tv->pass.ring_k, th->pass.ring_k) &&
                          (reinterpret_cast<uintptr_t>(d.src) & 15) == 0 && (d.src_pitch & 15) == 0;
-            Cand c{idx, {}, d.channels, tv->pass.ring_k, th->pass.ring_k};
+            Cand c{idx, {}, d.channels, tv->pass.ring_k, th->pass.ring_k, 0, 0};
+            if (fused_has_uniform(d.channels, c.kv, c.kh, tv->pass.uni_step, th->pass.uni_step)) {
+                c.sv = tv->pass.uni_step;
+                c.sh = th->pass.uni_step;
+            }
             if (fused) {
                 const int max_out = 256;  // outputs per strip (bounds the kernel's left/right table)
                 fused = cut_strips(*th->host, d.channels, int(d.sw), fused_max_src_bytes(d.channels), max_out,
@@ -401,9 +401,9 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         }
         FusedGroup* g = nullptr;
         for (auto& gg : lp.groups)
-            if (gg.channels == c.ch && gg.kv == c.kv && gg.kh == c.kh) g = &gg;
+            if (gg.channels == c.ch && gg.kv == c.kv && gg.kh == c.kh && gg.sv == c.sv && gg.sh == c.sh) g = &gg;
         if (!g) {
-            lp.groups.push_back(FusedGroup{c.ch, c.kv, c.kh, {}, {}, {}});
+            lp.groups.push_back(FusedGroup{c.ch, c.kv, c.kh, {}, {}, {}, c.sv, c.sh});
             g = &lp.groups.back();
         }
         const PassPlan& hp = *lp.keepalive[size_t(c.job) * 2 + 1]->host;
@@ -455,7 +455,7 @@ void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, 
     for (auto& g : lp.groups) {
         const WorkItem* d_items = reinterpret_cast<const WorkItem*>(d_desc_base + off);
         if (g.kv == 0) check_cuda(launch_tile(d_jobs, d_items, g.tgeom, stream), "launch tile_kernel");
-        else check_cuda(launch_fused(g.channels, g.kv, g.kh, fused_words_per_thread(), d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");
+        else check_cuda(launch_fused(g.channels, g.kv, g.kh, g.sv, g.sh, d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");
         off += (sizeof(WorkItem) * g.items.size() + 15) & ~size_t(15);
         launches.fetch_add(1, std::memory_order_relaxed);
     }

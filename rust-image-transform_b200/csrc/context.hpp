@@ -56,6 +56,7 @@ struct FusedGroup {  // one kernel launch over a list of work items
     std::vector<WorkItem> items;
     FusedGeom geom{};
     TileGeom tgeom{};
+    int sv = 0, sh = 0;    // ring kernel: uniform vertical / horizontal step the launch is specialised for (0 = none)
 };
 
 // Everything needed to enqueue a set of device-resident jobs.

@@ -15,6 +15,8 @@ struct DevPass {
     int32_t ring_stride;   // ring_k rounded up to even (row stride of `ring`, in weight pairs)
     int32_t n_in, n_out;
     int32_t max_count;
+    int32_t uni_step;      // outputs [uni_lo, uni_hi) end uni_step source indices after their predecessor
+    int32_t uni_lo, uni_hi;
 };
 
 // One image resize, device pointers.

@@ -22,39 +22,25 @@
 namespace ikc {
 namespace {
 
-// A CTA has 8 / WPT warps (WPT = 32-bit source words per thread per row); no dedicated producer warp, so
-// the resident warps stay balanced over the 4 SMSPs.
-                                                // over the 4 SMSPs and keep a 255-register budget
-constexpr int kStageRows = 4;                   // source rows per ring stage (one mbarrier pair)
-constexpr int kSrcRowBytes = 1024;              // staged bytes per source row
-constexpr int kHalfRowBytes = kSrcRowBytes / 2; // offset of a thread's second word (WPT == 2)
-constexpr int kTmpRows = 16;                    // f32 intermediate rows per group
-constexpr int kHeaderBytes = 256;               // mbarriers
+// A CTA is four compute warps plus one producer warp that keeps the source ring full.  A compute
+// thread owns two 32-bit source words of every staged row.
+constexpr int kComputeWarps = 4;
+constexpr int kComputeThreads = 32 * kComputeWarps;
+constexpr int kThreads = kComputeThreads + 32;
+constexpr int kMaxSegs = 2 * kComputeWarps;      // horizontal segments: one per half warp
+constexpr int kStageRows = 4;                    // source rows per ring stage (one mbarrier pair)
+constexpr int kStages = 4;
+constexpr int kRingRows = kStageRows * kStages;
+constexpr int kSrcRowBytes = 1024;               // staged bytes per source row
+constexpr int kHalfRowBytes = kSrcRowBytes / 2;  // offset of a thread's second word
+constexpr int kTmpRows = 16;                     // f32 intermediate rows per group
+constexpr int kHeaderBytes = 256;                // mbarriers
 constexpr int kMaxStages = 8;
 constexpr int kMaxStripOut = 272;                // outputs of one strip (256) + ring pre-roll, in the left/right table
 
-template <int C>
-struct Layout;
-template <>
-struct Layout<4> {
-    static constexpr int kMaxSrcBytes = 1024;
-    static constexpr int kRingRows = 16;
-};
-template <>
-struct Layout<3> {
-    static constexpr int kMaxSrcBytes = 864;
-    static constexpr int kRingRows = 16;
-};
-template <>
-struct Layout<2> {
-    static constexpr int kMaxSrcBytes = 512;
-    static constexpr int kRingRows = 16;
-};
-template <>
-struct Layout<1> {
-    static constexpr int kMaxSrcBytes = 256;
-    static constexpr int kRingRows = 16;
-};
+constexpr int max_src_bytes(int channels) {
+    return channels == 4 ? 1024 : channels == 3 ? 864 : channels == 2 ? 512 : 256;
+}
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -90,7 +76,8 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
         "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
         : "memory");
 }
-__device__ __forceinline__ void compute_barrier() { __syncthreads(); }
+// Barrier over the compute warps only (the producer warp never joins it).
+__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
 
 // u8 -> f32, exact: PRMT drops the byte into the mantissa of 2^23, one FADD removes the bias.
 template <int BYTE>
@@ -101,9 +88,11 @@ __device__ __forceinline__ float byte_to_float(uint32_t word) {
 // clamp to [0,255] and round half away from zero (f32::round).  trunc(v + 0.5) equals round(v) for
 // every non-negative float except v = 0.5 - 2^-25 (the add rounds up to 1.0); this path's sums differ
 // from the reference's by FMA/association rounding anyway, and the EXACT path (generic.cu) has no such case.
+// The lower clamp is the conversion's own: cvt.rzi.u32.f32 saturates negative inputs (and NaN) to 0.
 __device__ __forceinline__ uint32_t quantize_u8(float v) {
-    v = fminf(fmaxf(v, 0.0f), 255.0f);
-    return __float2uint_rz(v + 0.5f);
+    uint32_t q;
+    asm("cvt.rzi.u32.f32 %0, %1;" : "=r"(q) : "f"(fminf(v, 255.0f) + 0.5f));
+    return q;
 }
 
 // Quantise one finished pixel and store it straight to the destination raster.  Lanes of a half
@@ -113,7 +102,7 @@ template <int C>
 __device__ __forceinline__ void store_pixel(uint8_t* dst_px, bool word_ok, float4 v) {
     const uint32_t r = quantize_u8(v.x), g = quantize_u8(v.y), b = quantize_u8(v.z), a = quantize_u8(v.w);
     if (C == 4 && word_ok) {
-        *reinterpret_cast<uint32_t*>(dst_px) = r | (g << 8) | (b << 16) | (a << 24);
+        *reinterpret_cast<uint32_t*>(dst_px) = __byte_perm(__byte_perm(r, g, 0x0040), __byte_perm(b, a, 0x0040), 0x5410);
     } else {
         dst_px[0] = uint8_t(r);
         if (C > 1) dst_px[1] = uint8_t(g);
@@ -122,45 +111,39 @@ __device__ __forceinline__ void store_pixel(uint8_t* dst_px, bool word_ok, float
     }
 }
 
-// shared-memory atomic add issued by one lane (kept as inline PTX so the compiler does not wrap it
-// in its warp-aggregation sequence)
-__device__ __forceinline__ int smem_atomic_inc(int* p) {
-    int old;
-    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_addr(p)) : "memory");
-    return old;
-}
-
 }  // namespace
 
-// Block = 4 warps; two CTAs are resident per SM.
-//
-// Shared memory: [mbarriers][source ring: kRingRows x 1024 B][vertical weight ring: kRingRows x KSV
+// Shared memory: [mbarriers][source ring: 16 rows x 1024 B][vertical weight ring: 16 rows x KSV
 //                pairs][horizontal weights of the strip: tmp_px x KSH pairs][(left,right) of the
 //                strip's outputs][tmp: 16 rows x tmp_px x float4].  Weights travel with TMA bulk
 //                copies too, so the hot loops only read shared memory.
 //
-// Vertical phase: thread t owns source byte columns [4t,4t+4) and [512+4t,512+4t+4) of the strip and
-// marches down the source rows; its KV ring slots hold the partial sums of the <= KV output rows
-// currently open (slot = output row mod KV).  A finished row goes to tmp as one float4 per pixel
-// (fewer than 4 channels are padded to 4 lanes).  Every 16 finished rows the horizontal phase runs:
-// lane & 15 = tmp row, half warp = x segment of the strip; the same ring march along x.  Outputs whose
-// window straddles a segment boundary are completed from head/tail partial sums parked in tmp columns
-// the thread has already consumed.  Finished pixels are quantised and stored straight to HBM.
-template <int C, int KV, int KH, int WPT>
-__global__ void __launch_bounds__(256 / WPT, 2)
+// Vertical phase: compute thread t owns source byte columns [4t,4t+4) and [512+4t,512+4t+4) of the
+// strip and marches down the source rows; its KV ring slots hold the partial sums of the <= KV output
+// rows currently open (slot = output row mod KV; the slot loop is unrolled, so every accumulator has a
+// fixed register).  A finished row goes to tmp as one float4 per pixel (fewer than 4 channels are
+// padded to 4 lanes).  Every 16 finished rows the horizontal phase runs: lane & 15 = tmp row, half
+// warp = x segment of the strip; the same ring march along x.  Outputs whose window straddles a
+// segment boundary are completed from head/tail partial sums parked in tmp columns the thread has
+// already consumed.  Finished pixels are quantised and stored straight to HBM.
+//
+// SV / SH > 0 add loops specialised for a uniform stretch of the pass (PassPlan::uni_step == SV: every
+// output ends exactly SV source rows after its predecessor, the interior of an integer-ratio resize):
+// a whole ring revolution (K outputs, K*S source rows) is straight-line code with no window lookups.
+// The general loops still handle the image borders, the ring pre-roll and every non-uniform pass.
+//
+// The ring is addressed by "virtual rows": chunk row r lives at virtual row rr = r + p0, ring row
+// rr % 16, stage (rr / 4) % 4.  p0 in [0,4) shifts the stage boundaries so that the first uniform
+// revolution starts on one; the first stage then simply holds 4 - p0 rows.
+template <int C, int KV, int KH, int SV, int SH>
+__global__ void __launch_bounds__(kThreads, 2)
 fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, const FusedGeom geom) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int KSV = (KV + 1) & ~1;  // ring row stride (weight pairs), even
     constexpr int KSH = (KH + 1) & ~1;
-    constexpr int kRingRows = Layout<C>::kRingRows;
-    constexpr int kComputeWarps = 8 / WPT;
-    constexpr int kThreads = 32 * kComputeWarps;
-    constexpr int kMaxSegs = 2 * kComputeWarps;      // horizontal segments: one per half warp
-    constexpr int kStages = kRingRows / kStageRows;
-    static_assert(kStages <= kComputeWarps && kStageRows == 4 && kRingRows == 16, "ring geometry: warp s refills stage s");
 
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty_bar = full_bar + kMaxStages;   // one arrival per warp that has drained the stage
+    uint64_t* empty_bar = full_bar + kMaxStages;   // one arrival per compute warp that has drained the stage
     uint64_t* hw_bar = empty_bar + kMaxStages;
     uint8_t* src_ring = smem + kHeaderBytes;
     float4* vw_ring = reinterpret_cast<float4*>(src_ring + kRingRows * kSrcRowBytes);  // [row][KSV/2]
@@ -196,20 +179,20 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     const int y_last = __ldg(vright + oy1 - 1);
     const int nrows = y_last - y_first;
 
-    // The source ring is refilled by whichever warp is last to finish a stage (see the row loop);
-    // the first fill of every stage is issued here.
-    const uint8_t* const gsrc = J->src + size_t(y_first) * J->src_pitch + b0;
-    const size_t src_pitch = J->src_pitch;
-    auto issue_fill = [&](int stage, int r0) {  // rows [r0, r0 + kStageRows) of the chunk -> stage
-        const int n = min(kStageRows, nrows - r0);
-        const uint32_t wbytes = uint32_t(n) * (KSV * 8);
-        mbar_expect_tx(full_bar + stage, uint32_t(n) * uint32_t(nb) + wbytes);
-        for (int i = 0; i < n; ++i)
-            bulk_load(src_ring + (stage * kStageRows + i) * kSrcRowBytes, gsrc + size_t(r0 + i) * src_pitch,
-                      uint32_t(nb), full_bar + stage);
-        bulk_load(vw_ring + stage * kStageRows * (KSV / 2), vring + size_t(y_first + r0) * (KSV / 2), wbytes,
-                  full_bar + stage);
-    };
+    // Uniform vertical stretch of this chunk: revolutions that start at a multiple of KV inside
+    // [v_fast_lo, v_fast_hi) run the specialised loop.  p0 puts the first of them on a stage boundary.
+    int v_fast_lo = 0, v_fast_hi = 0, p0 = 0;
+    if (SV > 0 && J->v.uni_step == SV) {
+        const int lo = (max(max(oy0, J->v.uni_lo), 1) + KV - 1) / KV * KV;
+        const int hi = min(oy1, J->v.uni_hi);
+        if (lo + KV <= hi) {
+            v_fast_lo = lo;
+            v_fast_hi = hi;
+            const int before = max(0, __ldg(vright + lo - 1) - y_first);  // chunk rows consumed before it
+            p0 = (4 - (before & 3)) & 3;
+        }
+    }
+
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_bar + s, 1);
@@ -218,16 +201,45 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
         mbar_init(hw_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int s = 0; s < kStages && s * kStageRows < nrows; ++s) issue_fill(s, s * kStageRows);
-        // horizontal ring weights of the strip's source pixels [xl, xr): one bulk copy, used by every group
-        const uint32_t hbytes = uint32_t(xr - xl) * (KSH * 8);
-        mbar_expect_tx(hw_bar, hbytes);
-        bulk_load(hw_smem, hring + size_t(xl) * (KSH / 2), hbytes, hw_bar);
     }
     // (left, right) of the strip's outputs (plus the few before ox0 whose windows reach into the strip)
     const int o_lo = max(0, ox0 - KH + 1);
     for (int i = tid; i < ox1 - o_lo; i += kThreads) hlr[i] = make_int2(__ldg(hleft + o_lo + i), __ldg(hright + o_lo + i));
     __syncthreads();
+
+    // ---------------------------------------------------------------- producer warp
+    if (warp == kComputeWarps) {
+        if (lane == 0) {
+            const uint8_t* const gsrc = J->src + size_t(y_first) * J->src_pitch + b0;
+            const size_t src_pitch = J->src_pitch;
+            const int v_end = p0 + nrows;  // virtual rows [p0, v_end) exist
+            auto issue_fill = [&](int f) {   // virtual rows [4f, 4f+4) -> stage f % 4
+                const int stage = f % kStages;
+                const int v0 = max(f * kStageRows, p0), v1 = min((f + 1) * kStageRows, v_end);
+                const int n = v1 - v0;
+                const uint32_t wbytes = uint32_t(n) * (KSV * 8);
+                mbar_expect_tx(full_bar + stage, uint32_t(n) * uint32_t(nb) + wbytes);
+                for (int i = 0; i < n; ++i)
+                    bulk_load(src_ring + ((v0 + i) % kRingRows) * kSrcRowBytes, gsrc + size_t(v0 + i - p0) * src_pitch,
+                              uint32_t(nb), full_bar + stage);
+                bulk_load(vw_ring + (v0 % kRingRows) * (KSV / 2), vring + size_t(y_first + v0 - p0) * (KSV / 2), wbytes,
+                          full_bar + stage);
+            };
+            const int n_fill = (v_end + kStageRows - 1) / kStageRows;
+            int f = 0;
+            for (; f < min(n_fill, kStages); ++f) issue_fill(f);
+            // horizontal ring weights of the strip's source pixels [xl, xr): one bulk copy, used by every group
+            const uint32_t hbytes = uint32_t(xr - xl) * (KSH * 8);
+            mbar_expect_tx(hw_bar, hbytes);
+            bulk_load(hw_smem, hring + size_t(xl) * (KSH / 2), hbytes, hw_bar);
+            for (; f < n_fill; ++f) {
+                mbar_wait(empty_bar + f % kStages, uint32_t(f / kStages - 1) & 1);  // every compute warp has drained it
+                issue_fill(f);
+            }
+        }
+        return;
+    }
+
     const int2* const lr_tab = hlr - o_lo;  // indexed by absolute output column
 
     // ---------------------------------------------------------------- horizontal segmentation
@@ -263,41 +275,35 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     const size_t dst_pitch = J->dst_pitch;
     const bool word_ok = C == 4 && ((reinterpret_cast<uintptr_t>(dst_base) | dst_pitch) & 3) == 0;
     bool hw_ready = false;
-    // Uniform stretch of this segment's outputs: whole ring revolutions [fast_lo, fast_hi) of outputs
-    // whose windows lie inside the segment and end exactly fast_s pixels after the previous one (every
-    // interior output of an integer-ratio resize).  The horizontal loop walks them without any per-output
-    // window lookups or branches.
-    int fast_lo = 0, fast_hi = 0, fast_s = 0;
+    // head_end: the segment's outputs [os, head_end) start in an earlier segment (finished in the fix-up).
+    // [h_fast_lo, h_fast_hi): whole revolutions of this segment inside the pass's uniform stretch.
+    int head_end = os, h_fast_lo = 0, h_fast_hi = 0;
     if (h_active) {
-        auto prev_end = [&](int o) { return o > os ? lr_tab[o - 1].y : seg_lo; };
-        int o = os;
-        while (o < oe && lr_tab[o].x < seg_lo) ++o;  // heads are finished in the fix-up pass
-        for (int cand = (o + KH - 1) / KH * KH; cand + KH <= oe; cand += KH) {
-            const int s_px = lr_tab[cand].y - prev_end(cand);
-            int hi = cand;
-            while (hi < oe && lr_tab[hi].y - prev_end(hi) == s_px) ++hi;
-            hi = cand + (hi - cand) / KH * KH;
-            if (hi > cand && s_px >= 1) {
-                fast_lo = cand; fast_hi = hi; fast_s = s_px;
-                break;
+        while (head_end < oe && lr_tab[head_end].x < seg_lo) ++head_end;
+        if (SH > 0 && J->h.uni_step == SH) {
+            const int lo = (max(max(os, J->h.uni_lo), 1) + KH - 1) / KH * KH;
+            const int hi = min(oe, J->h.uni_hi);
+            if (lo + KH <= hi) {
+                h_fast_lo = lo;
+                h_fast_hi = lo + (hi - lo) / KH * KH;
             }
         }
     }
 
     // ---------------------------------------------------------------- vertical state
-    float2 vacc[KV][2 * WPT];  // [slot][byte pair]: bytes 0-1, 2-3 of the first word (and of the second)
+    float2 vacc[KV][4];  // [slot][byte pair]: bytes 0-1, 2-3 of the first word, then of the second
 #pragma unroll
     for (int j = 0; j < KV; ++j)
 #pragma unroll
-        for (int q = 0; q < 2 * WPT; ++q) vacc[j][q] = make_float2(0.0f, 0.0f);
+        for (int q = 0; q < 4; ++q) vacc[j][q] = make_float2(0.0f, 0.0f);
     const bool v_active0 = 4 * tid < nb;
-    const bool v_active1 = WPT == 2 && kHalfRowBytes + 4 * tid < nb;
-    const uint8_t* my_src = src_ring + 4 * tid;
+    const bool v_active1 = kHalfRowBytes + 4 * tid < nb;
+    const uint8_t* const my_src = src_ring + 4 * tid;
 
     // Where this thread's eight vertical results land in a tmp row (float index within the row).
-    int emit_off[4 * WPT];
+    int emit_off[8];
 #pragma unroll
-    for (int i = 0; i < 4 * WPT; ++i) {
+    for (int i = 0; i < 8; ++i) {
         const int byte = b0 + (i >> 2) * kHalfRowBytes + 4 * tid + (i & 3);
         emit_off[i] = (byte / C - pxb) * 4 + (byte % C);
     }
@@ -324,11 +330,13 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     while (yend_next <= y_first) yend_next = v_end_of(++ov);
     int c_start = ov % KV;  // slot of output ov is ov mod KV; the unrolled slot loop is entered here
 
-    // All ring bookkeeping derives from r = rows of the chunk consumed so far: ring row r % 16, stage
-    // (r / 4) % 4, fill parity (r / 16) & 1.
-    uint32_t r = 0;
+    // All ring bookkeeping derives from rr = virtual rows consumed so far: ring row rr % 16, stage
+    // (rr / 4) % 4, fill parity (rr / 16) & 1.
+    uint32_t rr = uint32_t(p0);
+    const int y_virt0 = y_first - p0;  // source row of virtual row 0
     int g0 = oy0;           // first output row of the group being assembled in tmp
     int emitted = 0;        // rows of that group already in tmp
+    if (p0 != 0) mbar_wait(full_bar + 0, 0);  // the first stage is entered in its middle
 
     auto fma_row = [&](uint32_t d0, uint32_t d1, const float4 (&w)[KSV / 2]) {
         const float2 s0 = make_float2(byte_to_float<0>(d0), byte_to_float<1>(d0));
@@ -341,97 +349,134 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             const float2 wj = (j & 1) ? make_float2(ww.z, ww.w) : make_float2(ww.x, ww.y);
             vacc[j][0] = __ffma2_rn(wj, s0, vacc[j][0]);
             vacc[j][1] = __ffma2_rn(wj, s1, vacc[j][1]);
-            if (WPT == 2) {
-                vacc[j][2 * WPT - 2] = __ffma2_rn(wj, s2, vacc[j][2 * WPT - 2]);
-                vacc[j][2 * WPT - 1] = __ffma2_rn(wj, s3, vacc[j][2 * WPT - 1]);
-            }
+            vacc[j][2] = __ffma2_rn(wj, s2, vacc[j][2]);
+            vacc[j][3] = __ffma2_rn(wj, s3, vacc[j][3]);
         }
     };
-    // Called after the row that closes a stage: this warp has drained `stage` (all its loads have
-    // returned: their values were consumed).  Warp w refills stage w, one stage late: by then the other
-    // warps have drained it too, so the wait normally falls through and nobody stalls on the slowest warp.
-    auto stage_drained = [&](uint32_t stage, uint32_t r_last) {
+    // Called after the row that closes a stage: this warp has drained it (all its loads have returned:
+    // their values were consumed).  The producer refills the stage once all four warps have arrived.
+    auto stage_drained = [&](uint32_t stage) {
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(empty_bar + stage);
-            const uint32_t prev = (stage + kStages - 1) % kStages;
-            if (uint32_t(warp) == prev && r_last >= 2 * kStageRows - 1) {
-                const uint32_t prev_r0 = r_last - (2 * kStageRows - 1);  // first row the previous stage held
-                if (prev_r0 + kRingRows < uint32_t(nrows)) {
-                    mbar_wait(empty_bar + prev, (prev_r0 / kRingRows) & 1);
-                    issue_fill(int(prev), int(prev_r0 + kRingRows));
-                }
-            }
-        }
+        if (lane == 0) mbar_arrive(empty_bar + stage);
     };
-    // Source rows [r, rend) of the chunk into every open ring slot; two rows per trip when both lie in
-    // the same ring stage (all loads first, then both rows' conversions and FMAs), otherwise one.
+    // Virtual rows [rr, rend) into every open ring slot; two rows per trip when both lie in the same
+    // ring stage (all loads first, then both rows' conversions and FMAs), otherwise one.
     auto consume_rows = [&](uint32_t rend) {
-        while (r < rend) {
-            const uint32_t stage = (r / kStageRows) % kStages;
-            const uint32_t in_stage = r % kStageRows;
-            if (in_stage == 0) mbar_wait(full_bar + stage, (r / kRingRows) & 1);  // the stage has landed
-            const uint32_t ring_row = r % kRingRows;
+        while (rr < rend) {
+            const uint32_t stage = (rr / kStageRows) % kStages;
+            const uint32_t in_stage = rr % kStageRows;
+            if (in_stage == 0) mbar_wait(full_bar + stage, (rr / kRingRows) & 1);  // the stage has landed
+            const uint32_t ring_row = rr % kRingRows;
             const uint8_t* src = my_src + ring_row * kSrcRowBytes;
             const float4* wrow = vw_ring + ring_row * (KSV / 2);
-            if (r + 1 < rend && in_stage != kStageRows - 1) {
+            if (rr + 1 < rend && in_stage != kStageRows - 1) {
                 const uint32_t a0 = *reinterpret_cast<const uint32_t*>(src);
-                const uint32_t a1 = WPT == 2 ? *reinterpret_cast<const uint32_t*>(src + kHalfRowBytes) : 0u;
+                const uint32_t a1 = *reinterpret_cast<const uint32_t*>(src + kHalfRowBytes);
                 const uint32_t c0 = *reinterpret_cast<const uint32_t*>(src + kSrcRowBytes);
-                const uint32_t c1 = WPT == 2 ? *reinterpret_cast<const uint32_t*>(src + kSrcRowBytes + kHalfRowBytes) : 0u;
+                const uint32_t c1 = *reinterpret_cast<const uint32_t*>(src + kSrcRowBytes + kHalfRowBytes);
                 float4 wa[KSV / 2], wc[KSV / 2];
 #pragma unroll
                 for (int jj = 0; jj < KSV / 2; ++jj) { wa[jj] = wrow[jj]; wc[jj] = wrow[KSV / 2 + jj]; }
                 fma_row(a0, a1, wa);
                 fma_row(c0, c1, wc);
-                if (in_stage == kStageRows - 2) stage_drained(stage, r + 1);
-                r += 2;
+                if (in_stage == kStageRows - 2) stage_drained(stage);
+                rr += 2;
             } else {
                 const uint32_t a0 = *reinterpret_cast<const uint32_t*>(src);
-                const uint32_t a1 = WPT == 2 ? *reinterpret_cast<const uint32_t*>(src + kHalfRowBytes) : 0u;
+                const uint32_t a1 = *reinterpret_cast<const uint32_t*>(src + kHalfRowBytes);
                 float4 wa[KSV / 2];
 #pragma unroll
                 for (int jj = 0; jj < KSV / 2; ++jj) wa[jj] = wrow[jj];
                 fma_row(a0, a1, wa);
-                if (in_stage == kStageRows - 1) stage_drained(stage, r);
-                r += 1;
+                if (in_stage == kStageRows - 1) stage_drained(stage);
+                rr += 1;
             }
         }
     };
+    // Slot c's finished row -> tmp row `emitted`; the slot restarts from zero.
+    auto emit_slot = [&](float2 (&a)[4]) {
+        float* trow = reinterpret_cast<float*>(tmp + size_t(emitted) * geom.tmp_px);
+        if (C == 4) {
+            if (v_active0) *reinterpret_cast<float4*>(trow + emit_off[0]) = make_float4(a[0].x, a[0].y, a[1].x, a[1].y);
+            if (v_active1) *reinterpret_cast<float4*>(trow + emit_off[4]) = make_float4(a[2].x, a[2].y, a[3].x, a[3].y);
+        } else {
+            if (v_active0) {
+                trow[emit_off[0]] = a[0].x; trow[emit_off[1]] = a[0].y;
+                trow[emit_off[2]] = a[1].x; trow[emit_off[3]] = a[1].y;
+            }
+            if (v_active1) {
+                trow[emit_off[4]] = a[2].x; trow[emit_off[5]] = a[2].y;
+                trow[emit_off[6]] = a[3].x; trow[emit_off[7]] = a[3].y;
+            }
+        }
+        ++emitted;
+    };
+
+    // State of the specialised vertical loop: whether the revolution in progress is a uniform one, and
+    // the ring stage its current rows live in (a stage spans several slots' rows, and a revolution may
+    // be interrupted by the horizontal phase after any slot).
+    bool v_fast = false, yend_stale = false;
+    const uint8_t* f_src = my_src;
+    const float4* f_w = vw_ring;
+    uint32_t f_stage = 0;
 
     while (ov < oy1) {
         // ============================ vertical phase: fill tmp until the group is complete
         for (;;) {
+            if (SV > 0 && c_start == 0) {
+                v_fast = ov >= v_fast_lo && ov + KV <= v_fast_hi && (rr & 3) == 0 &&
+                         (yend_stale || uint32_t(yend_next - y_virt0) == rr + SV);
+            }
+            if (SV > 0 && v_fast) {
+                yend_stale = true;
+#pragma unroll
+                for (int c = 0; c < KV; ++c) {
+                    if (c >= c_start) {
+#pragma unroll
+                        for (int i = 0; i < SV; ++i) {
+                            const int q = (c * SV + i) & 3;  // row within its stage (static after unrolling)
+                            if (q == 0) {
+                                f_stage = (rr / kStageRows) % kStages;
+                                mbar_wait(full_bar + f_stage, (rr / kRingRows) & 1);
+                                f_src = my_src + (rr % kRingRows) * kSrcRowBytes;
+                                f_w = vw_ring + (rr % kRingRows) * (KSV / 2);
+                            }
+                            const uint32_t a0 = *reinterpret_cast<const uint32_t*>(f_src + q * kSrcRowBytes);
+                            const uint32_t a1 = *reinterpret_cast<const uint32_t*>(f_src + q * kSrcRowBytes + kHalfRowBytes);
+                            float4 wa[KSV / 2];
+#pragma unroll
+                            for (int jj = 0; jj < KSV / 2; ++jj) wa[jj] = f_w[q * (KSV / 2) + jj];
+                            fma_row(a0, a1, wa);
+                            if (q == 3) stage_drained(f_stage);
+                            rr += 1;
+                        }
+                        emit_slot(vacc[c]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) vacc[c][q] = make_float2(0.0f, 0.0f);
+                        ++ov;
+                        if (emitted == kTmpRows) {
+                            c_start = (c + 1) % KV;
+                            goto vertical_done;
+                        }
+                    }
+                }
+                c_start = 0;
+                if (ov == oy1) goto vertical_done;
+                continue;
+            }
+            if (SV > 0 && yend_stale) {  // back from uniform revolutions: look the next window end up again
+                yend_next = v_end_of(ov);
+                yend_stale = false;
+            }
 #pragma unroll
             for (int c = 0; c < KV; ++c) {
                 if (c >= c_start) {  // output ov accumulates in slot c
-                    const uint32_t rend = uint32_t(yend_next - y_first);  // rows of the chunk output ov needs
+                    const uint32_t rend = uint32_t(yend_next - y_virt0);  // virtual rows output ov needs
                     yend_next = (ov + 1 < oy1) ? v_end_of(ov + 1) : 0x7fffffff;
                     consume_rows(rend);
-                    if (ov >= oy0) {
-                        float* trow = reinterpret_cast<float*>(tmp + size_t(emitted) * geom.tmp_px);
-                        if (C == 4) {
-                            if (v_active0)
-                                *reinterpret_cast<float4*>(trow + emit_off[0]) =
-                                    make_float4(vacc[c][0].x, vacc[c][0].y, vacc[c][1].x, vacc[c][1].y);
-                            if (WPT == 2 && v_active1)
-                                *reinterpret_cast<float4*>(trow + emit_off[4 * WPT - 4]) =
-                                    make_float4(vacc[c][2 * WPT - 2].x, vacc[c][2 * WPT - 2].y, vacc[c][2 * WPT - 1].x,
-                                                vacc[c][2 * WPT - 1].y);
-                        } else {
-                            if (v_active0) {
-                                trow[emit_off[0]] = vacc[c][0].x; trow[emit_off[1]] = vacc[c][0].y;
-                                trow[emit_off[2]] = vacc[c][1].x; trow[emit_off[3]] = vacc[c][1].y;
-                            }
-                            if (WPT == 2 && v_active1) {
-                                trow[emit_off[4 * WPT - 4]] = vacc[c][2 * WPT - 2].x; trow[emit_off[4 * WPT - 3]] = vacc[c][2 * WPT - 2].y;
-                                trow[emit_off[4 * WPT - 2]] = vacc[c][2 * WPT - 1].x; trow[emit_off[4 * WPT - 1]] = vacc[c][2 * WPT - 1].y;
-                            }
-                        }
-                        ++emitted;
-                    }
+                    if (ov >= oy0) emit_slot(vacc[c]);
 #pragma unroll
-                    for (int q = 0; q < 2 * WPT; ++q) vacc[c][q] = make_float2(0.0f, 0.0f);
+                    for (int q = 0; q < 4; ++q) vacc[c][q] = make_float2(0.0f, 0.0f);
                     ++ov;
                     if (emitted == kTmpRows || ov == oy1) {
                         c_start = (c + 1) % KV;
@@ -442,7 +487,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             c_start = 0;
         }
     vertical_done:
-        __syncthreads();  // tmp rows [0, emitted) are complete
+        compute_barrier();  // tmp rows [0, emitted) are complete
 
         // ============================ horizontal phase
         if (!hw_ready) {  // the strip's horizontal weights were requested at kernel start
@@ -479,36 +524,35 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                 }
             };
             for (;;) {
-                if (hc_start == 0 && oh >= fast_lo && oh + KH <= fast_hi) {
-                    // ---- uniform stretch: slot c finishes after exactly fast_s more pixels
+                if (SH > 0 && hc_start == 0 && oh >= h_fast_lo && oh + KH <= h_fast_hi && x + SH == lr_next.y) {
+                    // ---- uniform stretch: every slot finishes after exactly SH more pixels
+                    uint8_t* d = my_dst + size_t(oh) * C;
                     do {
 #pragma unroll
                         for (int c = 0; c < KH; ++c) {
-                            int left_px = fast_s;
-                            for (; left_px >= 2; left_px -= 2) {  // two pixels per trip: all loads first
-                                const float4 p0 = px[0], p1 = px[1];
-                                float4 w0[KSH / 2], w1[KSH / 2];
 #pragma unroll
-                                for (int jj = 0; jj < KSH / 2; ++jj) { w0[jj] = wh[jj]; w1[jj] = wh[KSH / 2 + jj]; }
-                                accumulate(p0, w0);
-                                accumulate(p1, w1);
-                                px += 2; wh += KSH;
-                            }
-                            if (left_px) {
-                                const float4 p0 = px[0];
-                                float4 w0[KSH / 2];
+                            for (int i = 0; i < SH; ++i) {
+                                const float4 p = px[c * SH + i];
+                                float4 w[KSH / 2];
 #pragma unroll
-                                for (int jj = 0; jj < KSH / 2; ++jj) w0[jj] = wh[jj];
-                                accumulate(p0, w0);
-                                px += 1; wh += KSH / 2;
+                                for (int jj = 0; jj < KSH / 2; ++jj) w[jj] = wh[(c * SH + i) * (KSH / 2) + jj];
+                                accumulate(p, w);
                             }
                             const float4 v = make_float4(hacc[c][0].x, hacc[c][0].y, hacc[c][1].x, hacc[c][1].y);
-                            if (row_live) store_pixel<C>(my_dst + size_t(oh + c) * C, word_ok, v);
+                            if (oh + c >= head_end) {
+                                if (row_live) store_pixel<C>(d + c * C, word_ok, v);
+                            } else {
+                                my_row[seg_lo + n_heads] = v;
+                                ++n_heads;
+                            }
                             hacc[c][0] = hacc[c][1] = make_float2(0.0f, 0.0f);
                         }
                         oh += KH;
-                        x += KH * fast_s;
-                    } while (oh + KH <= fast_hi);
+                        x += KH * SH;
+                        px += KH * SH;
+                        wh += KH * SH * (KSH / 2);
+                        d += KH * C;
+                    } while (oh + KH <= h_fast_hi);
                     lr_next = window_of(oh);
                 }
 #pragma unroll
@@ -519,20 +563,20 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                         lr_next = window_of(oh + 1);
                         const int xend = lr.y;  // <= seg_hi: every owned window ends inside the segment
                         while (x + 1 < xend) {  // two pixels per trip: all loads are issued first
-                            const float4 p0 = px[0], p1 = px[1];
+                            const float4 p0v = px[0], p1v = px[1];
                             float4 w0[KSH / 2], w1[KSH / 2];
 #pragma unroll
                             for (int jj = 0; jj < KSH / 2; ++jj) { w0[jj] = wh[jj]; w1[jj] = wh[KSH / 2 + jj]; }
-                            accumulate(p0, w0);
-                            accumulate(p1, w1);
+                            accumulate(p0v, w0);
+                            accumulate(p1v, w1);
                             x += 2; px += 2; wh += KSH;
                         }
                         if (x < xend) {
-                            const float4 p0 = px[0];
+                            const float4 p0v = px[0];
                             float4 w0[KSH / 2];
 #pragma unroll
                             for (int jj = 0; jj < KSH / 2; ++jj) w0[jj] = wh[jj];
-                            accumulate(p0, w0);
+                            accumulate(p0v, w0);
                             x += 1; px += 1; wh += KSH / 2;
                         }
                         const float4 v = make_float4(hacc[c][0].x, hacc[c][0].y, hacc[c][1].x, hacc[c][1].y);
@@ -558,7 +602,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                     my_row[seg_lo + KH + j] = make_float4(hacc[j][0].x, hacc[j][0].y, hacc[j][1].x, hacc[j][1].y);
             }
         }
-        __syncthreads();
+        compute_barrier();
         // fix-up: heads (the first n_heads outputs of the segment) + tails of earlier segments
         for (int i = 0; i < n_heads; ++i) {
             const int oh = os + i;
@@ -574,7 +618,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             }
             if (row_live) store_pixel<C>(my_dst + size_t(oh) * C, word_ok, v);
         }
-        __syncthreads();  // tmp (incl. parked partial sums) is free for the next vertical rows
+        compute_barrier();  // tmp (incl. parked partial sums) is free for the next vertical rows
         g0 += emitted;
         emitted = 0;
     }
@@ -582,31 +626,13 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
 
 // ---- launcher ---------------------------------------------------------------------------------
 
-static int ring_rows_for(int channels) {
-    switch (channels) {
-        case 4: return Layout<4>::kRingRows;
-        case 3: return Layout<3>::kRingRows;
-        case 2: return Layout<2>::kRingRows;
-        default: return Layout<1>::kRingRows;
-    }
-}
-
-size_t fused_smem_bytes(int channels, int kv, int kh, const FusedGeom& g) {
+size_t fused_smem_bytes(int /*channels*/, int kv, int kh, const FusedGeom& g) {
     const size_t ksv = size_t((kv + 1) & ~1), ksh = size_t((kh + 1) & ~1);
-    const size_t ring = size_t(ring_rows_for(channels));
-    return size_t(kHeaderBytes) + ring * kSrcRowBytes + ring * ksv * 8 + size_t(g.tmp_px) * ksh * 8 +
-           size_t(kMaxStripOut) * sizeof(int2) + size_t(kTmpRows) * g.tmp_px * sizeof(float4);
+    return size_t(kHeaderBytes) + size_t(kRingRows) * kSrcRowBytes + size_t(kRingRows) * ksv * 8 +
+           size_t(g.tmp_px) * ksh * 8 + size_t(kMaxStripOut) * sizeof(int2) + size_t(kTmpRows) * g.tmp_px * sizeof(float4);
 }
 
-int fused_max_src_bytes(int channels) {
-    switch (channels) {
-        case 4: return Layout<4>::kMaxSrcBytes;
-        case 3: return Layout<3>::kMaxSrcBytes;
-        case 2: return Layout<2>::kMaxSrcBytes;
-        case 1: return Layout<1>::kMaxSrcBytes;
-    }
-    return 0;
-}
+int fused_max_src_bytes(int channels) { return (channels >= 1 && channels <= 4) ? max_src_bytes(channels) : 0; }
 
 int fused_group_rows() { return kTmpRows; }
 
@@ -614,29 +640,34 @@ bool fused_supported(int channels, int kv, int kh) {
     return (channels == 3 || channels == 4) && kv >= 6 && kv <= 7 && kh >= 6 && kh <= 7;
 }
 
-template <int C, int KV, int KH, int WPT>
-static cudaError_t launch_one(const DevJob* jobs, const WorkItem* items, const FusedGeom& geom,
-                              cudaStream_t stream) {
+// Specialised uniform loops exist for the integer ratios 2 and 4 (ring size 6, a whole number of ring
+// stages per revolution) in both passes at once.
+bool fused_has_uniform(int channels, int kv, int kh, int step_v, int step_h) {
+    return fused_supported(channels, kv, kh) && kv == 6 && kh == 6 && step_v == step_h && (step_v == 2 || step_v == 4);
+}
+
+template <int C, int KV, int KH, int SV, int SH>
+static cudaError_t launch_one(const DevJob* jobs, const WorkItem* items, const FusedGeom& geom, cudaStream_t stream) {
     const size_t smem = fused_smem_bytes(C, KV, KH, geom);
     // Opt in to > 48 KB dynamic shared memory (per device; cheap, so done on every launch).
-    cudaError_t e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH, WPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH, SV, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          int(smem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH, WPT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH, SV, SH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    fused_ring_kernel<C, KV, KH, WPT><<<geom.n_items, 256 / WPT, smem, stream>>>(jobs, items, geom);
+    fused_ring_kernel<C, KV, KH, SV, SH><<<geom.n_items, kThreads, smem, stream>>>(jobs, items, geom);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fused(int channels, int kv, int kh, int wpt, const DevJob* jobs, const WorkItem* items,
+cudaError_t launch_fused(int channels, int kv, int kh, int sv, int sh, const DevJob* jobs, const WorkItem* items,
                          const FusedGeom& geom, cudaStream_t stream) {
-#define IKC_CASE(C_, KV_, KH_)                                                                              \
-    if (channels == C_ && kv == KV_ && kh == KH_)                                                           \
-        return wpt == 1 ? launch_one<C_, KV_, KH_, 1>(jobs, items, geom, stream)                            \
-                        : launch_one<C_, KV_, KH_, 2>(jobs, items, geom, stream);
-    IKC_CASE(4, 6, 6) IKC_CASE(4, 6, 7) IKC_CASE(4, 7, 6) IKC_CASE(4, 7, 7)
-    IKC_CASE(3, 6, 6) IKC_CASE(3, 6, 7) IKC_CASE(3, 7, 6) IKC_CASE(3, 7, 7)
+#define IKC_CASE(C_, KV_, KH_, SV_, SH_)                                    \
+    if (channels == C_ && kv == KV_ && kh == KH_ && sv == SV_ && sh == SH_) \
+        return launch_one<C_, KV_, KH_, SV_, SH_>(jobs, items, geom, stream);
+    IKC_CASE(4, 6, 6, 2, 2) IKC_CASE(4, 6, 6, 4, 4) IKC_CASE(3, 6, 6, 2, 2) IKC_CASE(3, 6, 6, 4, 4)
+    IKC_CASE(4, 6, 6, 0, 0) IKC_CASE(4, 6, 7, 0, 0) IKC_CASE(4, 7, 6, 0, 0) IKC_CASE(4, 7, 7, 0, 0)
+    IKC_CASE(3, 6, 6, 0, 0) IKC_CASE(3, 6, 7, 0, 0) IKC_CASE(3, 7, 6, 0, 0) IKC_CASE(3, 7, 7, 0, 0)
 #undef IKC_CASE
     return cudaErrorInvalidValue;
 }

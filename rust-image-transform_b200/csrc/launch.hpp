@@ -16,9 +16,11 @@ bool fused_supported(int channels, int ring_k_v, int ring_k_h);
 int fused_max_src_bytes(int channels);   // source bytes of one strip row the kernel can stage
 int fused_group_rows();                  // intermediate rows per group
 size_t fused_smem_bytes(int channels, int ring_k_v, int ring_k_h, const FusedGeom& geom);
-// words_per_thread: 1 = 8 warps per CTA (one source word per thread per row), 2 = 4 warps per CTA
-cudaError_t launch_fused(int channels, int ring_k_v, int ring_k_h, int words_per_thread, const DevJob* jobs, const WorkItem* items,
-                         const FusedGeom& geom, cudaStream_t stream);
+// True when the kernel has loops specialised for these uniform steps (PassPlan::uni_step of both passes).
+bool fused_has_uniform(int channels, int ring_k_v, int ring_k_h, int step_v, int step_h);
+// step_v / step_h: uniform steps the launch is specialised for (both 0: general loops only).
+cudaError_t launch_fused(int channels, int ring_k_v, int ring_k_h, int step_v, int step_h, const DevJob* jobs,
+                         const WorkItem* items, const FusedGeom& geom, cudaStream_t stream);
 
 // Tile kernel (tile.cu): output-stationary fused passes over shared-memory tiles.
 size_t tile_smem_bytes(const TileGeom& geom);

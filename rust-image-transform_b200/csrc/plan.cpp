@@ -185,6 +185,22 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
         k = std::max(k, run);
     }
     p.ring_k = k;
+    // Longest run of outputs that advance by the same number of source indices.
+    {
+        uint32_t best_lo = 0, best_len = 0, lo = 1;
+        for (uint32_t o = 2; o <= n_out; ++o) {
+            const bool same = o < n_out && p.right[o] - p.right[o - 1] == p.right[lo] - p.right[lo - 1];
+            if (!same) {
+                if (lo < n_out && o - lo > best_len) { best_len = o - lo; best_lo = lo; }
+                lo = o;
+            }
+        }
+        if (best_len >= 4u * uint32_t(std::max(k, 1)) && p.right[best_lo] - p.right[best_lo - 1] >= 1) {
+            p.uni_step = p.right[best_lo] - p.right[best_lo - 1];
+            p.uni_lo = int(best_lo);
+            p.uni_hi = int(best_lo + best_len);
+        }
+    }
     if (k >= 1 && k <= 8) {  // only the fused kernels use it; they handle ring_k <= 8
         p.ring_stride = (k + 1) & ~1;  // even: every ring row is a whole number of 16-byte loads
         p.ring.assign(size_t(n_in) * p.ring_stride * 2, 0.0f);

@@ -36,6 +36,10 @@ struct PassPlan {
     std::vector<float> ring;            // [n_in * ring_stride * 2]
     std::vector<int32_t> right;         // [n_out] left + count
     uint32_t max_count = 0;
+    // Uniform stretch: outputs o in [uni_lo, uni_hi) all end exactly uni_step source indices after their
+    // predecessor (right[o] - right[o-1] == uni_step), as every interior output of an integer-ratio
+    // downscale does.  uni_step == 0: no stretch long enough to be worth a specialised loop.
+    int uni_step = 0, uni_lo = 0, uni_hi = 0;
 };
 
 std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n_out);
