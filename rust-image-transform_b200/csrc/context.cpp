@@ -345,7 +345,8 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
 
             bool fused = !exact && d.bps == 1 && d.sh >= d.dh && d.sw >= d.dw &&
                          fused_supported(d.channels, tv->pass.ring_k, th->pass.ring_k) &&
-                         (reinterpret_cast<uintptr_t>(d.src) & 15) == 0 && (d.src_pitch & 15) == 0;
+                         (reinterpret_cast<uintptr_t>(d.src) & 15) == 0 && (d.src_pitch & 15) == 0 &&
+                         (d.channels != 4 || ((reinterpret_cast<uintptr_t>(d.dst) | d.dst_pitch) & 3) == 0);
             Cand c{idx, {}, d.channels, tv->pass.ring_k, th->pass.ring_k, 0, 0};
             if (fused_has_uniform(d.channels, c.kv, c.kh, tv->pass.uni_step, th->pass.uni_step)) {
                 c.sv = tv->pass.uni_step;

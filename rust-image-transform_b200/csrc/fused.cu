@@ -68,6 +68,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// The producer's wait: sleeps between polls so that its spinning does not take issue slots from the compute warps.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(100);
+    }
+}
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile(
@@ -98,10 +115,11 @@ __device__ __forceinline__ uint32_t quantize_u8(float v) {
 // Quantise one finished pixel and store it straight to the destination raster.  Lanes of a half
 // warp hold 16 different rows of the same column, so these are scattered 4-byte (or 1-byte) stores;
 // the sectors are completed in L2 by the same thread's next pixels before they reach HBM.
+// (4-channel destinations are word aligned: the planner only sends those here.)
 template <int C>
-__device__ __forceinline__ void store_pixel(uint8_t* dst_px, bool word_ok, float4 v) {
+__device__ __forceinline__ void store_pixel(uint8_t* dst_px, float4 v) {
     const uint32_t r = quantize_u8(v.x), g = quantize_u8(v.y), b = quantize_u8(v.z), a = quantize_u8(v.w);
-    if (C == 4 && word_ok) {
+    if (C == 4) {
         *reinterpret_cast<uint32_t*>(dst_px) = __byte_perm(__byte_perm(r, g, 0x0040), __byte_perm(b, a, 0x0040), 0x5410);
     } else {
         dst_px[0] = uint8_t(r);
@@ -123,9 +141,8 @@ __device__ __forceinline__ void store_pixel(uint8_t* dst_px, bool word_ok, float
 // rows currently open (slot = output row mod KV; the slot loop is unrolled, so every accumulator has a
 // fixed register).  A finished row goes to tmp as one float4 per pixel (fewer than 4 channels are
 // padded to 4 lanes).  Every 16 finished rows the horizontal phase runs: lane & 15 = tmp row, half
-// warp = x segment of the strip; the same ring march along x.  Outputs whose window straddles a
-// segment boundary are completed from head/tail partial sums parked in tmp columns the thread has
-// already consumed.  Finished pixels are quantised and stored straight to HBM.
+// warp = x segment of the strip; the same ring march along x, started one window early so that each
+// segment is self-contained.  Finished pixels are quantised and stored straight to HBM.
 //
 // SV / SH > 0 add loops specialised for a uniform stretch of the pass (PassPlan::uni_step == SV: every
 // output ends exactly SV source rows after its predecessor, the interior of an integer-ratio resize):
@@ -233,7 +250,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             mbar_expect_tx(hw_bar, hbytes);
             bulk_load(hw_smem, hring + size_t(xl) * (KSH / 2), hbytes, hw_bar);
             for (; f < n_fill; ++f) {
-                mbar_wait(empty_bar + f % kStages, uint32_t(f / kStages - 1) & 1);  // every compute warp has drained it
+                mbar_wait_relaxed(empty_bar + f % kStages, uint32_t(f / kStages - 1) & 1);  // every compute warp has drained it
                 issue_fill(f);
             }
         }
@@ -243,50 +260,32 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     const int2* const lr_tab = hlr - o_lo;  // indexed by absolute output column
 
     // ---------------------------------------------------------------- horizontal segmentation
-    // The strip's outputs [ox0, ox1) are cut into n_seg runs of `per` outputs (a multiple of KH, so
-    // every segment starts on the same ring slot and the half warps of a warp walk the unrolled slot
-    // code in lock step).  Segment s owns outputs [os, oe) and the source pixels [seg_lo, seg_hi)
-    // between the end of the previous segment's last window and the end of its own last window.
-    const int span = xr - xl;
+    // The strip's outputs [ox0, ox1) are cut into runs of `per` outputs (a multiple of KH, so every
+    // segment starts on the same ring slot and the half warps of a warp walk the unrolled slot code in
+    // lock step).  Segment s computes outputs [os, oe) from the source pixels [left[os], right[oe-1]):
+    // neighbouring segments overlap by one window, which costs a few extra FMAs per row but leaves
+    // every output to exactly one thread (no partial sums to exchange between segments).
     const int n_out = ox1 - ox0;
-    // A segment only needs 2*KH consumed pixels to park its head and tail partial sums in; windows may
-    // span several segments (the fix-up pass adds the tails of all earlier segments they touch).
-    const int want_seg = max(1, min(kMaxSegs, span / (2 * KH + 2)));
-    const int per_min = (2 * KH * n_out + span - 1) / span + 1;  // outputs that cover >= 2*KH source pixels
-    const int per = (max((n_out + want_seg - 1) / want_seg, per_min) + KH - 1) / KH * KH;
+    const int per = ((n_out + kMaxSegs - 1) / kMaxSegs + KH - 1) / KH * KH;
     const int hrow = lane & 15;
     const int sidx = 2 * warp + (lane >> 4);
-    // A short last run (< KH outputs) is merged into the run before it: near the right edge several
-    // windows end on the same (clamped) pixel, and a segment must own at least one pixel per head.
-    int n_act = (n_out + per - 1) / per;
-    if (n_act > 1 && n_out - (n_act - 1) * per < KH) --n_act;
     const int os = ox0 + sidx * per;
-    const bool h_active = sidx < n_act;
-    const bool has_next_seg = sidx + 1 < n_act;
-    const int oe = has_next_seg ? os + per : ox1;
-    int seg_lo = xr, seg_hi = xr;
-    if (h_active) {
-        seg_lo = (sidx == 0) ? xl : lr_tab[os - 1].y;
-        seg_hi = lr_tab[oe - 1].y;
-    }
+    const bool h_active = os < ox1;
+    const int oe = min(os + per, ox1);
+    const int seg_lo = h_active ? lr_tab[os].x : xr;
     const int h_slot0 = ox0 % KH;  // ring slot of every segment's first output
-    float4* const my_row = tmp + size_t(hrow) * geom.tmp_px - pxb;  // indexed by absolute source pixel
+    const float4* const my_row = tmp + size_t(hrow) * geom.tmp_px - pxb;  // indexed by absolute source pixel
     uint8_t* const dst_base = J->dst;
     const size_t dst_pitch = J->dst_pitch;
-    const bool word_ok = C == 4 && ((reinterpret_cast<uintptr_t>(dst_base) | dst_pitch) & 3) == 0;
     bool hw_ready = false;
-    // head_end: the segment's outputs [os, head_end) start in an earlier segment (finished in the fix-up).
     // [h_fast_lo, h_fast_hi): whole revolutions of this segment inside the pass's uniform stretch.
-    int head_end = os, h_fast_lo = 0, h_fast_hi = 0;
-    if (h_active) {
-        while (head_end < oe && lr_tab[head_end].x < seg_lo) ++head_end;
-        if (SH > 0 && J->h.uni_step == SH) {
-            const int lo = (max(max(os, J->h.uni_lo), 1) + KH - 1) / KH * KH;
-            const int hi = min(oe, J->h.uni_hi);
-            if (lo + KH <= hi) {
-                h_fast_lo = lo;
-                h_fast_hi = lo + (hi - lo) / KH * KH;
-            }
+    int h_fast_lo = 0, h_fast_hi = 0;
+    if (SH > 0 && h_active && J->h.uni_step == SH) {
+        const int lo = (max(max(os, J->h.uni_lo), 1) + KH - 1) / KH * KH;
+        const int hi = min(oe, J->h.uni_hi);
+        if (lo + KH <= hi) {
+            h_fast_lo = lo;
+            h_fast_hi = lo + (hi - lo) / KH * KH;
         }
     }
 
@@ -496,7 +495,6 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
         }
         uint8_t* const my_dst = dst_base + size_t(g0 + hrow) * dst_pitch;  // this lane's output row
         const bool row_live = hrow < emitted;
-        int n_heads = 0;
         if (h_active) {
             float2 hacc[KH][2];
 #pragma unroll
@@ -504,10 +502,9 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             int x = seg_lo;
             const float4* px = my_row + seg_lo;
             const float4* wh = hw_smem + size_t(seg_lo - xl) * (KSH / 2);
-            // Start one ring revolution early: outputs before `os` that are still open at seg_lo (only
-            // possible for the strip's first segment) hold their slots until their windows close; they
-            // are walked like any other output but never emitted.  Every segment pre-rolls the same KH
-            // outputs so that all half warps stay on the same unrolled slot.
+            // Start one ring revolution early: the outputs before `os` whose windows are still open at
+            // seg_lo hold their slots until they close; they are walked like any other output (consuming
+            // the pixels up to their window end) but never stored.
             int oh = os - KH;
             int hc_start = h_slot0;
             auto window_of = [&](int o) { return (o >= o_lo && o < oe) ? lr_tab[o] : make_int2(0, 0); };
@@ -539,12 +536,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                                 accumulate(p, w);
                             }
                             const float4 v = make_float4(hacc[c][0].x, hacc[c][0].y, hacc[c][1].x, hacc[c][1].y);
-                            if (oh + c >= head_end) {
-                                if (row_live) store_pixel<C>(d + c * C, word_ok, v);
-                            } else {
-                                my_row[seg_lo + n_heads] = v;
-                                ++n_heads;
-                            }
+                            if (row_live) store_pixel<C>(d + c * C, v);
                             hacc[c][0] = hacc[c][1] = make_float2(0.0f, 0.0f);
                         }
                         oh += KH;
@@ -559,9 +551,8 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                 for (int c = 0; c < KH; ++c) {
                     if (c >= hc_start) {  // output oh accumulates in slot c
                         if (oh >= oe) goto horizontal_done;
-                        const int2 lr = lr_next;
+                        const int xend = lr_next.y;
                         lr_next = window_of(oh + 1);
-                        const int xend = lr.y;  // <= seg_hi: every owned window ends inside the segment
                         while (x + 1 < xend) {  // two pixels per trip: all loads are issued first
                             const float4 p0v = px[0], p1v = px[1];
                             float4 w0[KSH / 2], w1[KSH / 2];
@@ -579,14 +570,9 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                             accumulate(p0v, w0);
                             x += 1; px += 1; wh += KSH / 2;
                         }
-                        const float4 v = make_float4(hacc[c][0].x, hacc[c][0].y, hacc[c][1].x, hacc[c][1].y);
-                        if (oh >= os) {
-                            if (lr.x >= seg_lo) {  // the whole window lies in this segment: finished pixel
-                                if (row_live) store_pixel<C>(my_dst + size_t(oh) * C, word_ok, v);
-                            } else {               // head: the window started in an earlier segment; park the
-                                my_row[seg_lo + n_heads] = v;  // partial sum in a tmp column already consumed
-                                ++n_heads;
-                            }
+                        if (oh >= os && row_live) {
+                            const float4 v = make_float4(hacc[c][0].x, hacc[c][0].y, hacc[c][1].x, hacc[c][1].y);
+                            store_pixel<C>(my_dst + size_t(oh) * C, v);
                         }
                         hacc[c][0] = hacc[c][1] = make_float2(0.0f, 0.0f);
                         ++oh;
@@ -594,31 +580,9 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                 }
                 hc_start = 0;
             }
-        horizontal_done:
-            // tails: partial sums of the windows still open at seg_hi (slot = output index mod KH)
-            if (has_next_seg) {
-#pragma unroll
-                for (int j = 0; j < KH; ++j)
-                    my_row[seg_lo + KH + j] = make_float4(hacc[j][0].x, hacc[j][0].y, hacc[j][1].x, hacc[j][1].y);
-            }
+        horizontal_done:;
         }
-        compute_barrier();
-        // fix-up: heads (the first n_heads outputs of the segment) + tails of earlier segments
-        for (int i = 0; i < n_heads; ++i) {
-            const int oh = os + i;
-            float4 v = my_row[seg_lo + i];
-            const int first = lr_tab[oh].x;
-            const int slot = oh % KH;
-            for (int sg = sidx - 1; sg >= 0; --sg) {
-                const int sg_hi = lr_tab[ox0 + (sg + 1) * per - 1].y;
-                if (sg_hi <= first) break;  // the window starts after that segment
-                const int sg_lo = (sg == 0) ? xl : lr_tab[ox0 + sg * per - 1].y;
-                const float4 t = my_row[sg_lo + KH + slot];
-                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-            }
-            if (row_live) store_pixel<C>(my_dst + size_t(oh) * C, word_ok, v);
-        }
-        compute_barrier();  // tmp (incl. parked partial sums) is free for the next vertical rows
+        compute_barrier();  // tmp is free for the next vertical rows
         g0 += emitted;
         emitted = 0;
     }

@@ -57,6 +57,8 @@ FUSED_SHAPES = [  # Lanczos3 downscales that take the fused ring kernel: (h, w, 
     (480, 640, 3, 200, 150), (480, 640, 4, 320, 240), (1080, 1920, 3, 400, 225), (1000, 1504, 4, 752, 500),
     (777, 1031, 3, 515, 388), (901, 1200, 4, 411, 309), (2160, 3840, 4, 1920, 1080), (3024, 4032, 3, 400, 300),
     (512, 512, 4, 511, 511), (300, 5000, 3, 2500, 150), (4000, 304, 4, 152, 2000), (768, 1024, 3, 1000, 750),
+    # integer ratios (the kernel's uniform-stretch loops): 4x both channel counts, 2x with ragged strips, 2x by 4x
+    (1024, 2048, 4, 512, 256), (960, 1280, 3, 320, 240), (1500, 2002, 3, 1001, 750), (1216, 1216, 4, 608, 304),
 ]
 
 
@@ -72,7 +74,8 @@ def test_fused_kernel_parity(ctx, ik, oracle, shape, content):
     got = ctx.resize(src, dw, dh, ik.FILTER_LANCZOS3)
     assert ctx.kernel_launches - before == 1, "expected the single-launch fused kernel"
     want = oracle.resize_exact(src, dw, dh, oracle.LANCZOS3)
-    _check_fast(got, want, (shape, content), max_off=0.002 if content == "noise" else 0.03)
+    # checkerboards on integer ratios put many sums exactly on x.5, where FMA contraction decides the tie
+    _check_fast(got, want, (shape, content), max_off={"noise": 0.002, "photo": 0.03, "edges": 0.06}[content])
 
 
 def test_fused_gaussian_downscale(ctx, ik, oracle):
