@@ -68,22 +68,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// The producer's wait: sleeps between polls so that its spinning does not take issue slots from the compute warps.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    for (;;) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_addr(bar)), "r"(parity)
-            : "memory");
-        if (done) return;
-        __nanosleep(100);
-    }
+// The producer's wait: try_wait with a suspend-time hint parks the thread in hardware until the phase
+// completes (or the hint, in ns, runs out), so its polling does not take issue slots from the compute warps.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity), "r"(20000u)
+        : "memory");
 }
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -105,11 +103,11 @@ __device__ __forceinline__ float byte_to_float(uint32_t word) {
 // clamp to [0,255] and round half away from zero (f32::round).  trunc(v + 0.5) equals round(v) for
 // every non-negative float except v = 0.5 - 2^-25 (the add rounds up to 1.0); this path's sums differ
 // from the reference's by FMA/association rounding anyway, and the EXACT path (generic.cu) has no such case.
-// The lower clamp is the conversion's own: cvt.rzi.u32.f32 saturates negative inputs (and NaN) to 0.
+// clamp(v) + 0.5 == clamp(v + 0.5, 0.5, 255.5); adding 2^23 with round-toward-zero then leaves
+// floor(that) in the low mantissa byte, all on the FMA pipe (no F2I on the quarter-rate XU pipe).
 __device__ __forceinline__ uint32_t quantize_u8(float v) {
-    uint32_t q;
-    asm("cvt.rzi.u32.f32 %0, %1;" : "=r"(q) : "f"(fminf(v, 255.0f) + 0.5f));
-    return q;
+    const float t = fminf(fmaxf(v + 0.5f, 0.5f), 255.5f);
+    return __float_as_uint(__fadd_rz(t, 8388608.0f));  // low byte = result; upper bytes = 0x4B0000
 }
 
 // Quantise one finished pixel and store it straight to the destination raster.  Lanes of a half
@@ -250,7 +248,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             mbar_expect_tx(hw_bar, hbytes);
             bulk_load(hw_smem, hring + size_t(xl) * (KSH / 2), hbytes, hw_bar);
             for (; f < n_fill; ++f) {
-                mbar_wait_relaxed(empty_bar + f % kStages, uint32_t(f / kStages - 1) & 1);  // every compute warp has drained it
+                mbar_wait_parked(empty_bar + f % kStages, uint32_t(f / kStages - 1) & 1);  // every compute warp has drained it
                 issue_fill(f);
             }
         }
@@ -337,19 +335,22 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     int emitted = 0;        // rows of that group already in tmp
     if (p0 != 0) mbar_wait(full_bar + 0, 0);  // the first stage is entered in its middle
 
+    // (source-pair major: consecutive FFMA2s share their source operand, which the register operand reuse
+    //  cache serves -- measured 127 vs 108 FMA lanes/clk/SM against the slot-major order)
     auto fma_row = [&](uint32_t d0, uint32_t d1, const float4 (&w)[KSV / 2]) {
-        const float2 s0 = make_float2(byte_to_float<0>(d0), byte_to_float<1>(d0));
-        const float2 s1 = make_float2(byte_to_float<2>(d0), byte_to_float<3>(d0));
-        const float2 s2 = make_float2(byte_to_float<0>(d1), byte_to_float<1>(d1));
-        const float2 s3 = make_float2(byte_to_float<2>(d1), byte_to_float<3>(d1));
+        float2 s[4];
+        s[0] = make_float2(byte_to_float<0>(d0), byte_to_float<1>(d0));
+        s[1] = make_float2(byte_to_float<2>(d0), byte_to_float<3>(d0));
+        s[2] = make_float2(byte_to_float<0>(d1), byte_to_float<1>(d1));
+        s[3] = make_float2(byte_to_float<2>(d1), byte_to_float<3>(d1));
 #pragma unroll
-        for (int j = 0; j < KV; ++j) {
-            const float4 ww = w[j >> 1];
-            const float2 wj = (j & 1) ? make_float2(ww.z, ww.w) : make_float2(ww.x, ww.y);
-            vacc[j][0] = __ffma2_rn(wj, s0, vacc[j][0]);
-            vacc[j][1] = __ffma2_rn(wj, s1, vacc[j][1]);
-            vacc[j][2] = __ffma2_rn(wj, s2, vacc[j][2]);
-            vacc[j][3] = __ffma2_rn(wj, s3, vacc[j][3]);
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int j = 0; j < KV; ++j) {
+                const float4 ww = w[j >> 1];
+                const float2 wj = (j & 1) ? make_float2(ww.z, ww.w) : make_float2(ww.x, ww.y);
+                vacc[j][q] = __ffma2_rn(wj, s[q], vacc[j][q]);
+            }
         }
     };
     // Called after the row that closes a stage: this warp has drained it (all its loads have returned:
@@ -511,13 +512,15 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             int2 lr_next = window_of(oh);
 
             auto accumulate = [&](const float4& p, const float4* w) {
-                const float2 plo = make_float2(p.x, p.y), phi = make_float2(p.z, p.w);
+                const float2 ph[2] = {make_float2(p.x, p.y), make_float2(p.z, p.w)};
 #pragma unroll
-                for (int j = 0; j < KH; ++j) {
-                    const float4 ww = w[j >> 1];
-                    const float2 wj = (j & 1) ? make_float2(ww.z, ww.w) : make_float2(ww.x, ww.y);
-                    hacc[j][0] = __ffma2_rn(wj, plo, hacc[j][0]);
-                    hacc[j][1] = __ffma2_rn(wj, phi, hacc[j][1]);
+                for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                    for (int j = 0; j < KH; ++j) {
+                        const float4 ww = w[j >> 1];
+                        const float2 wj = (j & 1) ? make_float2(ww.z, ww.w) : make_float2(ww.x, ww.y);
+                        hacc[j][q] = __ffma2_rn(wj, ph[q], hacc[j][q]);
+                    }
                 }
             };
             for (;;) {
