@@ -34,7 +34,8 @@ constexpr int kRingRows = kStageRows * kStages;
 constexpr int kSrcRowBytes = 1024;               // staged bytes per source row
 constexpr int kHalfRowBytes = kSrcRowBytes / 2;  // offset of a thread's second word
 constexpr int kTmpRows = 16;                     // f32 intermediate rows per group
-constexpr int kHeaderBytes = 256;                // mbarriers
+constexpr int kHeaderBytes = 512;                // mbarriers, then the uniform stretches' tap weights
+constexpr int kTapOffsetV = 128, kTapOffsetH = 320;  // byte offsets of the (duplicated) tap weights, <= 24 pairs each
 constexpr int kMaxStages = 8;
 constexpr int kMaxStripOut = 272;                // outputs of one strip (256) + ring pre-roll, in the left/right table
 
@@ -156,6 +157,10 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int KSV = (KV + 1) & ~1;  // ring row stride (weight pairs), even
     constexpr int KSH = (KH + 1) & ~1;
+    // Uniform stretches whose whole window (K * S taps) fits a few registers run from tap weights held
+    // in registers instead of the per-row ring weights in shared memory.
+    constexpr int LV = KV * SV, LH = KH * SH;
+    constexpr bool RWV = SV > 0 && LV <= 12, RWH = SH > 0 && LH <= 12;
 
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty_bar = full_bar + kMaxStages;   // one arrival per compute warp that has drained the stage
@@ -165,6 +170,8 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     float4* hw_smem = vw_ring + kRingRows * (KSV / 2);                                 // [px][KSH/2]
     int2* hlr = reinterpret_cast<int2*>(hw_smem + size_t(geom.tmp_px) * (KSH / 2));    // (left, right)
     float4* tmp = reinterpret_cast<float4*>(hlr + kMaxStripOut);
+    float2* const vtap = reinterpret_cast<float2*>(smem + kTapOffsetV);  // [LV] (w, w)
+    float2* const htap = reinterpret_cast<float2*>(smem + kTapOffsetH);  // [LH]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -199,7 +206,9 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     int v_fast_lo = 0, v_fast_hi = 0, p0 = 0;
     if (SV > 0 && J->v.uni_step == SV) {
         const int lo = (max(max(oy0, J->v.uni_lo), 1) + KV - 1) / KV * KV;
-        const int hi = min(oy1, J->v.uni_hi);
+        // With tap registers the outputs that enter the ring during a revolution (the next KV) must belong
+        // to the stretch too, unless they lie below the chunk and are never emitted.
+        const int hi = (!RWV || oy1 <= J->v.uni_hi) ? min(oy1, J->v.uni_hi) : J->v.uni_hi - KV;
         if (lo + KV <= hi) {
             v_fast_lo = lo;
             v_fast_hi = hi;
@@ -216,6 +225,15 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
         mbar_init(hw_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // tap weights of the uniform stretches (every output of a stretch has the same ones)
+    if (RWV && tid < LV && J->v.uni_step == SV) {
+        const float w = __ldg(J->v.w + size_t(J->v.uni_lo) * J->v.stride + tid);
+        vtap[tid] = make_float2(w, w);
+    }
+    if (RWH && tid >= 32 && tid < 32 + LH && J->h.uni_step == SH) {
+        const float w = __ldg(J->h.w + size_t(J->h.uni_lo) * J->h.stride + (tid - 32));
+        htap[tid - 32] = make_float2(w, w);
     }
     // (left, right) of the strip's outputs (plus the few before ox0 whose windows reach into the strip)
     const int o_lo = max(0, ox0 - KH + 1);
@@ -277,13 +295,20 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     const size_t dst_pitch = J->dst_pitch;
     bool hw_ready = false;
     // [h_fast_lo, h_fast_hi): whole revolutions of this segment inside the pass's uniform stretch.
-    int h_fast_lo = 0, h_fast_hi = 0;
+    int h_fast_lo = 0, h_fast_hi = 0, h_pre = 0;
     if (SH > 0 && h_active && J->h.uni_step == SH) {
         const int lo = (max(max(os, J->h.uni_lo), 1) + KH - 1) / KH * KH;
-        const int hi = min(oe, J->h.uni_hi);
+        const int hi = (!RWH || oe <= J->h.uni_hi) ? min(oe, J->h.uni_hi) : J->h.uni_hi - KH;  // as for the rows
         if (lo + KH <= hi) {
             h_fast_lo = lo;
             h_fast_hi = lo + (hi - lo) / KH * KH;
+            // The pre-roll revolution is uniform too when the walk starts SH pixels before the first
+            // window (so that the first pre-roll output also takes SH pixels): those pixels only reach
+            // slots of outputs that are never stored.
+            if (lo == os && h_slot0 == 0 && os - KH >= J->h.uni_lo) {
+                h_fast_lo = os - KH;
+                h_pre = SH;
+            }
         }
     }
 
@@ -350,6 +375,23 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                 const float4 ww = w[j >> 1];
                 const float2 wj = (j & 1) ? make_float2(ww.z, ww.w) : make_float2(ww.x, ww.y);
                 vacc[j][q] = __ffma2_rn(wj, s[q], vacc[j][q]);
+            }
+        }
+    };
+    // The same for row m of a uniform revolution, weights from the tap registers: slot j is at tap
+    // (m - SV*(j+1)) mod LV of its window (the slot's previous output closed SV*(j+1) rows into the revolution).
+    auto fma_row_taps = [&](uint32_t d0, uint32_t d1, const float2* wt, int m) {
+        float2 s[4];
+        s[0] = make_float2(byte_to_float<0>(d0), byte_to_float<1>(d0));
+        s[1] = make_float2(byte_to_float<2>(d0), byte_to_float<3>(d0));
+        s[2] = make_float2(byte_to_float<0>(d1), byte_to_float<1>(d1));
+        s[3] = make_float2(byte_to_float<2>(d1), byte_to_float<3>(d1));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int j = 0; j < KV; ++j) {
+                const int t = (m - SV * (j + 1) + 2 * LV) % (LV > 0 ? LV : 1);
+                vacc[j][q] = __ffma2_rn(wt[t], s[q], vacc[j][q]);
             }
         }
     };
@@ -429,6 +471,11 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             }
             if (SV > 0 && v_fast) {
                 yend_stale = true;
+                float2 wt[RWV ? LV : 1];
+                if (RWV) {
+#pragma unroll
+                    for (int t = 0; t < LV; ++t) wt[t] = vtap[t];
+                }
 #pragma unroll
                 for (int c = 0; c < KV; ++c) {
                     if (c >= c_start) {
@@ -443,10 +490,14 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                             }
                             const uint32_t a0 = *reinterpret_cast<const uint32_t*>(f_src + q * kSrcRowBytes);
                             const uint32_t a1 = *reinterpret_cast<const uint32_t*>(f_src + q * kSrcRowBytes + kHalfRowBytes);
-                            float4 wa[KSV / 2];
+                            if (RWV) {
+                                fma_row_taps(a0, a1, wt, c * SV + i);
+                            } else {
+                                float4 wa[KSV / 2];
 #pragma unroll
-                            for (int jj = 0; jj < KSV / 2; ++jj) wa[jj] = f_w[q * (KSV / 2) + jj];
-                            fma_row(a0, a1, wa);
+                                for (int jj = 0; jj < KSV / 2; ++jj) wa[jj] = f_w[q * (KSV / 2) + jj];
+                                fma_row(a0, a1, wa);
+                            }
                             if (q == 3) stage_drained(f_stage);
                             rr += 1;
                         }
@@ -500,9 +551,9 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             float2 hacc[KH][2];
 #pragma unroll
             for (int j = 0; j < KH; ++j) hacc[j][0] = hacc[j][1] = make_float2(0.0f, 0.0f);
-            int x = seg_lo;
-            const float4* px = my_row + seg_lo;
-            const float4* wh = hw_smem + size_t(seg_lo - xl) * (KSH / 2);
+            int x = seg_lo - h_pre;
+            const float4* px = my_row + x;
+            const float4* wh = hw_smem + (x - xl) * (KSH / 2);
             // Start one ring revolution early: the outputs before `os` whose windows are still open at
             // seg_lo hold their slots until they close; they are walked like any other output (consuming
             // the pixels up to their window end) but never stored.
@@ -524,22 +575,39 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                 }
             };
             for (;;) {
-                if (SH > 0 && hc_start == 0 && oh >= h_fast_lo && oh + KH <= h_fast_hi && x + SH == lr_next.y) {
+                if (SH > 0 && hc_start == 0 && oh >= h_fast_lo && oh + KH <= h_fast_hi && (oh < os || x + SH == lr_next.y)) {
                     // ---- uniform stretch: every slot finishes after exactly SH more pixels
-                    uint8_t* d = my_dst + size_t(oh) * C;
+                    uint8_t* d = my_dst + ptrdiff_t(oh) * C;
+                    float2 ht[RWH ? LH : 1];
+                    if (RWH) {
+#pragma unroll
+                        for (int t = 0; t < LH; ++t) ht[t] = htap[t];
+                    }
                     do {
 #pragma unroll
                         for (int c = 0; c < KH; ++c) {
 #pragma unroll
                             for (int i = 0; i < SH; ++i) {
                                 const float4 p = px[c * SH + i];
-                                float4 w[KSH / 2];
+                                if (RWH) {  // pixel m of the revolution: slot j is at tap (m - SH*(j+1)) mod LH
+                                    const float2 ph[2] = {make_float2(p.x, p.y), make_float2(p.z, p.w)};
 #pragma unroll
-                                for (int jj = 0; jj < KSH / 2; ++jj) w[jj] = wh[(c * SH + i) * (KSH / 2) + jj];
-                                accumulate(p, w);
+                                    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                                        for (int j = 0; j < KH; ++j) {
+                                            const int t = (c * SH + i - SH * (j + 1) + 2 * LH) % (LH > 0 ? LH : 1);
+                                            hacc[j][q] = __ffma2_rn(ht[t], ph[q], hacc[j][q]);
+                                        }
+                                    }
+                                } else {
+                                    float4 w[KSH / 2];
+#pragma unroll
+                                    for (int jj = 0; jj < KSH / 2; ++jj) w[jj] = wh[(c * SH + i) * (KSH / 2) + jj];
+                                    accumulate(p, w);
+                                }
                             }
                             const float4 v = make_float4(hacc[c][0].x, hacc[c][0].y, hacc[c][1].x, hacc[c][1].y);
-                            if (row_live) store_pixel<C>(d + c * C, v);
+                            if (row_live && oh + c >= os) store_pixel<C>(d + c * C, v);
                             hacc[c][0] = hacc[c][1] = make_float2(0.0f, 0.0f);
                         }
                         oh += KH;

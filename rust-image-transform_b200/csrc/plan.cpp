@@ -4,6 +4,7 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <cstring>
 #include <cmath>
 #include <limits>
 
@@ -185,17 +186,27 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
         k = std::max(k, run);
     }
     p.ring_k = k;
-    // Longest run of outputs that advance by the same number of source indices.
-    {
-        uint32_t best_lo = 0, best_len = 0, lo = 1;
-        for (uint32_t o = 2; o <= n_out; ++o) {
-            const bool same = o < n_out && p.right[o] - p.right[o - 1] == p.right[lo] - p.right[lo - 1];
-            if (!same) {
-                if (lo < n_out && o - lo > best_len) { best_len = o - lo; best_lo = lo; }
-                lo = o;
-            }
+    // Uniform stretch: the longest run of outputs that (a) end the same number of source indices after
+    // their predecessor, (b) have full windows of ring_k * step taps that start where the window ring_k
+    // outputs earlier ended, and (c) share one set of weights bit for bit -- the interior of an
+    // integer-ratio downscale.  The fused kernel runs such a stretch from tap weights held in registers.
+    if (k >= 1 && n_out >= 2) {
+        auto uniform_with = [&](uint32_t o, uint32_t ref, int step) {
+            if (p.right[o] - p.right[o - 1] != step || p.count[o] != k * step) return false;
+            if (o >= uint32_t(k) && p.left[o] != p.right[o - uint32_t(k)]) return false;
+            return std::equal(ragged[o].begin(), ragged[o].end(), ragged[ref].begin(),
+                              [](float x, float y) { return std::memcmp(&x, &y, sizeof(float)) == 0; });
+        };
+        uint32_t best_lo = 0, best_len = 0;
+        for (uint32_t lo = 1; lo < n_out;) {
+            const int step = p.right[lo] - p.right[lo - 1];
+            uint32_t hi = lo;
+            if (step >= 1 && p.count[lo] == k * step)
+                while (hi < n_out && uniform_with(hi, lo, step)) ++hi;
+            if (hi - lo > best_len) { best_len = hi - lo; best_lo = lo; }
+            lo = std::max(hi, lo + 1);
         }
-        if (best_len >= 4u * uint32_t(std::max(k, 1)) && p.right[best_lo] - p.right[best_lo - 1] >= 1) {
+        if (best_len >= 4u * uint32_t(k)) {
             p.uni_step = p.right[best_lo] - p.right[best_lo - 1];
             p.uni_lo = int(best_lo);
             p.uni_hi = int(best_lo + best_len);

@@ -59,6 +59,7 @@ FUSED_SHAPES = [  # Lanczos3 downscales that take the fused ring kernel: (h, w, 
     (512, 512, 4, 511, 511), (300, 5000, 3, 2500, 150), (4000, 304, 4, 152, 2000), (768, 1024, 3, 1000, 750),
     # integer ratios (the kernel's uniform-stretch loops): 4x both channel counts, 2x with ragged strips, 2x by 4x
     (1024, 2048, 4, 512, 256), (960, 1280, 3, 320, 240), (1500, 2002, 3, 1001, 750), (1216, 1216, 4, 608, 304),
+    (600, 800, 4, 400, 300), (602, 802, 4, 401, 301), (300, 400, 3, 200, 150), (128, 96, 4, 48, 64),
 ]
 
 
