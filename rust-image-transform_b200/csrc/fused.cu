@@ -318,16 +318,16 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     for (int j = 0; j < KV; ++j)
 #pragma unroll
         for (int q = 0; q < 4; ++q) vacc[j][q] = make_float2(0.0f, 0.0f);
-    const bool v_active0 = 4 * tid < nb;
-    const bool v_active1 = kHalfRowBytes + 4 * tid < nb;
     const uint8_t* const my_src = src_ring + 4 * tid;
 
     // Where this thread's eight vertical results land in a tmp row (float index within the row).
     int emit_off[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int byte = b0 + (i >> 2) * kHalfRowBytes + 4 * tid + (i & 3);
-        emit_off[i] = (byte / C - pxb) * 4 + (byte % C);
+        const int in_row = (i >> 2) * kHalfRowBytes + 4 * tid;  // this word's offset in the staged row
+        const int byte = b0 + in_row + (i & 3);
+        // words beyond the strip's staged bytes go to the spare last column of the tmp row
+        emit_off[i] = in_row < nb ? (byte / C - pxb) * 4 + (byte % C) : (geom.tmp_px - 1) * 4 + (i & 3);
     }
 
     // `right` of 32 consecutive outputs lives one per lane and is broadcast with a shuffle one output
@@ -362,7 +362,9 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
 
     // (source-pair major: consecutive FFMA2s share their source operand, which the register operand reuse
     //  cache serves -- measured 127 vs 108 FMA lanes/clk/SM against the slot-major order)
-    auto fma_row = [&](uint32_t d0, uint32_t d1, const float4 (&w)[KSV / 2]) {
+    // fresh >= 0: slot `fresh` starts a new output with this row (its previous output was emitted just
+    // before), so its old contents are ignored instead of being zeroed separately.
+    auto fma_row = [&](uint32_t d0, uint32_t d1, const float4 (&w)[KSV / 2], int fresh) {
         float2 s[4];
         s[0] = make_float2(byte_to_float<0>(d0), byte_to_float<1>(d0));
         s[1] = make_float2(byte_to_float<2>(d0), byte_to_float<3>(d0));
@@ -374,7 +376,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             for (int j = 0; j < KV; ++j) {
                 const float4 ww = w[j >> 1];
                 const float2 wj = (j & 1) ? make_float2(ww.z, ww.w) : make_float2(ww.x, ww.y);
-                vacc[j][q] = __ffma2_rn(wj, s[q], vacc[j][q]);
+                vacc[j][q] = __ffma2_rn(wj, s[q], j == fresh ? make_float2(0.0f, 0.0f) : vacc[j][q]);
             }
         }
     };
@@ -390,8 +392,8 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
         for (int q = 0; q < 4; ++q) {
 #pragma unroll
             for (int j = 0; j < KV; ++j) {
-                const int t = (m - SV * (j + 1) + 2 * LV) % (LV > 0 ? LV : 1);
-                vacc[j][q] = __ffma2_rn(wt[t], s[q], vacc[j][q]);
+                const int t = (m - SV * (j + 1) + 2 * LV) % (LV > 0 ? LV : 1);  // t == 0: first row of a new output
+                vacc[j][q] = __ffma2_rn(wt[t], s[q], t == 0 ? make_float2(0.0f, 0.0f) : vacc[j][q]);
             }
         }
     };
@@ -419,8 +421,8 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                 float4 wa[KSV / 2], wc[KSV / 2];
 #pragma unroll
                 for (int jj = 0; jj < KSV / 2; ++jj) { wa[jj] = wrow[jj]; wc[jj] = wrow[KSV / 2 + jj]; }
-                fma_row(a0, a1, wa);
-                fma_row(c0, c1, wc);
+                fma_row(a0, a1, wa, -1);
+                fma_row(c0, c1, wc, -1);
                 if (in_stage == kStageRows - 2) stage_drained(stage);
                 rr += 2;
             } else {
@@ -429,7 +431,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                 float4 wa[KSV / 2];
 #pragma unroll
                 for (int jj = 0; jj < KSV / 2; ++jj) wa[jj] = wrow[jj];
-                fma_row(a0, a1, wa);
+                fma_row(a0, a1, wa, -1);
                 if (in_stage == kStageRows - 1) stage_drained(stage);
                 rr += 1;
             }
@@ -439,17 +441,13 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     auto emit_slot = [&](float2 (&a)[4]) {
         float* trow = reinterpret_cast<float*>(tmp + size_t(emitted) * geom.tmp_px);
         if (C == 4) {
-            if (v_active0) *reinterpret_cast<float4*>(trow + emit_off[0]) = make_float4(a[0].x, a[0].y, a[1].x, a[1].y);
-            if (v_active1) *reinterpret_cast<float4*>(trow + emit_off[4]) = make_float4(a[2].x, a[2].y, a[3].x, a[3].y);
+            *reinterpret_cast<float4*>(trow + emit_off[0]) = make_float4(a[0].x, a[0].y, a[1].x, a[1].y);
+            *reinterpret_cast<float4*>(trow + emit_off[4]) = make_float4(a[2].x, a[2].y, a[3].x, a[3].y);
         } else {
-            if (v_active0) {
-                trow[emit_off[0]] = a[0].x; trow[emit_off[1]] = a[0].y;
-                trow[emit_off[2]] = a[1].x; trow[emit_off[3]] = a[1].y;
-            }
-            if (v_active1) {
-                trow[emit_off[4]] = a[2].x; trow[emit_off[5]] = a[2].y;
-                trow[emit_off[6]] = a[3].x; trow[emit_off[7]] = a[3].y;
-            }
+            trow[emit_off[0]] = a[0].x; trow[emit_off[1]] = a[0].y;
+            trow[emit_off[2]] = a[1].x; trow[emit_off[3]] = a[1].y;
+            trow[emit_off[4]] = a[2].x; trow[emit_off[5]] = a[2].y;
+            trow[emit_off[6]] = a[3].x; trow[emit_off[7]] = a[3].y;
         }
         ++emitted;
     };
@@ -496,14 +494,13 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                                 float4 wa[KSV / 2];
 #pragma unroll
                                 for (int jj = 0; jj < KSV / 2; ++jj) wa[jj] = f_w[q * (KSV / 2) + jj];
-                                fma_row(a0, a1, wa);
+                                // row i == 0 of slot c's rows is the first row of the output that re-uses slot c - 1
+                                fma_row(a0, a1, wa, i == 0 ? (c + KV - 1) % KV : -1);
                             }
                             if (q == 3) stage_drained(f_stage);
                             rr += 1;
                         }
-                        emit_slot(vacc[c]);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) vacc[c][q] = make_float2(0.0f, 0.0f);
+                        emit_slot(vacc[c]);  // (the slot is not zeroed: its next row starts it afresh)
                         ++ov;
                         if (emitted == kTmpRows) {
                             c_start = (c + 1) % KV;
@@ -515,9 +512,11 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                 if (ov == oy1) goto vertical_done;
                 continue;
             }
-            if (SV > 0 && yend_stale) {  // back from uniform revolutions: look the next window end up again
-                yend_next = v_end_of(ov);
+            if (SV > 0 && yend_stale) {  // back from uniform revolutions: look the next window end up again,
+                yend_next = v_end_of(ov);  // and clear the slot the last revolution emitted last
                 yend_stale = false;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) vacc[KV - 1][q] = make_float2(0.0f, 0.0f);
             }
 #pragma unroll
             for (int c = 0; c < KV; ++c) {
@@ -562,7 +561,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             auto window_of = [&](int o) { return (o >= o_lo && o < oe) ? lr_tab[o] : make_int2(0, 0); };
             int2 lr_next = window_of(oh);
 
-            auto accumulate = [&](const float4& p, const float4* w) {
+            auto accumulate = [&](const float4& p, const float4* w, int fresh) {
                 const float2 ph[2] = {make_float2(p.x, p.y), make_float2(p.z, p.w)};
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
@@ -570,7 +569,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                     for (int j = 0; j < KH; ++j) {
                         const float4 ww = w[j >> 1];
                         const float2 wj = (j & 1) ? make_float2(ww.z, ww.w) : make_float2(ww.x, ww.y);
-                        hacc[j][q] = __ffma2_rn(wj, ph[q], hacc[j][q]);
+                        hacc[j][q] = __ffma2_rn(wj, ph[q], j == fresh ? make_float2(0.0f, 0.0f) : hacc[j][q]);
                     }
                 }
             };
@@ -596,19 +595,18 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
 #pragma unroll
                                         for (int j = 0; j < KH; ++j) {
                                             const int t = (c * SH + i - SH * (j + 1) + 2 * LH) % (LH > 0 ? LH : 1);
-                                            hacc[j][q] = __ffma2_rn(ht[t], ph[q], hacc[j][q]);
+                                            hacc[j][q] = __ffma2_rn(ht[t], ph[q], t == 0 ? make_float2(0.0f, 0.0f) : hacc[j][q]);
                                         }
                                     }
                                 } else {
                                     float4 w[KSH / 2];
 #pragma unroll
                                     for (int jj = 0; jj < KSH / 2; ++jj) w[jj] = wh[(c * SH + i) * (KSH / 2) + jj];
-                                    accumulate(p, w);
+                                    accumulate(p, w, i == 0 ? (c + KH - 1) % KH : -1);
                                 }
                             }
                             const float4 v = make_float4(hacc[c][0].x, hacc[c][0].y, hacc[c][1].x, hacc[c][1].y);
                             if (row_live && oh + c >= os) store_pixel<C>(d + c * C, v);
-                            hacc[c][0] = hacc[c][1] = make_float2(0.0f, 0.0f);
                         }
                         oh += KH;
                         x += KH * SH;
@@ -616,6 +614,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                         wh += KH * SH * (KSH / 2);
                         d += KH * C;
                     } while (oh + KH <= h_fast_hi);
+                    hacc[KH - 1][0] = hacc[KH - 1][1] = make_float2(0.0f, 0.0f);  // the other slots restarted themselves
                     lr_next = window_of(oh);
                 }
 #pragma unroll
@@ -629,8 +628,8 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                             float4 w0[KSH / 2], w1[KSH / 2];
 #pragma unroll
                             for (int jj = 0; jj < KSH / 2; ++jj) { w0[jj] = wh[jj]; w1[jj] = wh[KSH / 2 + jj]; }
-                            accumulate(p0v, w0);
-                            accumulate(p1v, w1);
+                            accumulate(p0v, w0, -1);
+                            accumulate(p1v, w1, -1);
                             x += 2; px += 2; wh += KSH;
                         }
                         if (x < xend) {
@@ -638,7 +637,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                             float4 w0[KSH / 2];
 #pragma unroll
                             for (int jj = 0; jj < KSH / 2; ++jj) w0[jj] = wh[jj];
-                            accumulate(p0v, w0);
+                            accumulate(p0v, w0, -1);
                             x += 1; px += 1; wh += KSH / 2;
                         }
                         if (oh >= os && row_live) {
