@@ -101,30 +101,35 @@ __device__ __forceinline__ float byte_to_float(uint32_t word) {
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440u + BYTE)) - 8388608.0f;
 }
 
-// clamp to [0,255] and round half away from zero (f32::round).  trunc(v + 0.5) equals round(v) for
-// every non-negative float except v = 0.5 - 2^-25 (the add rounds up to 1.0); this path's sums differ
-// from the reference's by FMA/association rounding anyway, and the EXACT path (generic.cu) has no such case.
-// clamp(v) + 0.5 == clamp(v + 0.5, 0.5, 255.5); adding 2^23 with round-toward-zero then leaves
-// floor(that) in the low mantissa byte, all on the FMA pipe (no F2I on the quarter-rate XU pipe).
-__device__ __forceinline__ uint32_t quantize_u8(float v) {
-    const float t = fminf(fmaxf(v + 0.5f, 0.5f), 255.5f);
-    return __float_as_uint(__fadd_rz(t, 8388608.0f));  // low byte = result; upper bytes = 0x4B0000
+// Quantise one finished pixel: clamp to [0,255] and round half away from zero (f32::round), as
+// trunc(v + 0.5) with saturation.  The + 0.5 is already in `v`: every horizontal accumulator starts at
+// 0.5 instead of 0.  trunc(v + 0.5) equals round(v) for every non-negative float except
+// v = 0.5 - 2^-25; this path's sums differ from the reference's by FMA/association rounding anyway, and
+// the EXACT path (generic.cu) has no such case.  float -> s32 (rz) followed by the saturating u8 pack
+// compiles to two F2IP.U8.F32.TRUNC for the whole pixel.
+__device__ __forceinline__ uint32_t pack_pixel(float4 v_plus_half) {
+    const int r = __float2int_rz(v_plus_half.x), g = __float2int_rz(v_plus_half.y);
+    const int b = __float2int_rz(v_plus_half.z), a = __float2int_rz(v_plus_half.w);
+    uint32_t hi, px;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(a), "r"(b), "r"(0));   // bytes: b, a
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(px) : "r"(g), "r"(r), "r"(hi));  // bytes: r, g, b, a
+    return px;
 }
+constexpr float kRoundBias = 0.5f;  // initial value of every horizontal accumulator
 
-// Quantise one finished pixel and store it straight to the destination raster.  Lanes of a half
-// warp hold 16 different rows of the same column, so these are scattered 4-byte (or 1-byte) stores;
-// the sectors are completed in L2 by the same thread's next pixels before they reach HBM.
+// Store one finished pixel straight to the destination raster.  Lanes of a half warp hold 16 different
+// rows of the same column, so these are scattered 4-byte (or 1-byte) stores; the sectors are completed
+// in L2 by the same thread's next pixels before they reach HBM.
 // (4-channel destinations are word aligned: the planner only sends those here.)
 template <int C>
-__device__ __forceinline__ void store_pixel(uint8_t* dst_px, float4 v) {
-    const uint32_t r = quantize_u8(v.x), g = quantize_u8(v.y), b = quantize_u8(v.z), a = quantize_u8(v.w);
+__device__ __forceinline__ void store_pixel(uint8_t* dst_px, float4 v_plus_half) {
+    const uint32_t w = pack_pixel(v_plus_half);
     if (C == 4) {
-        *reinterpret_cast<uint32_t*>(dst_px) = __byte_perm(__byte_perm(r, g, 0x0040), __byte_perm(b, a, 0x0040), 0x5410);
+        *reinterpret_cast<uint32_t*>(dst_px) = w;
     } else {
-        dst_px[0] = uint8_t(r);
-        if (C > 1) dst_px[1] = uint8_t(g);
-        if (C > 2) dst_px[2] = uint8_t(b);
-        if (C > 3) dst_px[3] = uint8_t(a);
+        dst_px[0] = uint8_t(w);
+        if (C > 1) dst_px[1] = uint8_t(w >> 8);
+        if (C > 2) dst_px[2] = uint8_t(w >> 16);
     }
 }
 
@@ -549,7 +554,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
         if (h_active) {
             float2 hacc[KH][2];
 #pragma unroll
-            for (int j = 0; j < KH; ++j) hacc[j][0] = hacc[j][1] = make_float2(0.0f, 0.0f);
+            for (int j = 0; j < KH; ++j) hacc[j][0] = hacc[j][1] = make_float2(kRoundBias, kRoundBias);
             int x = seg_lo - h_pre;
             const float4* px = my_row + x;
             const float4* wh = hw_smem + (x - xl) * (KSH / 2);
@@ -569,7 +574,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                     for (int j = 0; j < KH; ++j) {
                         const float4 ww = w[j >> 1];
                         const float2 wj = (j & 1) ? make_float2(ww.z, ww.w) : make_float2(ww.x, ww.y);
-                        hacc[j][q] = __ffma2_rn(wj, ph[q], j == fresh ? make_float2(0.0f, 0.0f) : hacc[j][q]);
+                        hacc[j][q] = __ffma2_rn(wj, ph[q], j == fresh ? make_float2(kRoundBias, kRoundBias) : hacc[j][q]);
                     }
                 }
             };
@@ -595,7 +600,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
 #pragma unroll
                                         for (int j = 0; j < KH; ++j) {
                                             const int t = (c * SH + i - SH * (j + 1) + 2 * LH) % (LH > 0 ? LH : 1);
-                                            hacc[j][q] = __ffma2_rn(ht[t], ph[q], t == 0 ? make_float2(0.0f, 0.0f) : hacc[j][q]);
+                                            hacc[j][q] = __ffma2_rn(ht[t], ph[q], t == 0 ? make_float2(kRoundBias, kRoundBias) : hacc[j][q]);
                                         }
                                     }
                                 } else {
@@ -614,7 +619,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                         wh += KH * SH * (KSH / 2);
                         d += KH * C;
                     } while (oh + KH <= h_fast_hi);
-                    hacc[KH - 1][0] = hacc[KH - 1][1] = make_float2(0.0f, 0.0f);  // the other slots restarted themselves
+                    hacc[KH - 1][0] = hacc[KH - 1][1] = make_float2(kRoundBias, kRoundBias);  // the other slots restarted themselves
                     lr_next = window_of(oh);
                 }
 #pragma unroll
@@ -644,7 +649,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                             const float4 v = make_float4(hacc[c][0].x, hacc[c][0].y, hacc[c][1].x, hacc[c][1].y);
                             store_pixel<C>(my_dst + size_t(oh) * C, v);
                         }
-                        hacc[c][0] = hacc[c][1] = make_float2(0.0f, 0.0f);
+                        hacc[c][0] = hacc[c][1] = make_float2(kRoundBias, kRoundBias);
                         ++oh;
                     }
                 }

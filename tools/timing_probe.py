@@ -19,5 +19,5 @@ L.ikc_debug_timing(out, 1)
 b.launch(s.cuda_stream); s.synchronize()
 L.ikc_debug_timing(out, 0)
 v = list(out); n = v[7]
-names = ["V(all)", "V:wait_full", "V:stage_drained", "H", "barriers", "-", "total"]
+names = ["V", "bar V->H", "H (all)", "H fast loop", "bar H->V", "-", "total"]
 print(wl, "CTAs", n, {k: round(x / n) for k, x in zip(names, v[:7])}, "cycles per CTA (thread 0)")
