@@ -587,6 +587,31 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
 #pragma unroll
                         for (int t = 0; t < LH; ++t) ht[t] = htap[t];
                     }
+                    if (RWH && oh < os) {
+                                // ---- pre-roll revolution: nothing is stored, and pixel m only matters to the slots
+                                // whose real output has started by then (slot j restarts at pixel SH * (j + 1))
+#pragma unroll
+                        for (int c = 1; c < KH; ++c) {
+#pragma unroll
+                            for (int i = 0; i < SH; ++i) {
+                                const float4 p = px[c * SH + i];
+                                const float2 ph[2] = {make_float2(p.x, p.y), make_float2(p.z, p.w)};
+#pragma unroll
+                                for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                                    for (int j = 0; j < c; ++j) {
+                                        const int t = (c * SH + i - SH * (j + 1) + 2 * LH) % (LH > 0 ? LH : 1);
+                                        hacc[j][q] = __ffma2_rn(ht[t], ph[q], t == 0 ? make_float2(kRoundBias, kRoundBias) : hacc[j][q]);
+                                    }
+                                }
+                            }
+                        }
+                        oh += KH;
+                        x += KH * SH;
+                        px += KH * SH;
+                        wh += KH * SH * (KSH / 2);
+                        d += KH * C;
+                    }
                     do {
 #pragma unroll
                         for (int c = 0; c < KH; ++c) {
