@@ -87,9 +87,17 @@ enum ikc_mode {
 #define IKC_MAX_DIM 65535u              /* per-axis bound on source and destination             */
 #define IKC_MAX_PIXELS (1ull << 28)     /* per-image bound on width*height (268 MP)             */
 
+/* Channel counts: 1=Luma, 2=LumaA, 3=Rgb, 4=Rgba.  Every `channels` argument may also carry a
+ * destination channel count of 3 or 4 in bits 8..15 (0 there = same as the source): the store then
+ * applies DynamicImage::to_rgb8() / to_rgba8() to the resized pixel (8-bit only), which
+ * encode_image otherwise does on the CPU before every encode (src/transform.rs:123,131,140):
+ * grey is replicated into r,g,b; alpha is the source's, or 255 if it has none; to_rgb8 drops it. */
+#define IKC_CHANNELS(src_channels, dst_channels) ((int)(src_channels) | ((int)(dst_channels) << 8))
+
 /* One resize of a batch.  Pointers are HOST pointers for ikc_resize_batch and DEVICE pointers
  * for ikc_batch_prepare.  Rows are `pitch` bytes apart, pixels are `channels` interleaved
- * samples (1=Luma, 2=LumaA, 3=Rgb, 4=Rgba).  `status` and `device` are written by the library. */
+ * samples (see IKC_CHANNELS; dst rows hold the destination channel count).  `status` and `device`
+ * are written by the library. */
 typedef struct ikc_job {
     const void* src;
     void* dst;
@@ -146,6 +154,14 @@ IKC_API uint32_t ikc_pass_table(int filter, uint32_t n_in, uint32_t n_out, uint3
 IKC_API int ikc_resize_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch,
                           int channels, uint8_t* dst, uint32_t dw, uint32_t dh, size_t dst_pitch,
                           int filter);
+
+/* ikc_resize_u8 followed by DynamicImage::to_rgb8() (dst_channels = 3) or to_rgba8() (dst_channels = 4)
+ * of the result, fused into the kernels' store: replaces the resize at src/transform.rs:85-89 plus the
+ * conversion at src/transform.rs:123/131 (jpeg, webp: rgb) or :140 (avif: rgba).  Same as passing
+ * IKC_CHANNELS(src_channels, dst_channels) to ikc_resize_u8.  dst rows hold dw * dst_channels bytes. */
+IKC_API int ikc_resize_convert_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch,
+                                  int src_channels, uint8_t* dst, uint32_t dw, uint32_t dh, size_t dst_pitch,
+                                  int dst_channels, int filter);
 
 /* Same for 16-bit samples (Luma16/LumaA16/Rgb16/Rgba16 as produced by the PNG decoder);
  * pitches in bytes. */

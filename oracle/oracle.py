@@ -112,6 +112,22 @@ def resize_exact(src: np.ndarray, dw: int, dh: int, filt: int = LANCZOS3) -> np.
     return dst[:, :, 0] if squeeze else dst
 
 
+def to_rgb8(img: np.ndarray) -> np.ndarray:
+    """DynamicImage::to_rgb8() of an 8-bit HxW / HxWxC raster (image 0.25.8 color conversions; used by
+    encode_image, src/transform.rs:123,131): grey replicated, alpha dropped."""
+    a = _as_hwc(img)
+    c = a.shape[2]
+    return np.ascontiguousarray(a[:, :, [0, 0, 0]] if c <= 2 else a[:, :, :3])
+
+
+def to_rgba8(img: np.ndarray) -> np.ndarray:
+    """DynamicImage::to_rgba8() (src/transform.rs:140): as to_rgb8 plus the source's alpha, or 255."""
+    a = _as_hwc(img)
+    c = a.shape[2]
+    alpha = a[:, :, c - 1:c] if c in (2, 4) else np.full(a.shape[:2] + (1,), 255, np.uint8)
+    return np.ascontiguousarray(np.concatenate([to_rgb8(a), alpha], axis=2))
+
+
 def vertical_f32(src: np.ndarray, dh: int, filt: int = LANCZOS3) -> np.ndarray:
     """The unclamped f32 intermediate of vertical_sample: dh x sw x C float32."""
     s = _as_hwc(src)

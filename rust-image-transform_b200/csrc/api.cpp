@@ -41,9 +41,12 @@ int guarded(F&& f) {
     }
 }
 
+// `ch` may carry the destination channel count in bits 8..15 (IKC_CHANNELS(src, dst)); 0 there = same as source.
 JobDesc make_desc(const void* src, uint32_t sw, uint32_t sh, size_t sp, int ch, void* dst, uint32_t dw, uint32_t dh,
                   size_t dp, int filter, int bps) {
-    return JobDesc{src, dst, sw, sh, dw, dh, sp, dp, ch, bps, filter};
+    const int out = (ch >> 8) & 0xff;
+    if (ch < 0 || (ch >> 16) != 0) fail(kInvalidArg, "bad channels value");
+    return JobDesc{src, dst, sw, sh, dw, dh, sp, dp, ch & 0xff, bps, filter, out};
 }
 
 }  // namespace
@@ -122,6 +125,21 @@ int ikc_resize_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, si
     }
     return guarded([&] {
         ctx->impl.resize_host(make_desc(src, sw, sh, src_pitch, channels, dst, dw, dh, dst_pitch, filter, 1), nullptr);
+    });
+}
+
+int ikc_resize_convert_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch, int src_channels,
+                          uint8_t* dst, uint32_t dw, uint32_t dh, size_t dst_pitch, int dst_channels, int filter) {
+    if (!ctx) {
+        set_last_error("ctx is null");
+        return IKC_ERR_INVALID_ARG;
+    }
+    return guarded([&] {
+        if (src_channels < 1 || src_channels > 255 || dst_channels < 0 || dst_channels > 255)
+            fail(kInvalidArg, "bad channel count");
+        ctx->impl.resize_host(make_desc(src, sw, sh, src_pitch, IKC_CHANNELS(src_channels, dst_channels), dst, dw, dh,
+                                        dst_pitch, filter, 1),
+                              nullptr);
     });
 }
 
@@ -208,8 +226,10 @@ int ikc_resize_u8_device(ikc_ctx* ctx, int device_index, void* stream, const uin
         check_cuda(cudaSetDevice(dev.ordinal()), "cudaSetDevice");
         JobDesc d = make_desc(d_src, sw, sh, src_pitch, channels, d_dst, dw, dh, dst_pitch, filter, 1);
         validate_job(d);
-        const size_t row = size_t(dw) * channels;
+        const size_t row = size_t(dw) * d.oc();
         if (dw == 0 || dh == 0) return;
+        if ((sw == 0 || sh == 0 || (sw == dw && sh == dh)) && d.oc() != d.channels)
+            fail(kUnsupported, "device entry point: empty or same-size rasters cannot be combined with a channel conversion");
         if (sw == 0 || sh == 0) {
             check_cuda(cudaMemset2DAsync(d_dst, dst_pitch, 0, row, dh, s), "memset");
             return;

@@ -61,13 +61,17 @@ void validate_job(const JobDesc& d) {
     if (d.channels > 4) fail(kUnsupported, "more than 4 interleaved channels is not supported");
     if (d.bps != 1 && d.bps != 2) fail(kUnsupported, "only 8- and 16-bit samples are supported");
     if (d.filter < 0 || d.filter > 4) fail(kInvalidArg, "unknown filter");
+    if (d.oc() != d.channels) {  // to_rgb8() / to_rgba8() fused into the store
+        if (d.oc() != 3 && d.oc() != 4) fail(kInvalidArg, "destination channels must equal the source's, or be 3 or 4");
+        if (d.bps != 1) fail(kUnsupported, "channel conversion is only available for 8-bit rasters");
+    }
     if (d.sw > kMaxDim || d.sh > kMaxDim || d.dw > kMaxDim || d.dh > kMaxDim)
         fail(kTooLarge, "image dimension exceeds IKC_MAX_DIM");
     if (uint64_t(d.sw) * d.sh > kMaxPixels || uint64_t(d.dw) * d.dh > kMaxPixels)
         fail(kTooLarge, "image area exceeds IKC_MAX_PIXELS");
     if (d.dw != 0 && d.dh != 0) {
         if (!d.dst) fail(kInvalidArg, "dst is null");
-        if (d.dst_pitch < size_t(d.dw) * d.channels * d.bps) fail(kInvalidArg, "dst_pitch smaller than a row");
+        if (d.dst_pitch < size_t(d.dw) * d.oc() * d.bps) fail(kInvalidArg, "dst_pitch smaller than a row");
         if (d.bps == 2 && (d.dst_pitch & 1)) fail(kInvalidArg, "dst_pitch must be even for 16-bit samples");
     }
     if (d.sw != 0 && d.sh != 0) {
@@ -256,7 +260,7 @@ bool cut_strips(const PassPlan& h, int ch, int sw, int max_src, int max_out, std
 
 // Cut a job into output tiles for the tile kernel and grow `geom` to cover their source footprints.
 // Returns false (and leaves the outputs untouched) when no tile shape fits the shared-memory budget.
-bool plan_tiles(const PassPlan& v, const PassPlan& h, int ch, int job, std::vector<WorkItem>* items, TileGeom* geom) {
+bool plan_tiles(const PassPlan& v, const PassPlan& h, int ch, int och, int job, std::vector<WorkItem>* items, TileGeom* geom) {
     const int dw = int(h.n_out), dh = int(v.n_out);
     auto footprint = [](const PassPlan& p, int n_out, int t) {  // widest source span of any tile of t outputs
         int worst = 0;
@@ -276,7 +280,7 @@ bool plan_tiles(const PassPlan& v, const PassPlan& h, int ch, int job, std::vect
                 TileGeom probe{};
                 probe.pitch_f = pitch; probe.max_src_rows = rows; probe.max_tile_rows = t_h; probe.max_tile_cols = t_w;
                 probe.vstride = int(v.stride); probe.hstride = int(h.stride);
-                probe.out_pitch_b = ((t_w * ch + 3) & ~3) + 4;
+                probe.out_pitch_b = ((t_w * och + 3) & ~3) + 4;
                 const size_t smem = tile_smem_bytes(probe);
                 if (smem <= limit) { best_tw = t_w; best_th = t_h; best_rows = rows; best_pitch = pitch; break; }
             }
@@ -295,7 +299,7 @@ bool plan_tiles(const PassPlan& v, const PassPlan& h, int ch, int job, std::vect
     if (geom->pitch_f != 0 && (geom->vstride != int(v.stride) || geom->hstride != int(h.stride))) return false;
     merged.vstride = int(v.stride);
     merged.hstride = int(h.stride);
-    merged.out_pitch_b = std::max(merged.out_pitch_b, ((best_tw * ch + 3) & ~3) + 4);
+    merged.out_pitch_b = std::max(merged.out_pitch_b, ((best_tw * och + 3) & ~3) + 4);
     if (tile_smem_bytes(merged) > (size_t(110) << 10)) return false;
     *geom = merged;
     for (int oy = 0; oy < dh; oy += best_th)
@@ -313,6 +317,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         std::vector<std::pair<int, int>> strips;
         int ch, kv, kh;
         int sv, sh;  // uniform steps the ring kernel has a specialised loop for, else 0
+        bool convert;
     };
     std::vector<Cand> cands;
     std::vector<WorkItem> tile_items;
@@ -335,6 +340,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
             j.dst_pitch = d.dst_pitch;
             j.sw = d.sw; j.sh = d.sh; j.dw = d.dw; j.dh = d.dh;
             j.channels = d.channels;
+            j.out_channels = d.oc();
             j.bps = d.bps;
             j.v = tv->pass;
             j.h = th->pass;
@@ -346,8 +352,8 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
             bool fused = !exact && d.bps == 1 && d.sh >= d.dh && d.sw >= d.dw &&
                          fused_supported(d.channels, tv->pass.ring_k, th->pass.ring_k) &&
                          (reinterpret_cast<uintptr_t>(d.src) & 15) == 0 && (d.src_pitch & 15) == 0 &&
-                         (d.channels != 4 || ((reinterpret_cast<uintptr_t>(d.dst) | d.dst_pitch) & 3) == 0);
-            Cand c{idx, {}, d.channels, tv->pass.ring_k, th->pass.ring_k, 0, 0};
+                         (d.oc() != 4 || ((reinterpret_cast<uintptr_t>(d.dst) | d.dst_pitch) & 3) == 0);
+            Cand c{idx, {}, d.channels, tv->pass.ring_k, th->pass.ring_k, 0, 0, d.oc() != d.channels};
             if (fused_has_uniform(d.channels, c.kv, c.kh, tv->pass.uni_step, th->pass.uni_step)) {
                 c.sv = tv->pass.uni_step;
                 c.sh = th->pass.uni_step;
@@ -358,7 +364,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
                                    &c.strips);
             }
             if (fused) cands.push_back(std::move(c));
-            else if (!exact && d.bps == 1 && plan_tiles(*tv->host, *th->host, d.channels, idx, &tile_items, &tile_geom)) {
+            else if (!exact && d.bps == 1 && plan_tiles(*tv->host, *th->host, d.channels, d.oc(), idx, &tile_items, &tile_geom)) {
                 // taken by the tile kernel
             } else {
                 lp.generic_jobs.push_back(idx);
@@ -402,9 +408,11 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         }
         FusedGroup* g = nullptr;
         for (auto& gg : lp.groups)
-            if (gg.channels == c.ch && gg.kv == c.kv && gg.kh == c.kh && gg.sv == c.sv && gg.sh == c.sh) g = &gg;
+            if (gg.channels == c.ch && gg.kv == c.kv && gg.kh == c.kh && gg.sv == c.sv && gg.sh == c.sh &&
+                gg.convert == c.convert)
+                g = &gg;
         if (!g) {
-            lp.groups.push_back(FusedGroup{c.ch, c.kv, c.kh, {}, {}, {}, c.sv, c.sh});
+            lp.groups.push_back(FusedGroup{c.ch, c.kv, c.kh, {}, {}, {}, c.sv, c.sh, c.convert});
             g = &lp.groups.back();
         }
         const PassPlan& hp = *lp.keepalive[size_t(c.job) * 2 + 1]->host;
@@ -456,7 +464,7 @@ void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, 
     for (auto& g : lp.groups) {
         const WorkItem* d_items = reinterpret_cast<const WorkItem*>(d_desc_base + off);
         if (g.kv == 0) check_cuda(launch_tile(d_jobs, d_items, g.tgeom, stream), "launch tile_kernel");
-        else check_cuda(launch_fused(g.channels, g.kv, g.kh, g.sv, g.sh, d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");
+        else check_cuda(launch_fused(g.channels, g.kv, g.kh, g.sv, g.sh, g.convert, d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");
         off += (sizeof(WorkItem) * g.items.size() + 15) & ~size_t(15);
         launches.fetch_add(1, std::memory_order_relaxed);
     }
@@ -505,7 +513,7 @@ struct HostJobState {  // one in-flight host job on a lane
 // except the pageable staging memcpy.  finish_host_job() completes it.
 void start_host_job(Context& ctx, Device& dev, Lane& l, const JobDesc& d, HostJobState* st, bool exact) {
     const size_t in_row = size_t(d.sw) * d.channels * d.bps;
-    const size_t out_row = size_t(d.dw) * d.channels * d.bps;
+    const size_t out_row = size_t(d.dw) * d.oc() * d.bps;
     st->d = d;
     st->in_pitch = device_pitch(in_row);
     st->out_pitch = device_pitch(out_row);
@@ -552,7 +560,7 @@ void finish_host_job(Lane& l, const HostJobState& st) {
     check_cuda(cudaStreamSynchronize(l.stream), "resize (stream sync)");
     if (st.out_staged) {
         const JobDesc& d = st.d;
-        const size_t out_row = size_t(d.dw) * d.channels * d.bps;
+        const size_t out_row = size_t(d.dw) * d.oc() * d.bps;
         const uint8_t* hp = static_cast<const uint8_t*>(l.h_out.p);
         if (d.dst_pitch == out_row) std::memcpy(d.dst, hp, out_row * d.dh);
         else for (uint32_t y = 0; y < d.dh; ++y)
@@ -563,9 +571,28 @@ void finish_host_job(Lane& l, const HostJobState& st) {
 // Cases imageops::resize answers without resampling.  Returns true if handled.
 bool trivial_resize(const JobDesc& d) {
     if (d.dw == 0 || d.dh == 0) return true;
-    const size_t out_row = size_t(d.dw) * d.channels * d.bps;
+    const size_t out_row = size_t(d.dw) * d.oc() * d.bps;
     if (d.sw == 0 || d.sh == 0) {  // nothing to sample from: zeroed ImageBuffer::new(nw, nh)
-        for (uint32_t y = 0; y < d.dh; ++y) std::memset(static_cast<uint8_t*>(d.dst) + size_t(y) * d.dst_pitch, 0, out_row);
+        const bool opaque = d.oc() == 4 && (d.channels == 1 || d.channels == 3);  // to_rgba8() of it: alpha = 255
+        for (uint32_t y = 0; y < d.dh; ++y) {
+            uint8_t* row = static_cast<uint8_t*>(d.dst) + size_t(y) * d.dst_pitch;
+            std::memset(row, 0, out_row);
+            if (opaque) for (uint32_t x = 0; x < d.dw; ++x) row[size_t(x) * 4 + 3] = 255;
+        }
+        return true;
+    }
+    if (d.sw == d.dw && d.sh == d.dh && d.oc() != d.channels) {  // same dimensions: the layout conversion alone
+        const int c = d.channels, co = d.oc();
+        for (uint32_t y = 0; y < d.dh; ++y) {
+            const uint8_t* s = static_cast<const uint8_t*>(d.src) + size_t(y) * d.src_pitch;
+            uint8_t* o = static_cast<uint8_t*>(d.dst) + size_t(y) * d.dst_pitch;
+            for (uint32_t x = 0; x < d.dw; ++x, s += c, o += co) {
+                o[0] = s[0];
+                o[1] = c >= 3 ? s[1] : s[0];
+                o[2] = c >= 3 ? s[2] : s[0];
+                if (co == 4) o[3] = (c == 2 || c == 4) ? s[c - 1] : 255;
+            }
+        }
         return true;
     }
     if (d.sw == d.dw && d.sh == d.dh) {  // same dimensions: plain copy

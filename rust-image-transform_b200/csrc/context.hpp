@@ -40,6 +40,8 @@ struct JobDesc {
     int channels;
     int bps;  // bytes per sample
     int filter;
+    int out_channels = 0;  // destination samples per pixel; 0 = same as `channels`
+    int oc() const { return out_channels ? out_channels : channels; }
 };
 
 // Device copy of one PassPlan; frees its memory when the last holder lets go.
@@ -57,6 +59,7 @@ struct FusedGroup {  // one kernel launch over a list of work items
     FusedGeom geom{};
     TileGeom tgeom{};
     int sv = 0, sh = 0;    // ring kernel: uniform vertical / horizontal step the launch is specialised for (0 = none)
+    bool convert = false;  // ring kernel: the jobs store another channel count than they read
 };
 
 // Everything needed to enqueue a set of device-resident jobs.

@@ -28,6 +28,8 @@ struct DevJob {
     uint64_t dst_pitch;    // bytes
     uint32_t sw, sh, dw, dh;
     int32_t channels;
+    int32_t out_channels;  // interleaved samples per destination pixel: == channels, or 3 / 4 when the store
+                           // applies DynamicImage::to_rgb8() / to_rgba8() (8-bit only)
     int32_t bps;           // bytes per sample: 1 or 2
     DevPass v, h;
 };

@@ -19,8 +19,18 @@
 #include "device_types.hpp"
 #include "launch.hpp"
 
+// This file is compiled twice: as itself (IKC_FUSED_CONV=0) -> the kernels that store the source's own
+// channel count (compile-time pixel stride) plus the host-side helpers and the dispatcher; and through
+// fused_conv.cu (IKC_FUSED_CONV=1) -> the same kernels with a run-time destination channel count
+// (to_rgb8()/to_rgba8() fused into the store).
+#ifndef IKC_FUSED_CONV
+#define IKC_FUSED_CONV 0
+#endif
+
 namespace ikc {
 namespace {
+
+constexpr bool kConv = IKC_FUSED_CONV != 0;
 
 // A CTA is four compute warps plus one producer warp that keeps the source ring full.  A compute
 // thread owns two 32-bit source words of every staged row.
@@ -120,16 +130,19 @@ constexpr float kRoundBias = 0.5f;  // initial value of every horizontal accumul
 // Store one finished pixel straight to the destination raster.  Lanes of a half warp hold 16 different
 // rows of the same column, so these are scattered 4-byte (or 1-byte) stores; the sectors are completed
 // in L2 by the same thread's next pixels before they reach HBM.
-// (4-channel destinations are word aligned: the planner only sends those here.)
+// `co` = destination channels: C, or the other of {3, 4} when the store applies DynamicImage::to_rgb8()
+// (drop alpha) / to_rgba8() (alpha = 255) -- src/transform.rs:123,131,140 does that on the CPU before
+// encoding.  4-channel destinations are word aligned: the planner only sends those here.
 template <int C>
-__device__ __forceinline__ void store_pixel(uint8_t* dst_px, float4 v_plus_half) {
-    const uint32_t w = pack_pixel(v_plus_half);
-    if (C == 4) {
+__device__ __forceinline__ void store_pixel(uint8_t* dst_px, float4 v_plus_half, int co) {
+    uint32_t w = pack_pixel(v_plus_half);
+    if (co == 4) {
+        if (C == 3) w |= 0xff000000u;
         *reinterpret_cast<uint32_t*>(dst_px) = w;
     } else {
         dst_px[0] = uint8_t(w);
-        if (C > 1) dst_px[1] = uint8_t(w >> 8);
-        if (C > 2) dst_px[2] = uint8_t(w >> 16);
+        dst_px[1] = uint8_t(w >> 8);
+        dst_px[2] = uint8_t(w >> 16);
     }
 }
 
@@ -156,7 +169,7 @@ __device__ __forceinline__ void store_pixel(uint8_t* dst_px, float4 v_plus_half)
 // The ring is addressed by "virtual rows": chunk row r lives at virtual row rr = r + p0, ring row
 // rr % 16, stage (rr / 4) % 4.  p0 in [0,4) shifts the stage boundaries so that the first uniform
 // revolution starts on one; the first stage then simply holds 4 - p0 rows.
-template <int C, int KV, int KH, int SV, int SH>
+template <int C, int KV, int KH, int SV, int SH, bool CONV>
 __global__ void __launch_bounds__(kThreads, 2)
 fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, const FusedGeom geom) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -298,6 +311,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     const float4* const my_row = tmp + size_t(hrow) * geom.tmp_px - pxb;  // indexed by absolute source pixel
     uint8_t* const dst_base = J->dst;
     const size_t dst_pitch = J->dst_pitch;
+    const int CO = CONV ? J->out_channels : C;  // destination channels (3 or 4)
     bool hw_ready = false;
     // [h_fast_lo, h_fast_hi): whole revolutions of this segment inside the pass's uniform stretch.
     int h_fast_lo = 0, h_fast_hi = 0, h_pre = 0;
@@ -581,7 +595,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
             for (;;) {
                 if (SH > 0 && hc_start == 0 && oh >= h_fast_lo && oh + KH <= h_fast_hi && (oh < os || x + SH == lr_next.y)) {
                     // ---- uniform stretch: every slot finishes after exactly SH more pixels
-                    uint8_t* d = my_dst + ptrdiff_t(oh) * C;
+                    uint8_t* d = my_dst + ptrdiff_t(oh) * CO;
                     float2 ht[RWH ? LH : 1];
                     if (RWH) {
 #pragma unroll
@@ -610,7 +624,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                         x += KH * SH;
                         px += KH * SH;
                         wh += KH * SH * (KSH / 2);
-                        d += KH * C;
+                        d += KH * CO;
                     }
                     do {
 #pragma unroll
@@ -636,13 +650,13 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                                 }
                             }
                             const float4 v = make_float4(hacc[c][0].x, hacc[c][0].y, hacc[c][1].x, hacc[c][1].y);
-                            if (row_live && oh + c >= os) store_pixel<C>(d + c * C, v);
+                            if (row_live && oh + c >= os) store_pixel<C>(d, v, CO);
+                            d += CO;
                         }
                         oh += KH;
                         x += KH * SH;
                         px += KH * SH;
                         wh += KH * SH * (KSH / 2);
-                        d += KH * C;
                     } while (oh + KH <= h_fast_hi);
                     hacc[KH - 1][0] = hacc[KH - 1][1] = make_float2(kRoundBias, kRoundBias);  // the other slots restarted themselves
                     lr_next = window_of(oh);
@@ -672,7 +686,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
                         }
                         if (oh >= os && row_live) {
                             const float4 v = make_float4(hacc[c][0].x, hacc[c][0].y, hacc[c][1].x, hacc[c][1].y);
-                            store_pixel<C>(my_dst + size_t(oh) * C, v);
+                            store_pixel<C>(my_dst + size_t(oh) * CO, v, CO);
                         }
                         hacc[c][0] = hacc[c][1] = make_float2(kRoundBias, kRoundBias);
                         ++oh;
@@ -690,6 +704,7 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
 
 // ---- launcher ---------------------------------------------------------------------------------
 
+#if !IKC_FUSED_CONV
 size_t fused_smem_bytes(int /*channels*/, int kv, int kh, const FusedGeom& g) {
     const size_t ksv = size_t((kv + 1) & ~1), ksh = size_t((kh + 1) & ~1);
     return size_t(kHeaderBytes) + size_t(kRingRows) * kSrcRowBytes + size_t(kRingRows) * ksv * 8 +
@@ -710,22 +725,33 @@ bool fused_has_uniform(int channels, int kv, int kh, int step_v, int step_h) {
     return fused_supported(channels, kv, kh) && kv == 6 && kh == 6 && step_v == step_h && (step_v == 2 || step_v == 4);
 }
 
+#endif  // !IKC_FUSED_CONV
+
 template <int C, int KV, int KH, int SV, int SH>
 static cudaError_t launch_one(const DevJob* jobs, const WorkItem* items, const FusedGeom& geom, cudaStream_t stream) {
     const size_t smem = fused_smem_bytes(C, KV, KH, geom);
     // Opt in to > 48 KB dynamic shared memory (per device; cheap, so done on every launch).
-    cudaError_t e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH, SV, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         int(smem));
+    cudaError_t e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH, SV, SH, kConv>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH, SV, SH>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH, SV, SH, kConv>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    fused_ring_kernel<C, KV, KH, SV, SH><<<geom.n_items, kThreads, smem, stream>>>(jobs, items, geom);
+    fused_ring_kernel<C, KV, KH, SV, SH, kConv><<<geom.n_items, kThreads, smem, stream>>>(jobs, items, geom);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fused(int channels, int kv, int kh, int sv, int sh, const DevJob* jobs, const WorkItem* items,
-                         const FusedGeom& geom, cudaStream_t stream) {
+#if IKC_FUSED_CONV
+cudaError_t launch_fused_conv(int channels, int kv, int kh, int sv, int sh, const DevJob* jobs, const WorkItem* items,
+                              const FusedGeom& geom, cudaStream_t stream) {
+#else
+cudaError_t launch_fused_conv(int channels, int kv, int kh, int sv, int sh, const DevJob* jobs, const WorkItem* items,
+                              const FusedGeom& geom, cudaStream_t stream);  // fused_conv.cu
+
+cudaError_t launch_fused(int channels, int kv, int kh, int sv, int sh, bool convert, const DevJob* jobs,
+                         const WorkItem* items, const FusedGeom& geom, cudaStream_t stream) {
+    if (convert) return launch_fused_conv(channels, kv, kh, sv, sh, jobs, items, geom, stream);
+#endif
 #define IKC_CASE(C_, KV_, KH_, SV_, SH_)                                    \
     if (channels == C_ && kv == KV_ && kh == KH_ && sv == SV_ && sh == SH_) \
         return launch_one<C_, KV_, KH_, SV_, SH_>(jobs, items, geom, stream);

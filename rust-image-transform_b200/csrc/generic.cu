@@ -40,15 +40,30 @@ __global__ void __launch_bounds__(256) vertical_generic(const DevJob job) {
     job.tmp[size_t(oy) * ncol + col] = acc;
 }
 
+// One thread per destination sample.  With a channel conversion (out_channels != channels, 8-bit only:
+// DynamicImage::to_rgb8() / to_rgba8()) destination channel oc reads source channel c: grey replicated
+// into r, g, b; alpha from the source when it has one, else the constant 255.
 template <typename T, bool EXACT>
 __global__ void __launch_bounds__(256) horizontal_generic(const DevJob job) {
-    const uint32_t ch = uint32_t(job.channels);
-    const uint32_t nout = job.dw * ch;
+    const uint32_t ch = uint32_t(job.channels), och = uint32_t(job.out_channels);
+    const uint32_t nout = job.dw * och;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t oy = blockIdx.y;
     if (idx >= nout) return;
-    const uint32_t ox = idx / ch;
-    const uint32_t c = idx - ox * ch;
+    const uint32_t ox = idx / och;
+    const uint32_t oc = idx - ox * och;
+    uint32_t c = oc;
+    if (och != ch) {
+        if (oc == 3) {
+            if (ch == 1 || ch == 3) {
+                *reinterpret_cast<T*>(job.dst + size_t(oy) * job.dst_pitch + size_t(idx) * sizeof(T)) = T(255);
+                return;
+            }
+            c = ch - 1;
+        } else if (ch < 3) {
+            c = 0;
+        }
+    }
     const int first = job.h.left[ox];
     const int taps = job.h.right[ox] - first;
     const float* __restrict__ w = job.h.w + size_t(ox) * job.h.stride;
@@ -66,7 +81,7 @@ __global__ void __launch_bounds__(256) horizontal_generic(const DevJob job) {
 
 cudaError_t launch_generic(const DevJob& job, bool exact, cudaStream_t stream) {
     const uint32_t ncol = job.sw * uint32_t(job.channels);
-    const uint32_t nout = job.dw * uint32_t(job.channels);
+    const uint32_t nout = job.dw * uint32_t(job.out_channels);
     const dim3 block(256);
     const dim3 gv((ncol + 255) / 256, job.dh);
     const dim3 gh((nout + 255) / 256, job.dh);

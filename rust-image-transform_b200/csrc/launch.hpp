@@ -19,8 +19,9 @@ size_t fused_smem_bytes(int channels, int ring_k_v, int ring_k_h, const FusedGeo
 // True when the kernel has loops specialised for these uniform steps (PassPlan::uni_step of both passes).
 bool fused_has_uniform(int channels, int ring_k_v, int ring_k_h, int step_v, int step_h);
 // step_v / step_h: uniform steps the launch is specialised for (both 0: general loops only).
-cudaError_t launch_fused(int channels, int ring_k_v, int ring_k_h, int step_v, int step_h, const DevJob* jobs,
-                         const WorkItem* items, const FusedGeom& geom, cudaStream_t stream);
+// convert: the jobs of the launch store a different channel count than they read (DevJob::out_channels).
+cudaError_t launch_fused(int channels, int ring_k_v, int ring_k_h, int step_v, int step_h, bool convert,
+                         const DevJob* jobs, const WorkItem* items, const FusedGeom& geom, cudaStream_t stream);
 
 // Tile kernel (tile.cu): output-stationary fused passes over shared-memory tiles.
 size_t tile_smem_bytes(const TileGeom& geom);

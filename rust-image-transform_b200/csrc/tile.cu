@@ -41,6 +41,7 @@ tile_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items,
     const WorkItem it = items[blockIdx.x];
     const DevJob& J = jobs[it.job];
     const int C = J.channels;
+    const int CO = J.out_channels;  // == C, or 3 / 4: DynamicImage::to_rgb8() / to_rgba8() applied by the store
     const int ox0 = it.ox0, ox1 = it.ox1, oy0 = it.oy0, oy1 = it.oy1;
     const int tw = ox1 - ox0, th = oy1 - oy0;
     const int tid = threadIdx.x;
@@ -146,22 +147,31 @@ tile_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items,
         } else {
             for (int i = 0; i < win.y; ++i) a0 = fmaf(t[i], w[i], a0);
         }
-        uint8_t* d = out_s + oyl * out_pitch + oxl * C;
-        d[0] = uint8_t(quantize_u8_tile(a0));
-        if (C > 1) d[1] = uint8_t(quantize_u8_tile(a1));
-        if (C > 2) d[2] = uint8_t(quantize_u8_tile(a2));
-        if (C > 3) d[3] = uint8_t(quantize_u8_tile(a3));
+        uint8_t* d = out_s + oyl * out_pitch + oxl * CO;
+        const uint8_t q0 = uint8_t(quantize_u8_tile(a0)), q1 = uint8_t(quantize_u8_tile(a1));
+        const uint8_t q2 = uint8_t(quantize_u8_tile(a2)), q3 = uint8_t(quantize_u8_tile(a3));
+        if (CO == C) {
+            d[0] = q0;
+            if (C > 1) d[1] = q1;
+            if (C > 2) d[2] = q2;
+            if (C > 3) d[3] = q3;
+        } else {  // Luma(A) replicates its grey into r, g, b; alpha is the source's or 255
+            d[0] = q0;
+            d[1] = C >= 3 ? q1 : q0;
+            d[2] = C >= 3 ? q2 : q0;
+            if (CO == 4) d[3] = C == 2 ? q1 : 255;
+        }
     }
     __syncthreads();
 
     // ---- store the tile: whole 32-bit words where the destination allows, bytes at the ragged ends
     {
-        const int row_bytes = tw * C;
+        const int row_bytes = tw * CO;
         const int warp = tid >> 5, lane = tid & 31;
         for (int row = warp; row < th; row += kTileThreads / 32) {
             const uint8_t* sb = out_s + row * out_pitch;
             const uint32_t* sw_ = reinterpret_cast<const uint32_t*>(sb);
-            uint8_t* g = J.dst + size_t(oy0 + row) * J.dst_pitch + size_t(ox0) * C;
+            uint8_t* g = J.dst + size_t(oy0 + row) * J.dst_pitch + size_t(ox0) * CO;
             const int head = min(row_bytes, int((4 - (reinterpret_cast<uintptr_t>(g) & 3)) & 3));
             const int nwords = (row_bytes - head) >> 2;
             if (lane < head) g[lane] = sb[lane];

@@ -23,7 +23,7 @@ MAX_DIM, MAX_PIXELS = 65535, 1 << 28  # IKC_MAX_DIM, IKC_MAX_PIXELS
 EXPORTS = [
     "ikc_create", "ikc_destroy", "ikc_device_count", "ikc_set_mode", "ikc_get_mode", "ikc_kernel_launches",
     "ikc_last_error", "ikc_version", "ikc_target_dims", "ikc_pass_table", "ikc_resize_u8", "ikc_resize_u16",
-    "ikc_resize_image_u8", "ikc_resize_batch", "ikc_host_alloc", "ikc_host_free", "ikc_resize_u8_device",
+    "ikc_resize_convert_u8", "ikc_resize_image_u8", "ikc_resize_batch", "ikc_host_alloc", "ikc_host_free", "ikc_resize_u8_device",
     "ikc_batch_prepare", "ikc_batch_launch", "ikc_batch_launch_count", "ikc_batch_describe", "ikc_batch_free",
 ]
 
@@ -74,6 +74,8 @@ def load() -> C.CDLL:
     L.ikc_pass_table.restype = u32
     L.ikc_resize_u8.argtypes = [vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32]
     L.ikc_resize_u8.restype = i32
+    L.ikc_resize_convert_u8.argtypes = [vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32, i32]
+    L.ikc_resize_convert_u8.restype = i32
     L.ikc_resize_u16.argtypes = [vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32]
     L.ikc_resize_u16.restype = i32
     L.ikc_resize_image_u8.argtypes = [vp, vp, u32, u32, i32, i32, u32, i32, u32, vp, sz, pu32, pu32]

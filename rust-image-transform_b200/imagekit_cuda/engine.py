@@ -116,8 +116,11 @@ class Context:
 
     # ---- host-buffer entry points -------------------------------------------------------------
     def resize(self, src: np.ndarray, dw: int, dh: int, filt: int = _lib.FILTER_LANCZOS3,
-               out: np.ndarray | None = None) -> np.ndarray:
-        """imageops::resize(src, dw, dh, filt) on HxWxC (or HxW) u8/u16 host arrays."""
+               out: np.ndarray | None = None, out_channels: int | None = None) -> np.ndarray:
+        """imageops::resize(src, dw, dh, filt) on HxWxC (or HxW) u8/u16 host arrays.  out_channels = 3 / 4
+        additionally applies to_rgb8() / to_rgba8() to the result inside the kernels' store (u8 only)."""
+        if out_channels is not None:
+            return self._resize_convert(src, dw, dh, filt, out, out_channels)
         squeeze = src.ndim == 2
         s = src[:, :, None] if squeeze else src
         if s.ndim != 3:
@@ -141,6 +144,19 @@ class Context:
         if out is not None:
             return out
         return dst[:, :, 0] if squeeze else dst
+
+    def _resize_convert(self, src, dw, dh, filt, out, co):
+        s = np.ascontiguousarray(src[:, :, None] if src.ndim == 2 else src)
+        if s.ndim != 3 or s.dtype != np.uint8:
+            raise ImageKitError(_lib.ERR_UNSUPPORTED, "channel conversion needs an 8-bit HxW or HxWxC array")
+        sh, sw, ch = s.shape
+        if dw > _lib.MAX_DIM or dh > _lib.MAX_DIM or dw * dh > _lib.MAX_PIXELS:
+            raise ImageKitError(_lib.ERR_TOO_LARGE, "requested size exceeds IKC_MAX_DIM / IKC_MAX_PIXELS")
+        dst = out if out is not None else np.empty((dh, dw, co), np.uint8)
+        assert dst.shape == (dh, dw, co) and dst.dtype == np.uint8 and dst.flags.c_contiguous
+        _check(_lib.load().ikc_resize_convert_u8(self._h, s.ctypes.data, sw, sh, sw * ch, ch, dst.ctypes.data, dw, dh,
+                                                 dw * co, co, filt))
+        return dst
 
     def resize_image(self, src: np.ndarray, w: int | None, h: int | None) -> np.ndarray:
         """resize_image(img, w, h) for a tight 8-bit raster through ikc_resize_image_u8."""

@@ -196,3 +196,44 @@ def test_threads_share_one_context(ctx, ik, oracle):
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs, errs
+
+
+# ---- to_rgb8() / to_rgba8() fused into the store (src/transform.rs:123,131,140) ----------------
+CONVERT_CASES = [  # (h, w, c, dw, dh, filter, out_channels): ring kernel, tile kernel, both conversions, all variants
+    (2160, 3840, 4, 1920, 1080, 4, 3), (1080, 1920, 3, 400, 225, 4, 4), (600, 800, 4, 400, 300, 4, 3),
+    (600, 800, 3, 400, 300, 4, 4), (777, 1031, 3, 515, 388, 4, 4), (901, 1200, 4, 411, 309, 4, 3),
+    (240, 320, 3, 640, 480, 2, 4), (240, 320, 4, 640, 480, 2, 3), (300, 200, 1, 100, 150, 4, 3),
+    (300, 200, 1, 100, 150, 4, 4), (300, 200, 2, 100, 150, 1, 3), (300, 200, 2, 100, 150, 1, 4),
+    (64, 64, 2, 128, 128, 0, 4), (480, 640, 3, 200, 150, 3, 4),
+]
+
+
+@pytest.mark.parametrize("case", CONVERT_CASES)
+@pytest.mark.parametrize("mode", ["fast", "exact"])
+def test_resize_with_fused_channel_conversion(ctx, ik, oracle, case, mode):
+    h, w, c, dw, dh, filt, co = case
+    if mode == "exact" and h * w > 2_000_000:
+        pytest.skip("large shapes run in fast mode only")
+    src = splitmix_noise((h, w, c), image_id=co)
+    ctx.set_mode(ik.MODE_EXACT if mode == "exact" else ik.MODE_FAST)
+    got = ctx.resize(src, dw, dh, filt, out_channels=co)
+    resized = oracle.resize_exact(src, dw, dh, filt)
+    want = oracle.to_rgb8(resized) if co == 3 else oracle.to_rgba8(resized)
+    assert got.shape == want.shape == (dh, dw, co)
+    if mode == "exact":
+        assert np.array_equal(got, want), delta_histogram(got, want)
+    else:
+        _check_fast(got, want, (case, mode), max_off=0.002)
+    ctx.set_mode(ik.MODE_FAST)
+
+
+def test_channel_conversion_trivial_cases(ctx, ik, oracle):
+    src = splitmix_noise((40, 50, 3), image_id=5)
+    same = ctx.resize(src, 50, 40, ik.FILTER_LANCZOS3, out_channels=4)      # same size: conversion only
+    assert np.array_equal(same, oracle.to_rgba8(src))
+    grey = splitmix_noise((40, 50, 2), image_id=6)
+    assert np.array_equal(ctx.resize(grey, 50, 40, ik.FILTER_LANCZOS3, out_channels=3), oracle.to_rgb8(grey))
+    with pytest.raises(ik.ImageKitError):
+        ctx.resize(src, 20, 20, ik.FILTER_LANCZOS3, out_channels=2)         # only rgb / rgba destinations
+    with pytest.raises(ik.ImageKitError):
+        ctx.resize(src.astype(np.uint16), 20, 20, ik.FILTER_LANCZOS3, out_channels=4)
