@@ -40,6 +40,8 @@ extern "C" {
     pub fn ikc_target_dims(ow: u32, oh: u32, has_w: c_int, w: u32, has_h: c_int, h: u32, tw: *mut u32, th: *mut u32) -> c_int;
     pub fn ikc_resize_u8(ctx: *mut ikc_ctx, src: *const u8, sw: u32, sh: u32, src_pitch: usize, channels: c_int,
                          dst: *mut u8, dw: u32, dh: u32, dst_pitch: usize, filter: c_int) -> c_int;
+    pub fn ikc_resize_convert_u8(ctx: *mut ikc_ctx, src: *const u8, sw: u32, sh: u32, src_pitch: usize, src_channels: c_int,
+                                 dst: *mut u8, dw: u32, dh: u32, dst_pitch: usize, dst_channels: c_int, filter: c_int) -> c_int;
     pub fn ikc_resize_u16(ctx: *mut ikc_ctx, src: *const u16, sw: u32, sh: u32, src_pitch: usize, channels: c_int,
                           dst: *mut u16, dw: u32, dh: u32, dst_pitch: usize, filter: c_int) -> c_int;
     pub fn ikc_resize_batch(ctx: *mut ikc_ctx, jobs: *mut ikc_job, n: usize) -> c_int;

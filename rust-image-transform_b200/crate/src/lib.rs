@@ -94,3 +94,40 @@ pub fn resize_image(img: DynamicImage, w: Option<u32>, h: Option<u32>) -> Result
         _ => Err("unsupported pixel format (f32 rasters)".to_string()),
     }
 }
+
+/// `resize_image` for a caller that is about to encode the result (the `/img` and `/upload` handlers,
+/// src/lib.rs:180-186 and :286-292): `rgba = false` for jpeg/webp, `true` for avif.  The resize stores the
+/// variant `encode_image` converts to anyway (`to_rgb8()` / `to_rgba8()`, src/transform.rs:123,131,140), so
+/// that conversion becomes a no-op and an RGBA source sends 25 % fewer bytes back from the GPU.
+/// 16-bit rasters and the no-resample cases fall through to `resize_image`.
+pub fn resize_image_for(img: DynamicImage, w: Option<u32>, h: Option<u32>, rgba: bool) -> Result<DynamicImage, String> {
+    let (ow, oh) = img.dimensions();
+    let (mut tw, mut th) = (0u32, 0u32);
+    let code = unsafe {
+        ffi::ikc_target_dims(ow, oh, w.is_some() as i32, w.unwrap_or(0), h.is_some() as i32, h.unwrap_or(0), &mut tw, &mut th)
+    };
+    let (raw, ch): (&[u8], u32) = match &img {
+        DynamicImage::ImageLuma8(b) => (b.as_raw(), 1),
+        DynamicImage::ImageLumaA8(b) => (b.as_raw(), 2),
+        DynamicImage::ImageRgb8(b) => (b.as_raw(), 3),
+        DynamicImage::ImageRgba8(b) => (b.as_raw(), 4),
+        _ => return resize_image(img, w, h),
+    };
+    let co: u32 = if rgba { 4 } else { 3 };
+    if (w.is_none() && h.is_none()) || code != ffi::IKC_DIMS_RESAMPLE || co == ch {
+        return resize_image(img, w, h);
+    }
+    let mut out = vec![0u8; tw as usize * th as usize * co as usize];
+    let rc = unsafe {
+        ffi::ikc_resize_convert_u8(ctx()?, raw.as_ptr(), ow, oh, (ow * ch) as usize, ch as i32, out.as_mut_ptr(), tw, th,
+                                   (tw * co) as usize, co as i32, ffi::IKC_FILTER_LANCZOS3)
+    };
+    if rc != ffi::IKC_OK {
+        return Err(last_error());
+    }
+    Ok(if rgba {
+        DynamicImage::ImageRgba8(ImageBuffer::from_raw(tw, th, out).expect("size matches"))
+    } else {
+        DynamicImage::ImageRgb8(ImageBuffer::from_raw(tw, th, out).expect("size matches"))
+    })
+}

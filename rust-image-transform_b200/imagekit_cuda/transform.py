@@ -120,10 +120,17 @@ def decode_image(data: bytes):
     return DynamicImage(arr), fmt
 
 
-def resize_image(img: DynamicImage, w: int | None, h: int | None, ctx=None) -> DynamicImage:
+def resize_image(img: DynamicImage, w: int | None, h: int | None, ctx=None,
+                 encode_as: ImageFormat | None = None) -> DynamicImage:
     """transform.rs:62-90.  (None, None) returns the image untouched; otherwise the target size
     follows the reference's f32 rule, DynamicImage::resize fits it within (aspect preserved) and the
-    raster is resampled with Lanczos3 -- on the GPU, through ikc_resize_u8 / ikc_resize_u16."""
+    raster is resampled with Lanczos3 -- on the GPU, through ikc_resize_u8 / ikc_resize_u16.
+
+    encode_as (optional, not in the reference's signature): the format the caller is about to pass to
+    encode_image.  The resize then stores what encode_image would convert to anyway -- to_rgb8() for
+    jpeg/webp, to_rgba8() for avif (transform.rs:123,131,140) -- so the CPU conversion pass disappears
+    and an RGBA source going to jpeg/webp sends 25 % fewer bytes back over PCIe.  8-bit rasters only;
+    the result encodes to the same bytes as the unfused path."""
     if w is None and h is None:
         return img
     for v in (w, h):
@@ -134,7 +141,12 @@ def resize_image(img: DynamicImage, w: int | None, h: int | None, ctx=None) -> D
     if code != _lib.DIMS_RESAMPLE:
         return img.clone()
     ctx = ctx or default_context()
-    out = ctx.resize(img.pixels, tw, th, _lib.FILTER_LANCZOS3)
+    oc = None
+    if encode_as is not None and img.pixels.dtype == np.uint8:
+        oc = 4 if encode_as == ImageFormat.avif else 3
+        if oc == img.pixels.shape[2]:
+            oc = None
+    out = ctx.resize(img.pixels, tw, th, _lib.FILTER_LANCZOS3, out_channels=oc)
     return DynamicImage(out)
 
 

@@ -237,3 +237,15 @@ def test_channel_conversion_trivial_cases(ctx, ik, oracle):
         ctx.resize(src, 20, 20, ik.FILTER_LANCZOS3, out_channels=2)         # only rgb / rgba destinations
     with pytest.raises(ik.ImageKitError):
         ctx.resize(src.astype(np.uint16), 20, 20, ik.FILTER_LANCZOS3, out_channels=4)
+
+
+def test_resize_image_encode_as_matches_unfused_path(ctx, ik):
+    """resize_image(..., encode_as=f) must hand encode_image the bytes to_rgb8()/to_rgba8() would have produced."""
+    rgba = ik.DynamicImage(splitmix_noise((300, 400, 4), image_id=11))
+    grey = ik.DynamicImage(splitmix_noise((300, 400, 1), image_id=12))
+    for img in (rgba, grey):
+        plain = ik.resize_image(img, 200, None, ctx=ctx)
+        for fmt, conv in ((ik.ImageFormat.jpeg, "to_rgb8"), (ik.ImageFormat.webp, "to_rgb8"), (ik.ImageFormat.avif, "to_rgba8")):
+            fused = ik.resize_image(img, 200, None, ctx=ctx, encode_as=fmt)
+            assert np.array_equal(getattr(fused, conv)(), getattr(plain, conv)())
+            assert fused.pixels.shape[2] == (4 if fmt == ik.ImageFormat.avif else 3)
