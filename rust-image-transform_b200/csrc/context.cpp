@@ -143,11 +143,12 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     const size_t b_idx = up(sizeof(int32_t) * n_out);
     const size_t b_w = up(sizeof(float) * host->w.size());
     const size_t b_ring = up(sizeof(float) * host->ring.size());
+    const size_t b_up2 = up(sizeof(float) * host->up2_pairs.size());
     auto t = std::make_shared<DevTables>();
     t->device = ordinal_;
     t->host = host;
     check_cuda(cudaSetDevice(ordinal_), "cudaSetDevice");
-    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + b_ring + 256), "cudaMalloc(weight tables)");
+    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + b_ring + b_up2 + 256), "cudaMalloc(weight tables)");
     uint8_t* p = static_cast<uint8_t*>(t->base);
     auto put = [&](const void* src, size_t bytes, size_t slot) {
         uint8_t* at = p;
@@ -163,6 +164,10 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     t->pass.w = reinterpret_cast<const float*>(put(host->w.data(), sizeof(float) * host->w.size(), b_w));
     const uint8_t* ring = put(host->ring.data(), sizeof(float) * host->ring.size(), b_ring);
     t->pass.ring = host->ring.empty() ? nullptr : reinterpret_cast<const float*>(ring);
+    const uint8_t* up2 = put(host->up2_pairs.data(), sizeof(float) * host->up2_pairs.size(), b_up2);
+    t->pass.up2_pairs = host->up2_pairs.empty() ? nullptr : reinterpret_cast<const float2*>(up2);
+    t->pass.up2_off = host->up2_off;
+    t->pass.up2_taps = host->up2_taps;
     t->pass.stride = int32_t(host->stride);
     t->pass.ring_k = host->ring_k;
     t->pass.ring_stride = host->ring_stride;
@@ -363,8 +368,23 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
                 fused = cut_strips(*th->host, d.channels, int(d.sw), fused_max_src_bytes(d.channels), max_out,
                                    &c.strips);
             }
+            const bool up2 = !fused && !exact && d.bps == 1 && d.oc() == d.channels && d.dw == 2 * d.sw && d.dh == 2 * d.sh &&
+                             tv->pass.up2_pairs && th->pass.up2_pairs &&
+                             up2_supported(d.channels, tv->pass.up2_taps, th->pass.up2_taps);
             if (fused) cands.push_back(std::move(c));
-            else if (!exact && d.bps == 1 && plan_tiles(*tv->host, *th->host, d.channels, d.oc(), idx, &tile_items, &tile_geom)) {
+            else if (up2) {
+                FusedGroup* g = nullptr;
+                for (auto& gg : lp.groups)
+                    if (gg.up_taps == tv->pass.up2_taps && gg.channels == d.channels) g = &gg;
+                if (!g) {
+                    lp.groups.push_back(FusedGroup{d.channels, 0, 0, {}, {}, {}, 0, 0, false, tv->pass.up2_taps});
+                    g = &lp.groups.back();
+                }
+                const int tile_w = up2_tile_w(d.channels), tile_h = up2_tile_h();
+                for (int oy = 0; oy < int(d.dh); oy += tile_h)
+                    for (int ox = 0; ox < int(d.dw); ox += tile_w)
+                        g->items.push_back(WorkItem{idx, ox, std::min(int(d.dw), ox + tile_w), oy, std::min(int(d.dh), oy + tile_h)});
+            } else if (!exact && d.bps == 1 && plan_tiles(*tv->host, *th->host, d.channels, d.oc(), idx, &tile_items, &tile_geom)) {
                 // taken by the tile kernel
             } else {
                 lp.generic_jobs.push_back(idx);
@@ -432,7 +452,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         }
     }
     for (auto& g : lp.groups) {
-        if (g.kv == 0) continue;   // tile-kernel launch: geometry already final
+        if (g.kv == 0) continue;   // tile-kernel / 2x-upscale launch: geometry already final
         g.geom.tmp_px |= 1;        // odd pixel pitch: conflict-free float4 column walks
         g.geom.n_items = int(g.items.size());
         if (fused_smem_bytes(g.channels, g.kv, g.kh, g.geom) > 113 * 1024)
@@ -463,7 +483,8 @@ void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, 
     size_t off = (sizeof(DevJob) * lp.jobs.size() + 15) & ~size_t(15);
     for (auto& g : lp.groups) {
         const WorkItem* d_items = reinterpret_cast<const WorkItem*>(d_desc_base + off);
-        if (g.kv == 0) check_cuda(launch_tile(d_jobs, d_items, g.tgeom, stream), "launch tile_kernel");
+        if (g.up_taps) check_cuda(launch_up2(g.channels, g.up_taps, d_jobs, d_items, int(g.items.size()), stream), "launch up2_kernel");
+        else if (g.kv == 0) check_cuda(launch_tile(d_jobs, d_items, g.tgeom, stream), "launch tile_kernel");
         else check_cuda(launch_fused(g.channels, g.kv, g.kh, g.sv, g.sh, g.convert, d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");
         off += (sizeof(WorkItem) * g.items.size() + 15) & ~size_t(15);
         launches.fetch_add(1, std::memory_order_relaxed);

@@ -60,6 +60,7 @@ struct FusedGroup {  // one kernel launch over a list of work items
     TileGeom tgeom{};
     int sv = 0, sh = 0;    // ring kernel: uniform vertical / horizontal step the launch is specialised for (0 = none)
     bool convert = false;  // ring kernel: the jobs store another channel count than they read
+    int up_taps = 0;       // > 0 (with kv == 0): an exact-2x upscale launch (up2.cu) with this tap frame
 };
 
 // Everything needed to enqueue a set of device-resident jobs.

@@ -2,6 +2,8 @@
 #pragma once
 #include <cstdint>
 
+#include <vector_types.h>
+
 namespace ikc {
 
 // Device-resident tables of one separable pass (see plan.hpp for the host form).
@@ -17,6 +19,8 @@ struct DevPass {
     int32_t max_count;
     int32_t uni_step;      // outputs [uni_lo, uni_hi) end uni_step source indices after their predecessor
     int32_t uni_lo, uni_hi;
+    const float2* up2_pairs;  // exact 2x upscale: [n_in][up2_taps] (weight for output 2k, for output 2k+1), or nullptr
+    int32_t up2_off, up2_taps;
 };
 
 // One image resize, device pointers.

@@ -27,4 +27,10 @@ cudaError_t launch_fused(int channels, int ring_k_v, int ring_k_h, int step_v, i
 size_t tile_smem_bytes(const TileGeom& geom);
 cudaError_t launch_tile(const DevJob* jobs, const WorkItem* items, const TileGeom& geom, cudaStream_t stream);
 
+// Exact 2x upscale kernel (up2.cu).  Work items are output tiles of up2_tile_w(channels) x up2_tile_h().
+bool up2_supported(int channels, int taps_v, int taps_h);
+int up2_tile_w(int channels);
+int up2_tile_h();
+cudaError_t launch_up2(int channels, int taps, const DevJob* jobs, const WorkItem* items, int n_items, cudaStream_t stream);
+
 }  // namespace ikc

@@ -212,6 +212,25 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
             p.uni_hi = int(best_lo + best_len);
         }
     }
+    // Frame form for exact 2x upscales.
+    if (n_out == 2 * n_in) {
+        int off = 0x7fffffff, end = -0x7fffffff;
+        for (uint32_t o = 0; o < n_out; ++o) {
+            off = std::min(off, p.left[o] - int(o >> 1));
+            end = std::max(end, p.right[o] - int(o >> 1));
+        }
+        const int taps = end - off;
+        if (taps >= 1 && taps <= 8) {
+            p.up2_off = off;
+            p.up2_taps = taps;
+            p.up2_pairs.assign(size_t(n_in) * taps * 2, 0.0f);
+            for (uint32_t o = 0; o < n_out; ++o) {
+                const int base = int(o >> 1) + off;
+                for (int32_t i = 0; i < p.count[o]; ++i)
+                    p.up2_pairs[(size_t(o >> 1) * taps + size_t(p.left[o] + i - base)) * 2 + (o & 1)] = ragged[o][i];
+            }
+        }
+    }
     if (k >= 1 && k <= 8) {  // only the fused kernels use it; they handle ring_k <= 8
         p.ring_stride = (k + 1) & ~1;  // even: every ring row is a whole number of 16-byte loads
         p.ring.assign(size_t(n_in) * p.ring_stride * 2, 0.0f);

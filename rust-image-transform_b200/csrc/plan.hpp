@@ -40,6 +40,12 @@ struct PassPlan {
     // predecessor (right[o] - right[o-1] == uni_step), as every interior output of an integer-ratio
     // downscale does.  uni_step == 0: no stretch long enough to be worth a specialised loop.
     int uni_step = 0, uni_lo = 0, uni_hi = 0;
+    // Exact 2x upscale (n_out == 2 * n_in): every window fits a frame of up2_taps source indices that
+    // starts at (o >> 1) + up2_off.  up2_pairs[(k * up2_taps + t) * 2 + p] = weight of source index
+    // k + up2_off + t for output 2k + p (0 outside its window): the two outputs of a source index
+    // share their taps, so one packed FMA feeds both (csrc/up2.cu).  up2_taps == 0: not applicable.
+    int up2_off = 0, up2_taps = 0;
+    std::vector<float> up2_pairs;       // [n_in * up2_taps * 2]
 };
 
 std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n_out);

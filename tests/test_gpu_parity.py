@@ -249,3 +249,23 @@ def test_resize_image_encode_as_matches_unfused_path(ctx, ik):
             fused = ik.resize_image(img, 200, None, ctx=ctx, encode_as=fmt)
             assert np.array_equal(getattr(fused, conv)(), getattr(plain, conv)())
             assert fused.pixels.shape[2] == (4 if fmt == ik.ImageFormat.avif else 3)
+
+
+# ---- exact 2x upscales (csrc/up2.cu; BASELINE config 4) ------------------------------------------------------
+UP2_CASES = [  # (h, w, c, filter): output is (2w, 2h)
+    (1080, 1920, 3, 2), (540, 960, 4, 2), (300, 400, 4, 4), (300, 400, 3, 4), (123, 77, 3, 1), (77, 123, 4, 1),
+    (64, 64, 3, 0), (65, 33, 4, 0), (200, 336, 3, 3), (97, 224, 4, 3), (16, 8, 3, 2), (5, 3, 4, 4), (1, 1, 3, 2),
+]
+
+
+@pytest.mark.parametrize("case", UP2_CASES)
+@pytest.mark.parametrize("content", ["noise", "edges"])
+def test_exact_2x_upscale_kernel(ctx, ik, oracle, case, content):
+    h, w, c, filt = case
+    src = {"noise": splitmix_noise, "edges": checker}[content]((h, w, c))
+    _fast(ctx, ik)
+    before = ctx.kernel_launches
+    got = ctx.resize(src, 2 * w, 2 * h, filt)
+    assert ctx.kernel_launches - before == 1, "expected a single fused launch"
+    want = oracle.resize_exact(src, 2 * w, 2 * h, filt)
+    _check_fast(got, want, (case, content), max_off=0.002 if content == "noise" else 0.06)

@@ -1,7 +1,7 @@
 """Dev tool: join `nvdisasm -g -c` line info with an ncu SASS-level CSV (tools/sass_hotspots.py input)
 and print samples / executed warp instructions per CUDA source line of one kernel.
 usage: line_profile.py <fused.dis> <kernel mangled substring> <ncu sass csv> <source file>"""
-import csv, re, sys
+import csv, os, re, sys
 dis, kname, ncsv, srcfile = sys.argv[1:5]
 lines = open(dis).read().split("\n")
 start = next(i for i, l in enumerate(lines) if l.startswith(".text.") and kname in l)
@@ -27,8 +27,8 @@ for k, r in enumerate(d):
     if k >= len(per_instr): break
     c = per_instr[k]
     if c is None: key = -1
-    elif c[0].endswith("fused.cu"): key = c[1]
-    elif c[2] and c[2].endswith("fused.cu"): key = c[3]
+    elif c[0].endswith(os.path.basename(srcfile)): key = c[1]
+    elif c[2] and c[2].endswith(os.path.basename(srcfile)): key = c[3]
     else: key = -2
     a = agg.setdefault(key, [0, 0])
     a[0] += int(r[ix["# Samples"]]); a[1] += int(r[ix["Instructions Executed"]])

@@ -24,4 +24,4 @@ for _ in range(10):
     b.launch(s.cuda_stream)
 e1.record(s)
 s.synchronize()
-print(wl, "batch", batch, "ms/launch", e0.elapsed_time(e1) / 10, "us/image", e0.elapsed_time(e1) / 10 / batch * 1e3)
+print(b.describe()); print(wl, "batch", batch, "ms/launch", e0.elapsed_time(e1) / 10, "us/image", e0.elapsed_time(e1) / 10 / batch * 1e3)
