@@ -97,18 +97,41 @@ up2_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, 
     // Geometry of a tile's staged footprint.  Rows are staged as whole 16-byte chunks when the source
     // allows it (16-byte aligned base and pitch, no columns left of the image); `mis` is then the offset
     // of the first wanted byte inside the first chunk.
+    // The fields of a job the kernel needs, kept in shared memory (two slots: the job of the current tile
+    // and the job of the next one; job indices never decrease along the tile list) so that no tile waits
+    // for the DevJob in global memory.
+    struct JobLite {
+        const uint8_t* src;
+        uint8_t* dst;
+        size_t src_pitch, dst_pitch;
+        const float2* vpairs;
+        const float2* hpairs;
+        int sw, sh, voff, hoff;
+    };
+    __shared__ JobLite job_s[2];
+    __shared__ int job_id_s[2];
+    auto cache_job = [&](int job) {  // thread 0 only; readers come after the next barrier
+        if (job_id_s[job & 1] == job) return;
+        const DevJob& D = jobs[job];
+        JobLite l;
+        l.src = D.src; l.dst = D.dst; l.src_pitch = D.src_pitch; l.dst_pitch = D.dst_pitch;
+        l.vpairs = D.v.up2_pairs; l.hpairs = D.h.up2_pairs;
+        l.sw = int(D.sw); l.sh = int(D.sh); l.voff = D.v.up2_off; l.hoff = D.h.up2_off;
+        job_s[job & 1] = l;
+        job_id_s[job & 1] = job;
+    };
     struct Foot {
-        const DevJob* J;
+        const JobLite* J;
         int kx0, ky0, sx_first, sy_first, mis;
         bool vec;
     };
     auto footprint = [&](const WorkItem& it) {
         Foot f;
-        f.J = jobs + it.job;
+        f.J = job_s + (it.job & 1);
         f.kx0 = it.ox0 >> 1;  // tile origin in source pixels (tiles start on even outputs)
         f.ky0 = it.oy0 >> 1;
-        f.sx_first = f.kx0 + f.J->h.up2_off;  // first staged column / row (may be < 0)
-        f.sy_first = f.ky0 + f.J->v.up2_off;
+        f.sx_first = f.kx0 + f.J->hoff;  // first staged column / row (may be < 0)
+        f.sy_first = f.ky0 + f.J->voff;
         f.vec = f.sx_first >= 0 && ((reinterpret_cast<uintptr_t>(f.J->src) | f.J->src_pitch) & 15) == 0;
         f.mis = f.vec ? (f.sx_first * C) & 15 : 0;
         return f;
@@ -116,20 +139,19 @@ up2_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, 
     // Asynchronous part of staging tile `idx` into buffer `b`: weight pairs and (vector path) source rows.
     // Bytes that are not written keep whatever the buffer held: any byte converts to a finite float, and
     // everything outside the image meets a zero weight.
-    auto prefetch = [&](int idx, int b) {
-        const WorkItem it = items[idx];
+    auto prefetch = [&](const WorkItem& it, int b) {
         const Foot f = footprint(it);
         const int sw = int(f.J->sw), sh = int(f.J->sh);
         float2* vp = pair_buf + b * kPairs;
         float2* hp = vp + kUpKY * T;
         for (int i = tid; i < kUpKY * T; i += kUpThreads) {
             const int k = f.ky0 + i / T;
-            if (k < sh) cp_async8(vp + i, f.J->v.up2_pairs + size_t(k) * T + i % T);
+            if (k < sh) cp_async8(vp + i, f.J->vpairs + size_t(k) * T + i % T);
             else vp[i] = make_float2(0.0f, 0.0f);
         }
         for (int i = tid; i < G::kKX * T; i += kUpThreads) {
             const int k = f.kx0 + i / T;
-            if (k < sw) cp_async8(hp + i, f.J->h.up2_pairs + size_t(k) * T + i % T);
+            if (k < sw) cp_async8(hp + i, f.J->hpairs + size_t(k) * T + i % T);
             else hp[i] = make_float2(0.0f, 0.0f);
         }
         if (f.vec) {
@@ -148,14 +170,25 @@ up2_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, 
         cp_async_commit();
     };
 
+    // Tile descriptors are read two tiles ahead, so that neither the prefetch nor the tile itself waits
+    // for a global load of its own descriptor.
+    const int stride = int(gridDim.x);
+    auto item_at = [&](int idx) { return idx < n_items ? items[idx] : WorkItem{0, 0, 0, 0, 0}; };
     int buf = 0;
-    if (int(blockIdx.x) < n_items) prefetch(blockIdx.x, 0);
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, buf ^= 1) {
+    WorkItem it = item_at(blockIdx.x), it_next = item_at(int(blockIdx.x) + stride);
+    if (tid == 0) {
+        job_id_s[0] = job_id_s[1] = -1;
+        cache_job(it.job);
+    }
+    __syncthreads();
+    if (int(blockIdx.x) < n_items) prefetch(it, 0);
+    for (int idx = blockIdx.x; idx < n_items; idx += stride, buf ^= 1) {
+        const WorkItem it_next2 = item_at(idx + 2 * stride);
+        if (tid == 0 && idx + stride < n_items) cache_job(it_next.job);  // read by the prefetch after the barrier below
         cp_async_wait<0>();  // this tile's copies (issued one tile ago) have landed
-        const WorkItem it = items[idx];
         const Foot f = footprint(it);
-        const DevJob& J = *f.J;
-        const int sw = int(J.sw), sh = int(J.sh);
+        const JobLite& J = *f.J;
+        const int sw = J.sw, sh = J.sh;
         uint8_t* src_s = src_buf + buf * G::kSrcBytes;
         const float2* vp_s = pair_buf + buf * kPairs;
         const float2* hp_s = vp_s + kUpKY * T;
@@ -172,7 +205,7 @@ up2_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, 
         }
         __syncthreads();  // the tile's footprint and pairs are in shared memory; the previous tile is finished,
                           // so its buffers may be refilled while this one is computed
-        if (idx + int(gridDim.x) < n_items) prefetch(idx + gridDim.x, buf ^ 1);
+        if (idx + stride < n_items) prefetch(it_next, buf ^ 1);
 
         // ---- vertical pass: tmp[2k + p][col] = sum_t pair[k][t].p * src[k + t][col]
         if (tid < G::kColBytes) {
@@ -254,6 +287,8 @@ up2_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, 
                 for (int b = lane; b < row_bytes; b += 32) g[b] = sb[row * (kStageWords * 4) + b];
             }
         }
+        it = it_next;
+        it_next = it_next2;
     }
 }
 
