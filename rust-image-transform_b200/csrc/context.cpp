@@ -168,6 +168,8 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     t->pass.up2_pairs = host->up2_pairs.empty() ? nullptr : reinterpret_cast<const float2*>(up2);
     t->pass.up2_off = host->up2_off;
     t->pass.up2_taps = host->up2_taps;
+    t->pass.up2_uni_lo = host->up2_uni_lo;
+    t->pass.up2_uni_hi = host->up2_uni_hi;
     t->pass.stride = int32_t(host->stride);
     t->pass.ring_k = host->ring_k;
     t->pass.ring_stride = host->ring_stride;

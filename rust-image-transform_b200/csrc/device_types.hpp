@@ -21,6 +21,7 @@ struct DevPass {
     int32_t uni_lo, uni_hi;
     const float2* up2_pairs;  // exact 2x upscale: [n_in][up2_taps] (weight for output 2k, for output 2k+1), or nullptr
     int32_t up2_off, up2_taps;
+    int32_t up2_uni_lo, up2_uni_hi;  // source indices with bit-identical pairs
 };
 
 // One image resize, device pointers.

@@ -229,6 +229,17 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
                 for (int32_t i = 0; i < p.count[o]; ++i)
                     p.up2_pairs[(size_t(o >> 1) * taps + size_t(p.left[o] + i - base)) * 2 + (o & 1)] = ragged[o][i];
             }
+            // longest run of source indices with identical pairs
+            const size_t row = size_t(taps) * 2;
+            uint32_t best_lo = 0, best_len = 0;
+            for (uint32_t lo = 0; lo < n_in;) {
+                uint32_t hi = lo + 1;
+                while (hi < n_in && std::memcmp(&p.up2_pairs[hi * row], &p.up2_pairs[lo * row], row * sizeof(float)) == 0) ++hi;
+                if (hi - lo > best_len) { best_len = hi - lo; best_lo = lo; }
+                lo = hi;
+            }
+            p.up2_uni_lo = int(best_lo);
+            p.up2_uni_hi = int(best_lo + best_len);
         }
     }
     if (k >= 1 && k <= 8) {  // only the fused kernels use it; they handle ring_k <= 8

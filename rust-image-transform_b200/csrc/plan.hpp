@@ -46,6 +46,7 @@ struct PassPlan {
     // share their taps, so one packed FMA feeds both (csrc/up2.cu).  up2_taps == 0: not applicable.
     int up2_off = 0, up2_taps = 0;
     std::vector<float> up2_pairs;       // [n_in * up2_taps * 2]
+    int up2_uni_lo = 0, up2_uni_hi = 0; // source indices [lo, hi) whose pairs are bit-identical (the interior)
 };
 
 std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n_out);

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "device_types.hpp"
 #include "launch.hpp"
@@ -107,6 +108,7 @@ up2_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, 
         const float2* vpairs;
         const float2* hpairs;
         int sw, sh, voff, hoff;
+        int vlo, vhi, hlo, hhi;  // source rows / columns whose weight pairs are all the same (the interior)
     };
     __shared__ JobLite job_s[2];
     __shared__ int job_id_s[2];
@@ -117,6 +119,7 @@ up2_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, 
         l.src = D.src; l.dst = D.dst; l.src_pitch = D.src_pitch; l.dst_pitch = D.dst_pitch;
         l.vpairs = D.v.up2_pairs; l.hpairs = D.h.up2_pairs;
         l.sw = int(D.sw); l.sh = int(D.sh); l.voff = D.v.up2_off; l.hoff = D.h.up2_off;
+        l.vlo = D.v.up2_uni_lo; l.vhi = D.v.up2_uni_hi; l.hlo = D.h.up2_uni_lo; l.hhi = D.h.up2_uni_hi;
         job_s[job & 1] = l;
         job_id_s[job & 1] = job;
     };
@@ -213,13 +216,27 @@ up2_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, 
 #pragma unroll
             for (int r = 0; r < G::kRows; ++r)  // exact u8 -> f32: the byte in the mantissa of 2^23, minus 2^23
                 s[r] = __uint_as_float(0x4B000000u | src_s[r * G::kRowBytes + f.mis + tid]) - 8388608.0f;
+            if (f.ky0 >= J.vlo && f.ky0 + kUpKY <= J.vhi) {  // interior rows: one set of pairs, held in registers
+                float2 w[T];
 #pragma unroll
-            for (int k = 0; k < kUpKY; ++k) {
-                float2 acc = make_float2(0.0f, 0.0f);
+                for (int t = 0; t < T; ++t) w[t] = vp_s[t];
 #pragma unroll
-                for (int t = 0; t < T; ++t) acc = __ffma2_rn(vp_s[k * T + t], dup(s[k + t]), acc);
-                tmp_s[(2 * k) * G::kPitchF + tid] = acc.x;
-                tmp_s[(2 * k + 1) * G::kPitchF + tid] = acc.y;
+                for (int k = 0; k < kUpKY; ++k) {
+                    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) acc = __ffma2_rn(w[t], dup(s[k + t]), acc);
+                    tmp_s[(2 * k) * G::kPitchF + tid] = acc.x;
+                    tmp_s[(2 * k + 1) * G::kPitchF + tid] = acc.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kUpKY; ++k) {
+                    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) acc = __ffma2_rn(vp_s[k * T + t], dup(s[k + t]), acc);
+                    tmp_s[(2 * k) * G::kPitchF + tid] = acc.x;
+                    tmp_s[(2 * k + 1) * G::kPitchF + tid] = acc.y;
+                }
             }
         }
         __syncthreads();
@@ -235,23 +252,33 @@ up2_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, 
                 v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
             }
             float o[2 * kSegPx * C];  // o[px * C + c], value + 0.5
+            // interior columns share one set of pairs, held in registers; border tiles read them per pixel
+            auto hpass = [&](auto uniform) {
+                float2 wu[T];
+                if (decltype(uniform)::value) {
 #pragma unroll
-            for (int k = 0; k < kSegPx; ++k) {
-                float2 acc[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) acc[c] = make_float2(0.5f, 0.5f);
-#pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    const float2 w = hp_s[(warp * kSegPx + k) * T + t];
-#pragma unroll
-                    for (int c = 0; c < C; ++c) acc[c] = __ffma2_rn(w, dup(v[(k + t) * C + c]), acc[c]);
+                    for (int t = 0; t < T; ++t) wu[t] = hp_s[t];
                 }
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    o[(2 * k) * C + c] = acc[c].x;
-                    o[(2 * k + 1) * C + c] = acc[c].y;
+                for (int k = 0; k < kSegPx; ++k) {
+                    float2 acc[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[c] = make_float2(0.5f, 0.5f);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        const float2 w = decltype(uniform)::value ? wu[t] : hp_s[(warp * kSegPx + k) * T + t];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) acc[c] = __ffma2_rn(w, dup(v[(k + t) * C + c]), acc[c]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        o[(2 * k) * C + c] = acc[c].x;
+                        o[(2 * k + 1) * C + c] = acc[c].y;
+                    }
                 }
-            }
+            };
+            if (f.kx0 >= J.hlo && f.kx0 + G::kKX <= J.hhi) hpass(std::true_type{});
+            else hpass(std::false_type{});
 #pragma unroll
             for (int j = 0; j < G::kWords; ++j) words[j] = pack4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
         }
