@@ -143,6 +143,20 @@ IKC_API int ikc_target_dims(uint32_t ow, uint32_t oh, int has_w, uint32_t w, int
 IKC_API uint32_t ikc_pass_table(int filter, uint32_t n_in, uint32_t n_out, uint32_t* left, uint32_t* count,
                                 float* weights, uint32_t stride);
 
+/* What the planner derived for one separable pass (introspection for tests and tuning; no GPU
+ * needed).  ring_k: most windows covering any source index (the fused downscale kernel needs 6 or 7).
+ * uni_*: outputs [uni_lo, uni_hi) each end uni_step source indices after their predecessor with
+ * full, bit-identical windows (0: none) -- the interior of an integer-ratio downscale.
+ * up2_*: exact 2x upscale frame: up2_taps source indices from (o >> 1) + up2_off cover every
+ * window (0: not a 2x upscale); source indices [up2_uni_lo, up2_uni_hi) share one set of weights. */
+typedef struct ikc_pass_info_t {
+    uint32_t stride, max_count;
+    int32_t ring_k;
+    int32_t uni_step, uni_lo, uni_hi;
+    int32_t up2_taps, up2_off, up2_uni_lo, up2_uni_hi;
+} ikc_pass_info_t;
+IKC_API int ikc_pass_info(int filter, uint32_t n_in, uint32_t n_out, ikc_pass_info_t* out);
+
 /* ---- host-buffer entry points (the drop-in path; include H2D + D2H) -------------------------- */
 
 /* Replaces imageops::resize(&buf, dw, dh, filter) for 8-bit rasters (image 0.25.8

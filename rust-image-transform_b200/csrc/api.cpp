@@ -117,6 +117,24 @@ uint32_t ikc_pass_table(int filter, uint32_t n_in, uint32_t n_out, uint32_t* lef
     return need;
 }
 
+int ikc_pass_info(int filter, uint32_t n_in, uint32_t n_out, ikc_pass_info_t* out) {
+    if (!out) return IKC_ERR_INVALID_ARG;
+    return guarded([&] {
+        auto p = build_pass(filter, n_in, n_out);
+        if (!p) fail(kInvalidArg, "cannot plan pass");
+        out->stride = p->stride;
+        out->max_count = p->max_count;
+        out->ring_k = p->ring_k;
+        out->uni_step = p->uni_step;
+        out->uni_lo = p->uni_lo;
+        out->uni_hi = p->uni_hi;
+        out->up2_taps = p->up2_taps;
+        out->up2_off = p->up2_off;
+        out->up2_uni_lo = p->up2_uni_lo;
+        out->up2_uni_hi = p->up2_uni_hi;
+    });
+}
+
 int ikc_resize_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch, int channels,
                   uint8_t* dst, uint32_t dw, uint32_t dh, size_t dst_pitch, int filter) {
     if (!ctx) {

@@ -22,7 +22,7 @@ MAX_DIM, MAX_PIXELS = 65535, 1 << 28  # IKC_MAX_DIM, IKC_MAX_PIXELS
 # every symbol include/imagekit_cuda.h declares
 EXPORTS = [
     "ikc_create", "ikc_destroy", "ikc_device_count", "ikc_set_mode", "ikc_get_mode", "ikc_kernel_launches",
-    "ikc_last_error", "ikc_version", "ikc_target_dims", "ikc_pass_table", "ikc_resize_u8", "ikc_resize_u16",
+    "ikc_last_error", "ikc_version", "ikc_target_dims", "ikc_pass_table", "ikc_pass_info", "ikc_resize_u8", "ikc_resize_u16",
     "ikc_resize_convert_u8", "ikc_resize_image_u8", "ikc_resize_batch", "ikc_host_alloc", "ikc_host_free", "ikc_resize_u8_device",
     "ikc_batch_prepare", "ikc_batch_launch", "ikc_batch_launch_count", "ikc_batch_describe", "ikc_batch_free",
 ]
@@ -36,6 +36,13 @@ class Job(C.Structure):
         ("src_pitch", C.c_size_t), ("dst_pitch", C.c_size_t),
         ("channels", C.c_int32), ("filter", C.c_int32), ("status", C.c_int32), ("device", C.c_int32),
     ]
+
+
+class PassInfo(C.Structure):
+    """struct ikc_pass_info_t"""
+    _fields_ = [("stride", C.c_uint32), ("max_count", C.c_uint32), ("ring_k", C.c_int32),
+                ("uni_step", C.c_int32), ("uni_lo", C.c_int32), ("uni_hi", C.c_int32),
+                ("up2_taps", C.c_int32), ("up2_off", C.c_int32), ("up2_uni_lo", C.c_int32), ("up2_uni_hi", C.c_int32)]
 
 
 _lib = None
@@ -72,6 +79,8 @@ def load() -> C.CDLL:
     L.ikc_target_dims.restype = i32
     L.ikc_pass_table.argtypes = [i32, u32, u32, pu32, pu32, C.POINTER(C.c_float), u32]
     L.ikc_pass_table.restype = u32
+    L.ikc_pass_info.argtypes = [i32, u32, u32, C.POINTER(PassInfo)]
+    L.ikc_pass_info.restype = i32
     L.ikc_resize_u8.argtypes = [vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32]
     L.ikc_resize_u8.restype = i32
     L.ikc_resize_convert_u8.argtypes = [vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32, i32]

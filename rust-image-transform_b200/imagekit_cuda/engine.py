@@ -49,6 +49,13 @@ def pass_table(filt: int, n_in: int, n_out: int):
     return left, cnt, w
 
 
+def pass_info(filt: int, n_in: int, n_out: int) -> dict:
+    """What the planner derived for one pass (ring size, uniform stretch, 2x-upscale frame): ikc_pass_info."""
+    info = _lib.PassInfo()
+    _check(_lib.load().ikc_pass_info(filt, n_in, n_out, C.byref(info)))
+    return {name: getattr(info, name) for name, _ in _lib.PassInfo._fields_}
+
+
 class PinnedArray:
     """A numpy view over cudaMallocHost memory obtained through ikc_host_alloc."""
 

@@ -65,3 +65,50 @@ def test_error_paths_without_context(ik):
     assert L.ikc_device_count(None) == 0
     assert L.ikc_batch_launch(None, None) == ik._lib.ERR_INVALID_ARG
     assert b"null" in L.ikc_last_error()
+
+
+# ---- what the planner derives for the specialised kernels (host logic; checked against the oracle's tables) ----
+@pytest.mark.parametrize("filt,n_in,n_out", [(4, 2160, 1080), (4, 3840, 1920), (4, 1200, 300), (4, 3024, 300),
+                                             (4, 1080, 225), (2, 500, 250), (4, 777, 388), (4, 64, 32)])
+def test_uniform_stretch_of_downscale_passes(ik, oracle, filt, n_in, n_out):
+    from imagekit_cuda import engine
+    info = engine.pass_info(filt, n_in, n_out)
+    left, count, w = oracle.pass_table(filt, n_in, n_out)
+    right = left.astype(np.int64) + count
+    # ring size = most windows over any source index
+    cover = np.zeros(n_in + 1, np.int64)
+    np.add.at(cover, left, 1)
+    np.add.at(cover, right, -1)
+    assert info["ring_k"] == int(np.cumsum(cover)[:-1].max())
+    lo, hi, step = info["uni_lo"], info["uni_hi"], info["uni_step"]
+    if n_in % n_out == 0 and n_out >= 8 * info["ring_k"]:
+        assert step == n_in // n_out and hi - lo >= n_out - 8, (lo, hi, step)   # all but the clamped borders
+    if step:
+        k = info["ring_k"]
+        assert 1 <= lo < hi <= n_out
+        for o in range(lo, hi):
+            assert right[o] - right[o - 1] == step and count[o] == k * step
+            if o >= k:
+                assert left[o] == right[o - k]
+            assert np.array_equal(w[o, :count[o]].view(np.uint32), w[lo, :count[lo]].view(np.uint32))
+        # maximal: the outputs just outside break one of the conditions
+        for o in (lo - 1, hi):
+            if 1 <= o < n_out:
+                same = (right[o] - right[o - 1] == step and count[o] == k * step and (o < k or left[o] == right[o - k]) and
+                        np.array_equal(w[o, :count[o]].view(np.uint32), w[lo, :count[lo]].view(np.uint32)))
+                assert not same
+    else:
+        assert n_in % n_out != 0 or n_out < 8 * info["ring_k"]
+
+
+@pytest.mark.parametrize("filt,n_in", [(2, 1080), (2, 1920), (4, 400), (1, 77), (0, 64), (3, 200), (2, 1), (4, 3)])
+def test_exact_2x_upscale_frame(ik, oracle, filt, n_in):
+    from imagekit_cuda import engine
+    info = engine.pass_info(filt, n_in, 2 * n_in)
+    left, count, _ = oracle.pass_table(filt, n_in, 2 * n_in)
+    base = np.arange(2 * n_in) // 2 + info["up2_off"]
+    assert info["up2_taps"] >= 1
+    assert np.all(left >= base) and np.all(left + count <= base + info["up2_taps"])      # every window fits its frame
+    assert np.any(left == base) and np.any(left + count == base + info["up2_taps"])      # and the frame is tight
+    assert 0 <= info["up2_uni_lo"] < info["up2_uni_hi"] <= n_in
+    assert engine.pass_info(filt, n_in, 2 * n_in + 1)["up2_taps"] == 0                   # not an exact 2x upscale
