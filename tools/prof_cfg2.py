@@ -1,4 +1,5 @@
-"""Dev tool: a few launches of the cfg2 fused kernel for ncu (batch of 8 4K RGBA images)."""
+"""Dev tool: a few device-resident launches of one BASELINE workload (cfg1..cfg4) for timing and ncu:
+    python tools/prof_cfg2.py cfg2 16     # prints the kernel(s) used and us/image"""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "rust-image-transform_b200"))
