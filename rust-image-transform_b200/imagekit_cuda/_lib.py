@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("IKC_LIB_OVERRIDE") or os.path.join(os.path.dirname(_HERE), "libimagekit_cuda.so")
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libimagekit_cuda.so")
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_TOO_LARGE, ERR_CUDA, ERR_OOM = range(6)
 STATUS_NAMES = ["ok", "invalid-arg", "unsupported-layout", "too-large", "cuda-error", "oom"]
