@@ -3,7 +3,12 @@
 over a batch of synthetic 8 MP JPEGs, with a per-stage breakdown.  Decode and encode stay on the CPU
 (north-star); Pillow stands in for the reference's image/webp crates.
 
-usage: python tools/upload_pipeline.py [--images 64] [--width 800] [--threads N] [--cpu-resize]
+usage: python tools/upload_pipeline.py [--images 64] [--width 800] [--threads N] [--cpu-resize] [--pipelined]
+
+Default: the three stages run one after the other over the whole batch (per-stage breakdown).
+--pipelined: every worker thread takes one upload through decode -> resize -> encode, as the reference's
+tokio workers do (src/lib.rs:281-294), so decode(i+1), H2D+resize(i) and encode(i-1) of different uploads
+overlap; the resize stores rgb8 directly (encode_as=webp: to_rgb8() fused).
 """
 import argparse
 import io
@@ -37,6 +42,7 @@ def main():
     ap.add_argument("--width", type=int, default=800)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
     ap.add_argument("--cpu-resize", action="store_true", help="resize with the CPU oracle port instead (baseline)")
+    ap.add_argument("--pipelined", action="store_true", help="one upload per worker thread, stages overlapped")
     args = ap.parse_args()
     import imagekit_cuda as ik
     jpegs = synth_jpegs(min(args.images, 8))
@@ -48,6 +54,31 @@ def main():
         warm = ik.decode_image(jpegs[0])[0]
         tw, th, _ = ik.target_dims(warm.width(), warm.height(), args.width, None)
         ctx.resize_batch([warm.pixels] * 8, [(tw, th)] * 8)
+
+    if args.pipelined:
+        if args.cpu_resize:
+            from oracle import oracle
+
+            def one(b):
+                d = ik.decode_image(b)[0]
+                r = ik.DynamicImage(oracle.resize_image(d.pixels, args.width, None))
+                return len(ik.encode_image(r, ik.ImageFormat.webp, 80))
+        else:
+            def one(b):
+                d = ik.decode_image(b)[0]
+                r = ik.resize_image(d, args.width, None, ctx=ctx, encode_as=ik.ImageFormat.webp)
+                return len(ik.encode_image(r, ik.ImageFormat.webp, 80))
+        t0 = time.perf_counter()
+        sizes = list(pool.map(one, jpegs))
+        t3 = time.perf_counter()
+        print(json.dumps({
+            "workload": f"cfg5: {args.images} x 8 MP JPEG -> w={args.width} Lanczos3 -> webp q=80, one upload per worker thread",
+            "images_per_s": args.images / (t3 - t0), "threads": args.threads,
+            "gpus": 0 if args.cpu_resize else ctx.device_count,
+            "resize": "cpu oracle port" if args.cpu_resize else "gpu (ikc_resize_convert_u8, pageable host buffers)",
+            "seconds": t3 - t0, "out_bytes_mean": sum(sizes) / args.images,
+        }))
+        return
 
     t0 = time.perf_counter()
     decoded = list(pool.map(lambda b: ik.decode_image(b)[0], jpegs))           # CPU decode, threaded
