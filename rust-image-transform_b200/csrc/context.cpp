@@ -142,13 +142,13 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
     const size_t b_idx = up(sizeof(int32_t) * n_out);
     const size_t b_w = up(sizeof(float) * host->w.size());
-    const size_t b_ring = up(sizeof(float) * host->ring.size());
+    const size_t b_ring = up(sizeof(float) * host->ring_v.size());
     const size_t b_up2 = up(sizeof(float) * host->up2_pairs.size());
     auto t = std::make_shared<DevTables>();
     t->device = ordinal_;
     t->host = host;
     check_cuda(cudaSetDevice(ordinal_), "cudaSetDevice");
-    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + b_ring + b_up2 + 256), "cudaMalloc(weight tables)");
+    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + 2 * b_ring + b_up2 + 256), "cudaMalloc(weight tables)");
     uint8_t* p = static_cast<uint8_t*>(t->base);
     auto put = [&](const void* src, size_t bytes, size_t slot) {
         uint8_t* at = p;
@@ -162,8 +162,10 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     t->pass.left = reinterpret_cast<const int32_t*>(put(host->left.data(), sizeof(int32_t) * n_out, b_idx));
     t->pass.right = reinterpret_cast<const int32_t*>(put(host->right.data(), sizeof(int32_t) * n_out, b_idx));
     t->pass.w = reinterpret_cast<const float*>(put(host->w.data(), sizeof(float) * host->w.size(), b_w));
-    const uint8_t* ring = put(host->ring.data(), sizeof(float) * host->ring.size(), b_ring);
-    t->pass.ring = host->ring.empty() ? nullptr : reinterpret_cast<const float*>(ring);
+    const uint8_t* ring_v = put(host->ring_v.data(), sizeof(float) * host->ring_v.size(), b_ring);
+    const uint8_t* ring_h = put(host->ring_h.data(), sizeof(float) * host->ring_h.size(), b_ring);
+    t->pass.ring_v = host->ring_v.empty() ? nullptr : reinterpret_cast<const float*>(ring_v);
+    t->pass.ring_h = host->ring_h.empty() ? nullptr : reinterpret_cast<const float*>(ring_h);
     const uint8_t* up2 = put(host->up2_pairs.data(), sizeof(float) * host->up2_pairs.size(), b_up2);
     t->pass.up2_pairs = host->up2_pairs.empty() ? nullptr : reinterpret_cast<const float2*>(up2);
     t->pass.up2_off = host->up2_off;

@@ -6,12 +6,20 @@
 
 namespace ikc {
 
+// The fused ring kernel turns a byte into a float by dropping it into an all-zero word: the denormal
+// b * 2^-149 (one PRMT, no arithmetic; FFMA2 takes denormal operands at full rate on sm_100a).  The ring
+// weights carry the compensating powers of two, which is exact: vertical weights * 2^75, so the f32
+// intermediate is the reference's times 2^-74, and horizontal weights * 2^74.
+constexpr float kRingScaleV = 37778931862957161709568.0f;   // 2^75
+constexpr float kRingScaleH = 18889465931478580854784.0f;   // 2^74
+
 // Device-resident tables of one separable pass (see plan.hpp for the host form).
 struct DevPass {
     const int32_t* left;   // [n_out]
     const int32_t* right;  // [n_out]
     const float* w;        // [n_out * stride]
-    const float* ring;     // [n_in * ring_stride * 2] duplicated ring weights, or nullptr
+    const float* ring_v;   // [n_in * ring_stride * 2] duplicated ring weights * kRingScaleV (pass used vertically), or nullptr
+    const float* ring_h;   // the same * kRingScaleH (pass used horizontally)
     int32_t stride;
     int32_t ring_k;        // windows covering any source index (ring size)
     int32_t ring_stride;   // ring_k rounded up to even (row stride of `ring`, in weight pairs)

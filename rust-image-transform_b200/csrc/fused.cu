@@ -105,10 +105,11 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
 // Barrier over the compute warps only (the producer warp never joins it).
 __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
 
-// u8 -> f32, exact: PRMT drops the byte into the mantissa of 2^23, one FADD removes the bias.
+// u8 -> f32 with one PRMT and no arithmetic: the byte alone in a zero word is the denormal b * 2^-149;
+// the ring weights carry the compensating power of two (device_types.hpp: kRingScaleV / kRingScaleH).
 template <int BYTE>
 __device__ __forceinline__ float byte_to_float(uint32_t word) {
-    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440u + BYTE)) - 8388608.0f;
+    return __uint_as_float(__byte_perm(word, 0u, 0x4440u + BYTE));
 }
 
 // Quantise one finished pixel: clamp to [0,255] and round half away from zero (f32::round), as
@@ -203,8 +204,8 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     const int32_t* __restrict__ vright = J->v.right;
     const int32_t* __restrict__ hleft = J->h.left;
     const int32_t* __restrict__ hright = J->h.right;
-    const float4* __restrict__ vring = reinterpret_cast<const float4*>(J->v.ring);
-    const float4* __restrict__ hring = reinterpret_cast<const float4*>(J->h.ring);
+    const float4* __restrict__ vring = reinterpret_cast<const float4*>(J->v.ring_v);
+    const float4* __restrict__ hring = reinterpret_cast<const float4*>(J->h.ring_h);
 
     // Strip geometry along x: source pixels [xl, xr), source bytes [b0, b0 + nb) (16-byte aligned).
     const int xl = __ldg(hleft + ox0);
@@ -246,11 +247,11 @@ fused_ring_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ 
     }
     // tap weights of the uniform stretches (every output of a stretch has the same ones)
     if (RWV && tid < LV && J->v.uni_step == SV) {
-        const float w = __ldg(J->v.w + size_t(J->v.uni_lo) * J->v.stride + tid);
+        const float w = __ldg(J->v.w + size_t(J->v.uni_lo) * J->v.stride + tid) * kRingScaleV;
         vtap[tid] = make_float2(w, w);
     }
     if (RWH && tid >= 32 && tid < 32 + LH && J->h.uni_step == SH) {
-        const float w = __ldg(J->h.w + size_t(J->h.uni_lo) * J->h.stride + (tid - 32));
+        const float w = __ldg(J->h.w + size_t(J->h.uni_lo) * J->h.stride + (tid - 32)) * kRingScaleH;
         htap[tid - 32] = make_float2(w, w);
     }
     // (left, right) of the strip's outputs (plus the few before ox0 whose windows reach into the strip)

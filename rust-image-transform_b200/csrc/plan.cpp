@@ -3,6 +3,8 @@
 // exactly once, as the Rust reference does.
 #include "plan.hpp"
 
+#include "device_types.hpp"
+
 #include <algorithm>
 #include <cstring>
 #include <cmath>
@@ -244,12 +246,14 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
     }
     if (k >= 1 && k <= 8) {  // only the fused kernels use it; they handle ring_k <= 8
         p.ring_stride = (k + 1) & ~1;  // even: every ring row is a whole number of 16-byte loads
-        p.ring.assign(size_t(n_in) * p.ring_stride * 2, 0.0f);
+        p.ring_v.assign(size_t(n_in) * p.ring_stride * 2, 0.0f);
+        p.ring_h.assign(size_t(n_in) * p.ring_stride * 2, 0.0f);
         for (uint32_t o = 0; o < n_out; ++o) {
             const int j = int(o % uint32_t(k));
             for (int32_t i = 0; i < p.count[o]; ++i) {
                 const size_t at = (size_t(p.left[o] + i) * p.ring_stride + j) * 2;
-                p.ring[at] = p.ring[at + 1] = ragged[o][i];
+                p.ring_v[at] = p.ring_v[at + 1] = ragged[o][i] * kRingScaleV;  // exact: powers of two
+                p.ring_h[at] = p.ring_h[at + 1] = ragged[o][i] * kRingScaleH;
             }
         }
     }

@@ -33,7 +33,8 @@ struct PassPlan {
     // so that one 64-bit load feeds a packed fma.rn.f32x2.
     int ring_k = 0;
     int ring_stride = 0;                // ring_k rounded up to even
-    std::vector<float> ring;            // [n_in * ring_stride * 2]
+    std::vector<float> ring_v, ring_h;  // [n_in * ring_stride * 2] each, scaled by kRingScaleV / kRingScaleH
+                                        // (device_types.hpp: the kernel feeds bytes as denormals)
     std::vector<int32_t> right;         // [n_out] left + count
     uint32_t max_count = 0;
     // Uniform stretch: outputs o in [uni_lo, uni_hi) all end exactly uni_step source indices after their
