@@ -148,7 +148,7 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     t->device = ordinal_;
     t->host = host;
     check_cuda(cudaSetDevice(ordinal_), "cudaSetDevice");
-    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + 2 * b_ring + b_up2 + 256), "cudaMalloc(weight tables)");
+    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + 2 * b_ring + 2 * b_up2 + 256), "cudaMalloc(weight tables)");
     uint8_t* p = static_cast<uint8_t*>(t->base);
     auto put = [&](const void* src, size_t bytes, size_t slot) {
         uint8_t* at = p;
@@ -166,8 +166,13 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     const uint8_t* ring_h = put(host->ring_h.data(), sizeof(float) * host->ring_h.size(), b_ring);
     t->pass.ring_v = host->ring_v.empty() ? nullptr : reinterpret_cast<const float*>(ring_v);
     t->pass.ring_h = host->ring_h.empty() ? nullptr : reinterpret_cast<const float*>(ring_h);
-    const uint8_t* up2 = put(host->up2_pairs.data(), sizeof(float) * host->up2_pairs.size(), b_up2);
-    t->pass.up2_pairs = host->up2_pairs.empty() ? nullptr : reinterpret_cast<const float2*>(up2);
+    std::vector<float> scaled(host->up2_pairs.size());
+    for (size_t i = 0; i < scaled.size(); ++i) scaled[i] = host->up2_pairs[i] * kRingScaleV;  // exact: a power of two
+    const uint8_t* up2_v = put(scaled.data(), sizeof(float) * scaled.size(), b_up2);
+    for (size_t i = 0; i < scaled.size(); ++i) scaled[i] = host->up2_pairs[i] * kRingScaleH;
+    const uint8_t* up2_h = put(scaled.data(), sizeof(float) * scaled.size(), b_up2);
+    t->pass.up2_pairs_v = scaled.empty() ? nullptr : reinterpret_cast<const float2*>(up2_v);
+    t->pass.up2_pairs_h = scaled.empty() ? nullptr : reinterpret_cast<const float2*>(up2_h);
     t->pass.up2_off = host->up2_off;
     t->pass.up2_taps = host->up2_taps;
     t->pass.up2_uni_lo = host->up2_uni_lo;
@@ -373,7 +378,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
                                    &c.strips);
             }
             const bool up2 = !fused && !exact && d.bps == 1 && d.oc() == d.channels && d.dw == 2 * d.sw && d.dh == 2 * d.sh &&
-                             tv->pass.up2_pairs && th->pass.up2_pairs &&
+                             tv->pass.up2_pairs_v && th->pass.up2_pairs_h &&
                              up2_supported(d.channels, tv->pass.up2_taps, th->pass.up2_taps);
             if (fused) cands.push_back(std::move(c));
             else if (up2) {

@@ -27,7 +27,8 @@ struct DevPass {
     int32_t max_count;
     int32_t uni_step;      // outputs [uni_lo, uni_hi) end uni_step source indices after their predecessor
     int32_t uni_lo, uni_hi;
-    const float2* up2_pairs;  // exact 2x upscale: [n_in][up2_taps] (weight for output 2k, for output 2k+1), or nullptr
+    const float2* up2_pairs_v;  // exact 2x upscale: [n_in][up2_taps] (weight for output 2k, for output 2k+1) * kRingScaleV,
+    const float2* up2_pairs_h;  // and * kRingScaleH (up2.cu feeds bytes as denormals too); nullptr if not a 2x upscale
     int32_t up2_off, up2_taps;
     int32_t up2_uni_lo, up2_uni_hi;  // source indices with bit-identical pairs
 };

@@ -10,8 +10,10 @@
 // registers for all the outputs it feeds:
 //   * a CTA owns 128 x 32 outputs = 64 x 16 source pixels (+ T-1 halo), staged once as bytes
 //     (RGBA: 112 x 32 outputs = 56 x 16 source pixels, so that a staged row still has <= 256 byte columns);
-//   * vertical pass: thread = one byte column of the staged rows; its 16+T-1 samples are converted once
-//     (exact u8 -> f32) and produce the 32 rows of the unclamped f32 intermediate in shared memory;
+//   * vertical pass: thread = one byte column of the staged rows; its 16+T-1 samples are used as they are
+//     (a zero-extended byte is the denormal float b * 2^-149; the weight pairs carry the compensating
+//     powers of two, device_types.hpp) and produce the 32 rows of the unclamped f32 intermediate
+//     (times 2^-74) in shared memory;
 //   * horizontal pass: warp = 8 (RGBA: 7) source pixels, lane = intermediate row; the pixels of the row
 //     are loaded once with LDS.128 and produce 16 (14) finished pixels, packed with saturating F2IP
 //     conversions (round-half-away: the accumulators start at 0.5) and written as 16- / 8-byte stores.
@@ -117,7 +119,7 @@ up2_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, 
         const DevJob& D = jobs[job];
         JobLite l;
         l.src = D.src; l.dst = D.dst; l.src_pitch = D.src_pitch; l.dst_pitch = D.dst_pitch;
-        l.vpairs = D.v.up2_pairs; l.hpairs = D.h.up2_pairs;
+        l.vpairs = D.v.up2_pairs_v; l.hpairs = D.h.up2_pairs_h;
         l.sw = int(D.sw); l.sh = int(D.sh); l.voff = D.v.up2_off; l.hoff = D.h.up2_off;
         l.vlo = D.v.up2_uni_lo; l.vhi = D.v.up2_uni_hi; l.hlo = D.h.up2_uni_lo; l.hhi = D.h.up2_uni_hi;
         job_s[job & 1] = l;
@@ -214,8 +216,8 @@ up2_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, 
         if (tid < G::kColBytes) {
             float s[G::kRows];
 #pragma unroll
-            for (int r = 0; r < G::kRows; ++r)  // exact u8 -> f32: the byte in the mantissa of 2^23, minus 2^23
-                s[r] = __uint_as_float(0x4B000000u | src_s[r * G::kRowBytes + f.mis + tid]) - 8388608.0f;
+            for (int r = 0; r < G::kRows; ++r)  // the zero-extended byte *is* the float b * 2^-149 (a denormal); the weight
+                s[r] = __uint_as_float(uint32_t(src_s[r * G::kRowBytes + f.mis + tid]));  // pairs carry 2^75 (V) and 2^74 (H)
             if (f.ky0 >= J.vlo && f.ky0 + kUpKY <= J.vhi) {  // interior rows: one set of pairs, held in registers
                 float2 w[T];
 #pragma unroll
