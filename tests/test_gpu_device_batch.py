@@ -59,3 +59,23 @@ def test_full_size_properties_4k(ctx, ik):
     s = ra + rb
     inner = (ra > 0) & (ra < 255) & (rb > 0) & (rb < 255)   # unclamped samples
     assert np.abs(s[inner] - 255).max() <= 1
+
+
+def test_host_batch_shards_round_robin_over_all_devices(ik, oracle):
+    """ikc_resize_batch over every visible GPU: job i runs on device i mod G, no collective."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    ctx = ik.Context()                     # all visible devices
+    try:
+        g = ctx.device_count
+        assert g == torch.cuda.device_count()
+        srcs = [splitmix_noise((300 + 8 * i, 400, 3 + (i & 1)), image_id=i) for i in range(4 * g + 1)]
+        sizes = [(200, 150 + 4 * i) for i in range(len(srcs))]
+        outs, jobs = ctx.resize_batch(srcs, sizes)
+        for i, (s, (dw, dh), o_, j) in enumerate(zip(srcs, sizes, outs, jobs)):
+            assert j.status == 0 and j.device == i % g
+            hist = delta_histogram(o_, oracle.resize_exact(s, dw, dh, oracle.LANCZOS3))
+            assert max(abs(k) for k in hist) <= 1, hist
+    finally:
+        ctx.close()
