@@ -34,6 +34,40 @@ def test_prepared_batch_on_torch_stream(ctx, ik, oracle):
     batch.free()
 
 
+def test_prepared_batch_mixes_every_kernel(ctx, ik, oracle):
+    """One prepared batch whose jobs need the ring kernel (plain, uniform, converting), the 2x upscale kernel,
+    the tile kernel and the generic kernels: one launch per kernel variant, every job within +-1."""
+    import torch
+    ctx.set_mode(ik.MODE_FAST)
+    dev = torch.device("cuda:0")
+    cases = [  # (h, w, c, dw, dh, filter, out_channels)
+        (480, 640, 3, 200, 150, 4, 3), (600, 800, 4, 400, 300, 4, 4), (600, 800, 4, 400, 300, 4, 3),
+        (240, 320, 3, 640, 480, 2, 3), (240, 320, 4, 640, 480, 2, 4), (200, 300, 1, 150, 100, 4, 1),
+        (100, 120, 3, 333, 222, 1, 4), (300, 400, 3, 200, 150, 4, 4),
+    ]
+    keep, jobs, want = [], [], []
+    for i, (h, w, c, dw, dh, filt, co) in enumerate(cases):
+        s = splitmix_noise((h, w, c), image_id=40 + i)
+        ts = torch.from_numpy(s).to(dev)
+        td = torch.zeros((dh, dw, co), dtype=torch.uint8, device=dev)
+        keep.append((ts, td))
+        jobs.append((ts.data_ptr(), w, h, w * c, td.data_ptr(), dw, dh, dw * co, c | (co << 8) if co != c else c, filt))
+        r = oracle.resize_exact(s, dw, dh, filt)
+        want.append(r if co == c else (oracle.to_rgb8(r) if co == 3 else oracle.to_rgba8(r)))
+    batch = ctx.prepare_batch(0, jobs)
+    assert all(j.status == 0 for j in batch.jobs), [j.status for j in batch.jobs]
+    desc = batch.describe()
+    for name in ("fused_ring_kernel", "up2_kernel", "tile_kernel"):
+        assert name in desc, desc
+    stream = torch.cuda.Stream()
+    batch.launch(stream.cuda_stream)
+    stream.synchronize()
+    for (_, td), w_, case in zip(keep, want, cases):
+        hist = delta_histogram(td.cpu().numpy().reshape(w_.shape), w_)
+        assert max(abs(k) for k in hist) <= 1, (case, hist)
+    batch.free()
+
+
 def test_device_entry_point(ctx, ik, oracle):
     import torch
     ctx.set_mode(ik.MODE_FAST)
