@@ -3,7 +3,8 @@
 // 1-2 channel rasters, mild ratios with other ring sizes.  u8 only.
 //
 // One CTA computes a TW x TH tile of one image of the batch.  The source footprint of the tile is
-// converted to f32 once while it is staged into shared memory; the vertical pass (image 0.25.8
+// staged into shared memory once as f32 (a zero-extended byte is the denormal b * 2^-149; the staged weights
+// carry the compensating powers of two); the vertical pass (image 0.25.8
 // vertical_sample) writes an f32 tmp tile [TH][footprint columns] to shared memory; the horizontal pass
 // (horizontal_sample) reads it, clamps, rounds half away from zero and stores u8.  Same order of
 // passes and same unclamped f32 intermediate as the reference; sums use FMA, hence |delta| <= 1.
@@ -21,9 +22,12 @@ namespace {
 
 constexpr int kTileThreads = 256;
 
-__device__ __forceinline__ uint32_t quantize_u8_tile(float v) {
-    v = fminf(fmaxf(v, 0.0f), 255.0f);
-    return __float2uint_rz(v + 0.5f);  // see fused.cu: equals f32::round on [0, 255] except one float
+// clamp + round half away from zero as trunc(v + 0.5) with saturation (see fused.cu: equals f32::round on
+// [0, 255] except one float); the + 0.5 is the accumulators' initial value.  cvt to u8 saturates both ends.
+__device__ __forceinline__ uint32_t quantize_u8_tile(float v_plus_half) {
+    uint32_t q;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(q) : "f"(v_plus_half));
+    return q;
 }
 
 }  // namespace
@@ -80,16 +84,18 @@ tile_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items,
         // strides equal the job's table strides; the planner only merges jobs with equal strides.)
         const float* __restrict__ gv = J.v.w + size_t(oy0) * geom.vstride;
         const float* __restrict__ gh = J.h.w + size_t(ox0) * geom.hstride;
-        for (int i = tid; i < th * geom.vstride; i += kTileThreads) vw_s[i] = __ldg(gv + i);
-        for (int i = tid; i < tw * geom.hstride; i += kTileThreads) hw_s[i] = __ldg(gh + i);
+        // The staged source bytes are used as denormal floats (b * 2^-149, no int -> float conversion); the
+        // weights carry the compensating exact powers of two (device_types.hpp).
+        for (int i = tid; i < th * geom.vstride; i += kTileThreads) vw_s[i] = __ldg(gv + i) * kRingScaleV;
+        for (int i = tid; i < tw * geom.hstride; i += kTileThreads) hw_s[i] = __ldg(gh + i) * kRingScaleH;
     }
-    // ---- stage the footprint: coalesced byte loads, converted once
+    // ---- stage the footprint: coalesced byte loads, zero-extended into float words
     {
         const uint8_t* base = J.src + size_t(sy0) * J.src_pitch + size_t(sx0) * C;
         for (int row = tid / 32; row < nrow; row += kTileThreads / 32) {
             const uint8_t* g = base + size_t(row) * J.src_pitch;
             float* s = src_f + row * pitch;
-            for (int c = tid % 32; c < ncol; c += 32) s[c] = float(__ldg(g + c));
+            for (int c = tid % 32; c < ncol; c += 32) s[c] = __uint_as_float(uint32_t(__ldg(g + c)));
         }
     }
     __syncthreads();
@@ -124,7 +130,7 @@ tile_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items,
         const int2 win = hwin[oxl];
         const float* __restrict__ w = hw_s + oxl * geom.hstride;
         const float* t = tmp_f + oyl * pitch + win.x;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float a0 = 0.5f, a1 = 0.5f, a2 = 0.5f, a3 = 0.5f;  // + 0.5: round half away from zero at the end
         if (C == 4) {
 #pragma unroll 4
             for (int i = 0; i < win.y; ++i) {
