@@ -136,14 +136,20 @@ constexpr float kRoundBias = 0.5f;  // initial value of every horizontal accumul
 // encoding.  4-channel destinations are word aligned: the planner only sends those here.
 template <int C>
 __device__ __forceinline__ void store_pixel(uint8_t* dst_px, float4 v_plus_half, int co) {
-    uint32_t w = pack_pixel(v_plus_half);
+    uint32_t w = pack_pixel(v_plus_half);  // bytes: the pixel's C channels, then don't-care lanes
+    if (C <= 2 && co >= 3) {               // grey (+ alpha) -> r, g, b (, a): the grey replicated
+        const uint32_t grey = w & 0xffu;
+        const uint32_t alpha = C == 2 ? (w >> 8) & 0xffu : 0xffu;
+        w = grey * 0x010101u | (alpha << 24);
+    } else if (C == 3) {
+        w |= 0xff000000u;                  // rgb -> rgba: opaque
+    }
     if (co == 4) {
-        if (C == 3) w |= 0xff000000u;
         *reinterpret_cast<uint32_t*>(dst_px) = w;
     } else {
         dst_px[0] = uint8_t(w);
-        dst_px[1] = uint8_t(w >> 8);
-        dst_px[2] = uint8_t(w >> 16);
+        if (co >= 2) dst_px[1] = uint8_t(w >> 8);
+        if (co >= 3) dst_px[2] = uint8_t(w >> 16);
     }
 }
 
@@ -717,13 +723,14 @@ int fused_max_src_bytes(int channels) { return (channels >= 1 && channels <= 4) 
 int fused_group_rows() { return kTmpRows; }
 
 bool fused_supported(int channels, int kv, int kh) {
-    return (channels == 3 || channels == 4) && kv >= 6 && kv <= 7 && kh >= 6 && kh <= 7;
+    return channels >= 1 && channels <= 4 && kv >= 6 && kv <= 7 && kh >= 6 && kh <= 7;
 }
 
 // Specialised uniform loops exist for the integer ratios 2 and 4 (ring size 6, a whole number of ring
 // stages per revolution) in both passes at once.
 bool fused_has_uniform(int channels, int kv, int kh, int step_v, int step_h) {
-    return fused_supported(channels, kv, kh) && kv == 6 && kh == 6 && step_v == step_h && (step_v == 2 || step_v == 4);
+    return fused_supported(channels, kv, kh) && channels >= 3 && kv == 6 && kh == 6 && step_v == step_h &&
+           (step_v == 2 || step_v == 4);
 }
 
 #endif  // !IKC_FUSED_CONV
@@ -759,6 +766,8 @@ cudaError_t launch_fused(int channels, int kv, int kh, int sv, int sh, bool conv
     IKC_CASE(4, 6, 6, 2, 2) IKC_CASE(4, 6, 6, 4, 4) IKC_CASE(3, 6, 6, 2, 2) IKC_CASE(3, 6, 6, 4, 4)
     IKC_CASE(4, 6, 6, 0, 0) IKC_CASE(4, 6, 7, 0, 0) IKC_CASE(4, 7, 6, 0, 0) IKC_CASE(4, 7, 7, 0, 0)
     IKC_CASE(3, 6, 6, 0, 0) IKC_CASE(3, 6, 7, 0, 0) IKC_CASE(3, 7, 6, 0, 0) IKC_CASE(3, 7, 7, 0, 0)
+    IKC_CASE(2, 6, 6, 0, 0) IKC_CASE(2, 6, 7, 0, 0) IKC_CASE(2, 7, 6, 0, 0) IKC_CASE(2, 7, 7, 0, 0)
+    IKC_CASE(1, 6, 6, 0, 0) IKC_CASE(1, 6, 7, 0, 0) IKC_CASE(1, 7, 6, 0, 0) IKC_CASE(1, 7, 7, 0, 0)
 #undef IKC_CASE
     return cudaErrorInvalidValue;
 }

@@ -269,3 +269,26 @@ def test_exact_2x_upscale_kernel(ctx, ik, oracle, case, content):
     assert ctx.kernel_launches - before == 1, "expected a single fused launch"
     want = oracle.resize_exact(src, 2 * w, 2 * h, filt)
     _check_fast(got, want, (case, content), max_off=0.002 if content == "noise" else 0.06)
+
+
+# ---- Luma8 / LumaA8 downscales on the ring kernel -------------------------------------------------
+LUMA_RING_CASES = [  # (h, w, c, dw, dh, out_channels or None)
+    (3024, 4032, 1, 400, 300, None), (1080, 1920, 2, 400, 225, None), (600, 800, 1, 400, 300, None),
+    (777, 1031, 2, 515, 388, None), (1080, 1920, 1, 400, 225, 3), (901, 1200, 2, 411, 309, 4),
+    (480, 640, 1, 200, 150, 4), (480, 640, 2, 200, 150, 3),
+]
+
+
+@pytest.mark.parametrize("case", LUMA_RING_CASES)
+def test_luma_downscales_on_the_ring_kernel(ctx, ik, oracle, case):
+    h, w, c, dw, dh, co = case
+    src = splitmix_noise((h, w, c), image_id=c)
+    _fast(ctx, ik)
+    before = ctx.kernel_launches
+    got = ctx.resize(src, dw, dh, ik.FILTER_LANCZOS3, out_channels=co)
+    assert ctx.kernel_launches - before == 1, "expected the single-launch fused kernel"
+    want = oracle.resize_exact(src, dw, dh, oracle.LANCZOS3)
+    if co == 3: want = oracle.to_rgb8(want)
+    if co == 4: want = oracle.to_rgba8(want)
+    if want.ndim == 2: want = want[:, :, None]
+    _check_fast(got.reshape(want.shape), want, case, max_off=0.002)
