@@ -1,7 +1,7 @@
 // fused.cu -- fused single-launch "ring" resize kernel for 8-bit downscales (sm_100a).
 //
 // This is the product's main path for the reference's actual workload: Lanczos3 downscales of
-// Rgb8/Rgba8 rasters (resize_image, /root/reference/src/transform.rs:62-90, whose arithmetic is
+// 8-bit rasters -- Rgb8/Rgba8, and Luma8/LumaA8 on the general loops -- (resize_image, /root/reference/src/transform.rs:62-90, whose arithmetic is
 // image 0.25.8 imageops::resize = vertical_sample then horizontal_sample).
 //
 // One CTA owns an output tile (column strip x row chunk) of one image of the batch.  It streams

@@ -1,4 +1,4 @@
-// launch.hpp -- host-callable launchers implemented in kernels.cu.
+// launch.hpp -- host-callable launchers of the CUDA kernels (generic.cu, fused.cu / fused_conv.cu, tile.cu, up2.cu).
 #pragma once
 #include <cuda_runtime.h>
 

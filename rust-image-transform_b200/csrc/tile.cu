@@ -1,6 +1,6 @@
-// tile.cu -- fused single-launch tile kernel: the fast path for everything the ring kernel (fused.cu)
-// does not take: upscales (BASELINE config 4: 1080p -> 4K CatmullRom), Nearest/Triangle/CatmullRom,
-// 1-2 channel rasters, mild ratios with other ring sizes.  u8 only.
+// tile.cu -- fused single-launch tile kernel: the path for every 8-bit resize that neither the ring kernel
+// (fused.cu: downscales with ring size 6-7) nor the 2x upscale kernel (up2.cu) takes: other upscales,
+// mixed up/down ratios, Nearest/Triangle/CatmullRom at mild ratios, 1-2 channel upscales.
 //
 // One CTA computes a TW x TH tile of one image of the batch.  The source footprint of the tile is
 // staged into shared memory once as f32 (a zero-extended byte is the denormal b * 2^-149; the staged weights
