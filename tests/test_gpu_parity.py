@@ -292,3 +292,49 @@ def test_luma_downscales_on_the_ring_kernel(ctx, ik, oracle, case):
     if co == 4: want = oracle.to_rgba8(want)
     if want.ndim == 2: want = want[:, :, None]
     _check_fast(got.reshape(want.shape), want, case, max_off=0.002)
+
+
+def test_randomised_parity_sweep(ctx, ik, oracle):
+    """200 random shapes / ratios / channel counts / filters / conversions (seeded), with a bias towards the exact
+    integer ratios the specialised loops detect: the cases a fixed list does not think of."""
+    rng = np.random.default_rng(20261018)
+    failures = []
+    for _ in range(200):
+        kind = rng.choice(["down_int", "down_any", "up2", "up_any", "mixed"], p=[0.3, 0.3, 0.15, 0.1, 0.15])
+        c = int(rng.choice([1, 2, 3, 4], p=[0.1, 0.1, 0.4, 0.4]))
+        filt = int(rng.choice([0, 1, 2, 3, 4], p=[0.05, 0.1, 0.2, 0.1, 0.55]))
+        if kind == "down_int":
+            r = int(rng.choice([2, 2, 2, 3, 4, 4, 5]))
+            dw, dh = int(rng.integers(8, 600)), int(rng.integers(8, 400))
+            w, h = dw * r, dh * r
+            if rng.random() < 0.3:
+                h = dh * int(rng.choice([2, 3, 4]))
+        elif kind == "down_any":
+            w, h = int(rng.integers(16, 2000)), int(rng.integers(16, 1400))
+            dw, dh = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1))
+        elif kind == "up2":
+            w, h = int(rng.integers(1, 400)), int(rng.integers(1, 300))
+            dw, dh = 2 * w, 2 * h
+        elif kind == "up_any":
+            w, h = int(rng.integers(1, 250)), int(rng.integers(1, 250))
+            dw, dh = int(rng.integers(w, 3 * w + 2)), int(rng.integers(h, 3 * h + 2))
+        else:
+            w, h = int(rng.integers(8, 1000)), int(rng.integers(8, 1000))
+            dw, dh = int(rng.integers(1, 2 * w)), int(rng.integers(1, 2 * h))
+        if (w, h) == (dw, dh):
+            dw += 1
+        co = int(rng.choice([3, 4])) if rng.random() < 0.25 else None
+        exact = rng.random() < 0.15
+        src = (checker if rng.random() < 0.2 else splitmix_noise)((h, w, c))
+        ctx.set_mode(ik.MODE_EXACT if exact else ik.MODE_FAST)
+        got = ctx.resize(src, dw, dh, filt, out_channels=co)
+        want = oracle.resize_exact(src, dw, dh, filt)
+        if co == 3:
+            want = oracle.to_rgb8(want)
+        if co == 4:
+            want = oracle.to_rgba8(want)
+        d = int(np.abs(got.astype(np.int32).reshape(want.shape) - want.astype(np.int32)).max())
+        if d > (0 if exact else 1):
+            failures.append(dict(kind=str(kind), h=h, w=w, c=c, dw=dw, dh=dh, filt=filt, co=co, exact=exact, max_delta=d))
+    ctx.set_mode(ik.MODE_FAST)
+    assert not failures, failures[:5]
