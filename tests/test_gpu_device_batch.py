@@ -113,3 +113,56 @@ def test_host_batch_shards_round_robin_over_all_devices(ik, oracle):
             assert max(abs(k) for k in hist) <= 1, hist
     finally:
         ctx.close()
+
+
+def test_randomised_prepared_batches(ctx, ik, oracle):
+    """Random jobs sharing launches: prepared batches of 8 mixed shapes / ratios / channels / conversions, so that
+    jobs with different strip and tile geometries meet in one launch of each kernel variant."""
+    import torch
+    from conftest import checker
+    ctx.set_mode(ik.MODE_FAST)
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(77)
+    failures = []
+    for _ in range(25):
+        keep, jobs, want, descs = [], [], [], []
+        filt = int(rng.choice([1, 2, 3, 4], p=[0.1, 0.2, 0.1, 0.6]))
+        for _ in range(8):
+            kind = rng.choice(["down2", "down_any", "up2", "mixed"], p=[0.3, 0.4, 0.15, 0.15])
+            c = int(rng.choice([1, 2, 3, 4], p=[0.1, 0.1, 0.4, 0.4]))
+            if kind == "down2":
+                r = int(rng.choice([2, 2, 4]))
+                dw, dh = int(rng.integers(8, 500)), int(rng.integers(8, 300))
+                w, h = dw * r, dh * r
+            elif kind == "down_any":
+                w, h = int(rng.integers(16, 1800)), int(rng.integers(16, 1200))
+                dw, dh = int(rng.integers(1, w)), int(rng.integers(1, h))
+            elif kind == "up2":
+                w, h = int(rng.integers(1, 300)), int(rng.integers(1, 200))
+                dw, dh = 2 * w, 2 * h
+            else:
+                w, h = int(rng.integers(8, 800)), int(rng.integers(8, 800))
+                dw, dh = int(rng.integers(1, 2 * w)), int(rng.integers(1, 2 * h))
+            if (w, h) == (dw, dh):
+                dw += 1
+            co = int(rng.choice([3, 4])) if rng.random() < 0.25 else c
+            s = (checker if rng.random() < 0.2 else splitmix_noise)((h, w, c))
+            ts = torch.from_numpy(s).to(dev)
+            td = torch.zeros((dh, dw, co), dtype=torch.uint8, device=dev)
+            keep.append((ts, td))
+            jobs.append((ts.data_ptr(), w, h, w * c, td.data_ptr(), dw, dh, dw * co, c | (co << 8) if co != c else c, filt))
+            r_ = oracle.resize_exact(s, dw, dh, filt)
+            r_ = r_[:, :, None] if r_.ndim == 2 else r_
+            want.append(r_ if co == c else (oracle.to_rgb8(r_) if co == 3 else oracle.to_rgba8(r_)))
+            descs.append(dict(h=h, w=w, c=c, dw=dw, dh=dh, filt=filt, co=co))
+        batch = ctx.prepare_batch(0, jobs)
+        assert all(j.status == 0 for j in batch.jobs), [j.status for j in batch.jobs]
+        stream = torch.cuda.Stream()
+        batch.launch(stream.cuda_stream)
+        stream.synchronize()
+        for (_, td), w_, dsc in zip(keep, want, descs):
+            d = int(np.abs(td.cpu().numpy().astype(np.int32) - w_.astype(np.int32)).max())
+            if d > 1:
+                failures.append((dsc, d, batch.describe()))
+        batch.free()
+    assert not failures, failures[:4]
