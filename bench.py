@@ -270,6 +270,11 @@ def main():
     kernel_ms = (ms_total / args.steps) / max(1, launches_per_step)  # this rank's average launch duration
     peak, peak_src = measured_peak()
     achieved = algo_bytes / max(1, launches_per_step) / (kernel_ms * 1e-3) / 1e9
+    # The same launch against the FP32 pipe: algorithmic FMAs = one per tap, channel and sample of each pass
+    # (vertical pass over sw columns, then horizontal over dh rows), tap counts from the planner's own tables.
+    _, cnt_v, _ = ik.pass_table(filt, sh, dh)
+    _, cnt_h, _ = ik.pass_table(filt, sw, dw)
+    algo_fma = batch * ch * (sw * int(cnt_v.sum()) + dh * int(cnt_h.sum()))
 
     # ---- end to end through the C ABI with pinned HOST buffers (H2D + kernel + D2H inside the timed region)
     eb = max(1, min(args.e2e_batch, batch))
@@ -326,6 +331,12 @@ def main():
                      "kernel": prepared.describe(),
                      "algorithmic_bytes_per_launch": algo_bytes // max(1, launches_per_step),
                      "kernel_ms": kernel_ms},
+        "roofline_fp32": {"note": "secondary: Lanczos3 downscales sit above the FP32 ridge, so the FMA pipe, not HBM, "
+                                  "is their ceiling (DESIGN.md 4.1); peak = 128 FMA/clk/SM x SMs x max SM clock",
+                          "achieved": algo_fma / max(1, launches_per_step) / (kernel_ms * 1e-3) / 1e12,
+                          "peak": 128 * torch.cuda.get_device_properties(dev).multi_processor_count *
+                                  (clocks.max_mhz or 1965) * 1e6 / 1e12,
+                          "unit": "TFMA/s", "algorithmic_fma_per_launch": algo_fma // max(1, launches_per_step)},
         "cpu_baseline": cpu,
         "cpu_baseline_all_cores": cpu_mt,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": eb * sw * sh * ch,
@@ -335,6 +346,7 @@ def main():
         "clocks": clocks.summary(),
         "parity": parity,
     }
+    line["roofline_fp32"]["frac"] = line["roofline_fp32"]["achieved"] / line["roofline_fp32"]["peak"]
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
