@@ -131,3 +131,60 @@ pub fn resize_image_for(img: DynamicImage, w: Option<u32>, h: Option<u32>, rgba:
         DynamicImage::ImageRgb8(ImageBuffer::from_raw(tw, th, out).expect("size matches"))
     })
 }
+
+/// Batched `resize_image`: N independent uploads in one call, sharded round-robin over the box's GPUs
+/// (job i -> device i mod G) by `ikc_resize_batch`; no collective, images never leave their GPU.
+/// 8-bit variants only; an entry is `Err` if its image could not be resized (the others still are).
+/// `(None, None)` entries and same-size targets come back unchanged, as in `resize_image`.
+pub fn resize_batch(images: Vec<DynamicImage>, targets: &[(Option<u32>, Option<u32>)]) -> Vec<Result<DynamicImage, String>> {
+    assert_eq!(images.len(), targets.len());
+    let ctx = match ctx() {
+        Ok(c) => c,
+        Err(e) => return images.iter().map(|_| Err(e.clone())).collect(),
+    };
+    struct Slot { job: Option<usize>, ch: u32, tw: u32, th: u32, out: Vec<u8> }
+    let mut slots: Vec<Slot> = Vec::with_capacity(images.len());
+    let mut jobs: Vec<ffi::ikc_job> = Vec::new();
+    for (img, &(w, h)) in images.iter().zip(targets) {
+        let (ow, oh) = img.dimensions();
+        let (mut tw, mut th) = (0u32, 0u32);
+        let code = unsafe {
+            ffi::ikc_target_dims(ow, oh, w.is_some() as i32, w.unwrap_or(0), h.is_some() as i32, h.unwrap_or(0), &mut tw, &mut th)
+        };
+        let raw: Option<(&[u8], u32)> = match img {
+            DynamicImage::ImageLuma8(b) => Some((b.as_raw(), 1)),
+            DynamicImage::ImageLumaA8(b) => Some((b.as_raw(), 2)),
+            DynamicImage::ImageRgb8(b) => Some((b.as_raw(), 3)),
+            DynamicImage::ImageRgba8(b) => Some((b.as_raw(), 4)),
+            _ => None,
+        };
+        match raw {
+            Some((bytes, ch)) if (w.is_some() || h.is_some()) && code == ffi::IKC_DIMS_RESAMPLE => {
+                let mut out = vec![0u8; tw as usize * th as usize * ch as usize];
+                jobs.push(ffi::ikc_job {
+                    src: bytes.as_ptr() as *const _, dst: out.as_mut_ptr() as *mut _, sw: ow, sh: oh, dw: tw, dh: th,
+                    src_pitch: (ow * ch) as usize, dst_pitch: (tw * ch) as usize, channels: ch as i32,
+                    filter: ffi::IKC_FILTER_LANCZOS3, status: 0, device: 0,
+                });
+                slots.push(Slot { job: Some(jobs.len() - 1), ch, tw, th, out });
+            }
+            _ => slots.push(Slot { job: None, ch: 0, tw, th, out: Vec::new() }),
+        }
+    }
+    if !jobs.is_empty() {
+        unsafe { ffi::ikc_resize_batch(ctx, jobs.as_mut_ptr(), jobs.len()) };  // per-job results are in jobs[i].status
+    }
+    images.into_iter().zip(targets).zip(slots).map(|((img, &(w, h)), s)| match s.job {
+        None => resize_image(img, w, h),  // passthrough, clone, 16-bit: the single-image path
+        Some(j) if jobs[j].status != ffi::IKC_OK => Err(format!("resize failed with status {}", jobs[j].status)),
+        Some(_) => {
+            let out = s.out;
+            Ok(match s.ch {
+                1 => DynamicImage::ImageLuma8(ImageBuffer::from_raw(s.tw, s.th, out).expect("size matches")),
+                2 => DynamicImage::ImageLumaA8(ImageBuffer::from_raw(s.tw, s.th, out).expect("size matches")),
+                3 => DynamicImage::ImageRgb8(ImageBuffer::from_raw(s.tw, s.th, out).expect("size matches")),
+                _ => DynamicImage::ImageRgba8(ImageBuffer::from_raw(s.tw, s.th, out).expect("size matches")),
+            })
+        }
+    }).collect()
+}
