@@ -200,6 +200,11 @@ IKC_API int ikc_resize_batch(ikc_ctx* ctx, ikc_job* jobs, size_t n);
 /* Pinned host memory for callers that want zero-copy staging (decode straight into it). */
 IKC_API int ikc_host_alloc(size_t bytes, void** out);
 IKC_API void ikc_host_free(void* p);
+/* Page-lock memory the caller already owns (e.g. the Vec<u8> a decoder filled, src/transform.rs:27-43), so
+ * that the entry points above DMA from / to it directly instead of staging through the lane's pinned
+ * buffers.  Unregister before the memory is freed.  (cudaHostRegister / cudaHostUnregister.) */
+IKC_API int ikc_host_register(void* p, size_t bytes);
+IKC_API int ikc_host_unregister(void* p);
 
 /* ---- device-resident entry points (no PCIe; what the roofline is measured on) --------------- */
 

@@ -229,6 +229,14 @@ int ikc_host_alloc(size_t bytes, void** out) {
 void ikc_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
+int ikc_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return IKC_ERR_INVALID_ARG;
+    return guarded([&] { check_cuda(cudaHostRegister(p, bytes, cudaHostRegisterPortable), "cudaHostRegister"); });
+}
+int ikc_host_unregister(void* p) {
+    if (!p) return IKC_ERR_INVALID_ARG;
+    return guarded([&] { check_cuda(cudaHostUnregister(p), "cudaHostUnregister"); });
+}
 
 int ikc_resize_u8_device(ikc_ctx* ctx, int device_index, void* stream, const uint8_t* d_src, uint32_t sw,
                          uint32_t sh, size_t src_pitch, int channels, uint8_t* d_dst, uint32_t dw, uint32_t dh,

@@ -23,7 +23,7 @@ MAX_DIM, MAX_PIXELS = 65535, 1 << 28  # IKC_MAX_DIM, IKC_MAX_PIXELS
 EXPORTS = [
     "ikc_create", "ikc_destroy", "ikc_device_count", "ikc_set_mode", "ikc_get_mode", "ikc_kernel_launches",
     "ikc_last_error", "ikc_version", "ikc_target_dims", "ikc_pass_table", "ikc_pass_info", "ikc_resize_u8", "ikc_resize_u16",
-    "ikc_resize_convert_u8", "ikc_resize_image_u8", "ikc_resize_batch", "ikc_host_alloc", "ikc_host_free", "ikc_resize_u8_device",
+    "ikc_resize_convert_u8", "ikc_resize_image_u8", "ikc_resize_batch", "ikc_host_alloc", "ikc_host_free", "ikc_host_register", "ikc_host_unregister", "ikc_resize_u8_device",
     "ikc_batch_prepare", "ikc_batch_launch", "ikc_batch_launch_count", "ikc_batch_describe", "ikc_batch_free",
 ]
 
@@ -95,6 +95,10 @@ def load() -> C.CDLL:
     L.ikc_host_alloc.restype = i32
     L.ikc_host_free.argtypes = [vp]
     L.ikc_host_free.restype = None
+    L.ikc_host_register.argtypes = [vp, sz]
+    L.ikc_host_register.restype = i32
+    L.ikc_host_unregister.argtypes = [vp]
+    L.ikc_host_unregister.restype = i32
     L.ikc_resize_u8_device.argtypes = [vp, i32, vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32]
     L.ikc_resize_u8_device.restype = i32
     L.ikc_batch_prepare.argtypes = [vp, i32, C.POINTER(Job), sz, C.POINTER(vp)]

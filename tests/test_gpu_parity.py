@@ -338,3 +338,20 @@ def test_randomised_parity_sweep(ctx, ik, oracle):
             failures.append(dict(kind=str(kind), h=h, w=w, c=c, dw=dw, dh=dh, filt=filt, co=co, exact=exact, max_delta=d))
     ctx.set_mode(ik.MODE_FAST)
     assert not failures, failures[:5]
+
+
+def test_registered_host_memory_is_used_in_place(ctx, ik, oracle):
+    """ikc_host_register: the caller's own (pageable) buffers are page-locked and DMA'd directly; same result."""
+    L = ik._lib.load()
+    src = splitmix_noise((600, 800, 3), image_id=21)
+    dst = np.empty((300, 400, 3), np.uint8)
+    assert L.ikc_host_register(src.ctypes.data, src.nbytes) == 0
+    assert L.ikc_host_register(dst.ctypes.data, dst.nbytes) == 0
+    try:
+        _fast(ctx, ik)
+        ctx.resize(src, 400, 300, ik.FILTER_LANCZOS3, out=dst)
+        _check_fast(dst, oracle.resize_exact(src, 400, 300, oracle.LANCZOS3), "registered")
+    finally:
+        assert L.ikc_host_unregister(src.ctypes.data) == 0
+        assert L.ikc_host_unregister(dst.ctypes.data) == 0
+    assert L.ikc_host_register(None, 16) != 0
