@@ -112,3 +112,27 @@ def test_exact_2x_upscale_frame(ik, oracle, filt, n_in):
     assert np.any(left == base) and np.any(left + count == base + info["up2_taps"])      # and the frame is tight
     assert 0 <= info["up2_uni_lo"] < info["up2_uni_hi"] <= n_in
     assert engine.pass_info(filt, n_in, 2 * n_in + 1)["up2_taps"] == 0                   # not an exact 2x upscale
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: include/imagekit_cuda.h must compile as C99 and a C program must link the library."""
+    import os, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "rust-image-transform_b200")
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "imagekit_cuda.h"\n'
+                   "int main(void) {\n"
+                   "    ikc_pass_info_t info; ikc_job job; uint32_t tw = 0, th = 0;\n"
+                   "    (void)job;\n"
+                   "    if (ikc_version() <= 0) return 1;\n"
+                   "    if (ikc_target_dims(1920, 1080, 1, 400, 0, 0, &tw, &th) != 0 || tw != 400 || th != 225) return 2;\n"
+                   "    if (ikc_pass_info(IKC_FILTER_LANCZOS3, 2160, 1080, &info) != 0 || info.ring_k != 6 || info.uni_step != 2) return 3;\n"
+                   "    return IKC_CHANNELS(4, 3) == (4 | (3 << 8)) ? 0 : 4;\n"
+                   "}\n")
+    exe = tmp_path / "abi"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                           str(src), "-o", str(exe), "-L", lib_dir, "-limagekit_cuda", f"-Wl,-rpath,{lib_dir}"])
+    assert subprocess.call([str(exe)]) == 0
