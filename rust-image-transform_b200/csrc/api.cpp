@@ -342,7 +342,7 @@ int ikc_batch_describe(const ikc_batch* b, char* out, size_t cap) {
     for (auto& g : b->impl.lp.groups) {
         if (!s.empty()) s += "; ";
         if (g.up_taps) s += "up2_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.up_taps) + ">";
-        else if (g.kv == 0) s += "tile_kernel";
+        else if (g.kv == 0) s += g.bps == 2 ? "tile_kernel<u16>" : "tile_kernel";
         else s += "fused_ring_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.kv) + "," + std::to_string(g.kh) + "," + std::to_string(g.sv) + "," + std::to_string(g.sh) + ">";
         s += " x " + std::to_string(g.items.size()) + (g.up_taps ? " tiles (persistent CTAs)" : " CTAs");
     }

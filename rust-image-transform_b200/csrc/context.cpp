@@ -274,7 +274,8 @@ bool cut_strips(const PassPlan& h, int ch, int sw, int max_src, int max_out, std
 
 // Cut a job into output tiles for the tile kernel and grow `geom` to cover their source footprints.
 // Returns false (and leaves the outputs untouched) when no tile shape fits the shared-memory budget.
-bool plan_tiles(const PassPlan& v, const PassPlan& h, int ch, int och, int job, std::vector<WorkItem>* items, TileGeom* geom) {
+bool plan_tiles(const PassPlan& v, const PassPlan& h, int ch, int och, int bps, int job, std::vector<WorkItem>* items,
+                TileGeom* geom) {
     const int dw = int(h.n_out), dh = int(v.n_out);
     auto footprint = [](const PassPlan& p, int n_out, int t) {  // widest source span of any tile of t outputs
         int worst = 0;
@@ -294,7 +295,7 @@ bool plan_tiles(const PassPlan& v, const PassPlan& h, int ch, int och, int job, 
                 TileGeom probe{};
                 probe.pitch_f = pitch; probe.max_src_rows = rows; probe.max_tile_rows = t_h; probe.max_tile_cols = t_w;
                 probe.vstride = int(v.stride); probe.hstride = int(h.stride);
-                probe.out_pitch_b = ((t_w * och + 3) & ~3) + 4;
+                probe.out_pitch_b = ((t_w * och * bps + 3) & ~3) + 4;
                 const size_t smem = tile_smem_bytes(probe);
                 if (smem <= limit) { best_tw = t_w; best_th = t_h; best_rows = rows; best_pitch = pitch; break; }
             }
@@ -313,7 +314,7 @@ bool plan_tiles(const PassPlan& v, const PassPlan& h, int ch, int och, int job, 
     if (geom->pitch_f != 0 && (geom->vstride != int(v.stride) || geom->hstride != int(h.stride))) return false;
     merged.vstride = int(v.stride);
     merged.hstride = int(h.stride);
-    merged.out_pitch_b = std::max(merged.out_pitch_b, ((best_tw * och + 3) & ~3) + 4);
+    merged.out_pitch_b = std::max(merged.out_pitch_b, ((best_tw * och * bps + 3) & ~3) + 4);
     if (tile_smem_bytes(merged) > (size_t(110) << 10)) return false;
     *geom = merged;
     for (int oy = 0; oy < dh; oy += best_th)
@@ -334,8 +335,8 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         bool convert;
     };
     std::vector<Cand> cands;
-    std::vector<WorkItem> tile_items;
-    TileGeom tile_geom{};
+    std::vector<WorkItem> tile_items[2];  // [bytes per sample - 1]: one tile-kernel launch per sample type
+    TileGeom tile_geom[2]{};
     lp.jobs.reserve(n);
     for (size_t i = 0; i < n; ++i) {
         status[i] = kOk;
@@ -393,7 +394,8 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
                 for (int oy = 0; oy < int(d.dh); oy += tile_h)
                     for (int ox = 0; ox < int(d.dw); ox += tile_w)
                         g->items.push_back(WorkItem{idx, ox, std::min(int(d.dw), ox + tile_w), oy, std::min(int(d.dh), oy + tile_h)});
-            } else if (!exact && d.bps == 1 && plan_tiles(*tv->host, *th->host, d.channels, d.oc(), idx, &tile_items, &tile_geom)) {
+            } else if (!exact && plan_tiles(*tv->host, *th->host, d.channels, d.oc(), d.bps, idx, &tile_items[d.bps - 1],
+                                            &tile_geom[d.bps - 1])) {
                 // taken by the tile kernel
             } else {
                 lp.generic_jobs.push_back(idx);
@@ -404,9 +406,11 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
             set_last_error(e.what);
         }
     }
-    if (!tile_items.empty()) {
-        FusedGroup g{0, 0, 0, std::move(tile_items), {}, tile_geom};
+    for (int b = 0; b < 2; ++b) {
+        if (tile_items[b].empty()) continue;
+        FusedGroup g{0, 0, 0, std::move(tile_items[b]), {}, tile_geom[b]};
         g.tgeom.n_items = int(g.items.size());
+        g.bps = b + 1;
         lp.groups.push_back(std::move(g));
     }
     if (cands.empty()) return lp;
@@ -493,7 +497,7 @@ void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, 
     for (auto& g : lp.groups) {
         const WorkItem* d_items = reinterpret_cast<const WorkItem*>(d_desc_base + off);
         if (g.up_taps) check_cuda(launch_up2(g.channels, g.up_taps, d_jobs, d_items, int(g.items.size()), stream), "launch up2_kernel");
-        else if (g.kv == 0) check_cuda(launch_tile(d_jobs, d_items, g.tgeom, stream), "launch tile_kernel");
+        else if (g.kv == 0) check_cuda(launch_tile(g.bps, d_jobs, d_items, g.tgeom, stream), "launch tile_kernel");
         else check_cuda(launch_fused(g.channels, g.kv, g.kh, g.sv, g.sh, g.convert, d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");
         off += (sizeof(WorkItem) * g.items.size() + 15) & ~size_t(15);
         launches.fetch_add(1, std::memory_order_relaxed);

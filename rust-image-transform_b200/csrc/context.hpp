@@ -61,6 +61,7 @@ struct FusedGroup {  // one kernel launch over a list of work items
     int sv = 0, sh = 0;    // ring kernel: uniform vertical / horizontal step the launch is specialised for (0 = none)
     bool convert = false;  // ring kernel: the jobs store another channel count than they read
     int up_taps = 0;       // > 0 (with kv == 0): an exact-2x upscale launch (up2.cu) with this tap frame
+    int bps = 1;           // tile-kernel launch: bytes per sample of its jobs (1 or 2)
 };
 
 // Everything needed to enqueue a set of device-resident jobs.

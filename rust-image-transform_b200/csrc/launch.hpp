@@ -25,7 +25,8 @@ cudaError_t launch_fused(int channels, int ring_k_v, int ring_k_h, int step_v, i
 
 // Tile kernel (tile.cu): output-stationary fused passes over shared-memory tiles.
 size_t tile_smem_bytes(const TileGeom& geom);
-cudaError_t launch_tile(const DevJob* jobs, const WorkItem* items, const TileGeom& geom, cudaStream_t stream);
+cudaError_t launch_tile(int bytes_per_sample, const DevJob* jobs, const WorkItem* items, const TileGeom& geom,
+                        cudaStream_t stream);
 
 // Exact 2x upscale kernel (up2.cu).  Work items are output tiles of up2_tile_w(channels) x up2_tile_h().
 bool up2_supported(int channels, int taps_v, int taps_h);

@@ -24,9 +24,11 @@ constexpr int kTileThreads = 256;
 
 // clamp + round half away from zero as trunc(v + 0.5) with saturation (see fused.cu: equals f32::round on
 // [0, 255] except one float); the + 0.5 is the accumulators' initial value.  cvt to u8 saturates both ends.
-__device__ __forceinline__ uint32_t quantize_u8_tile(float v_plus_half) {
+template <typename T>
+__device__ __forceinline__ uint32_t quantize_tile(float v_plus_half) {
     uint32_t q;
-    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(q) : "f"(v_plus_half));
+    if (sizeof(T) == 1) asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(q) : "f"(v_plus_half));
+    else asm("cvt.rzi.u16.f32 %0, %1;" : "=r"(q) : "f"(v_plus_half));
     return q;
 }
 
@@ -39,6 +41,9 @@ __device__ __forceinline__ uint32_t quantize_u8_tile(float v_plus_half) {
 // Shared memory: [src f32: max_src_rows x pitch][tmp f32: max_tile_rows x pitch]
 //                [v (left,count): max_tile_rows][h (left,count): max_tile_cols]
 //                [v weights: max_tile_rows x vstride][h weights: max_tile_cols x hstride][out bytes: rows x out_pitch]
+// T = uint8_t or uint16_t samples (Luma16 / LumaA16 / Rgb16 / Rgba16 rasters from the PNG decoder: same
+// passes, clamp to 65535; a 16-bit sample is still a denormal float, so the same weight scaling applies).
+template <typename T>
 __global__ void __launch_bounds__(kTileThreads, 4)
 tile_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, const TileGeom geom) {
     extern __shared__ __align__(16) float tile_smem[];
@@ -67,8 +72,8 @@ tile_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items,
     int2* hwin = vwin + geom.max_tile_rows;                                             // ((first - sx0) * C, taps)
     float* vw_s = reinterpret_cast<float*>(hwin + geom.max_tile_cols);                  // [th][vstride]
     float* hw_s = vw_s + size_t(geom.max_tile_rows) * geom.vstride;                     // [tw][hstride]
-    uint8_t* out_s = reinterpret_cast<uint8_t*>(hw_s + size_t(geom.max_tile_cols) * geom.hstride);  // [th][out_pitch]
-    const int out_pitch = geom.out_pitch_b;
+    T* out_s = reinterpret_cast<T*>(hw_s + size_t(geom.max_tile_cols) * geom.hstride);  // [th][out_pitch bytes]
+    const int out_pitch = geom.out_pitch_b / int(sizeof(T));  // in samples
 
     // ---- stage windows + weights of the tile's output rows / columns
     for (int i = tid; i < th; i += kTileThreads) {
@@ -91,9 +96,9 @@ tile_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items,
     }
     // ---- stage the footprint: coalesced byte loads, zero-extended into float words
     {
-        const uint8_t* base = J.src + size_t(sy0) * J.src_pitch + size_t(sx0) * C;
+        const uint8_t* base = J.src + size_t(sy0) * J.src_pitch + size_t(sx0) * C * sizeof(T);
         for (int row = tid / 32; row < nrow; row += kTileThreads / 32) {
-            const uint8_t* g = base + size_t(row) * J.src_pitch;
+            const T* g = reinterpret_cast<const T*>(base + size_t(row) * J.src_pitch);
             float* s = src_f + row * pitch;
             for (int c = tid % 32; c < ncol; c += 32) s[c] = __uint_as_float(uint32_t(__ldg(g + c)));
         }
@@ -153,9 +158,9 @@ tile_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items,
         } else {
             for (int i = 0; i < win.y; ++i) a0 = fmaf(t[i], w[i], a0);
         }
-        uint8_t* d = out_s + oyl * out_pitch + oxl * CO;
-        const uint8_t q0 = uint8_t(quantize_u8_tile(a0)), q1 = uint8_t(quantize_u8_tile(a1));
-        const uint8_t q2 = uint8_t(quantize_u8_tile(a2)), q3 = uint8_t(quantize_u8_tile(a3));
+        T* d = out_s + oyl * out_pitch + oxl * CO;
+        const T q0 = T(quantize_tile<T>(a0)), q1 = T(quantize_tile<T>(a1));
+        const T q2 = T(quantize_tile<T>(a2)), q3 = T(quantize_tile<T>(a3));
         if (CO == C) {
             d[0] = q0;
             if (C > 1) d[1] = q1;
@@ -165,19 +170,19 @@ tile_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items,
             d[0] = q0;
             d[1] = C >= 3 ? q1 : q0;
             d[2] = C >= 3 ? q2 : q0;
-            if (CO == 4) d[3] = C == 2 ? q1 : 255;
+            if (CO == 4) d[3] = C == 2 ? q1 : T(255);  // (conversions exist for 8-bit rasters only)
         }
     }
     __syncthreads();
 
     // ---- store the tile: whole 32-bit words where the destination allows, bytes at the ragged ends
     {
-        const int row_bytes = tw * CO;
+        const int row_bytes = tw * CO * int(sizeof(T));
         const int warp = tid >> 5, lane = tid & 31;
         for (int row = warp; row < th; row += kTileThreads / 32) {
-            const uint8_t* sb = out_s + row * out_pitch;
+            const uint8_t* sb = reinterpret_cast<const uint8_t*>(out_s + row * out_pitch);
             const uint32_t* sw_ = reinterpret_cast<const uint32_t*>(sb);
-            uint8_t* g = J.dst + size_t(oy0 + row) * J.dst_pitch + size_t(ox0) * CO;
+            uint8_t* g = J.dst + size_t(oy0 + row) * J.dst_pitch + size_t(ox0) * CO * sizeof(T);
             const int head = min(row_bytes, int((4 - (reinterpret_cast<uintptr_t>(g) & 3)) & 3));
             const int nwords = (row_bytes - head) >> 2;
             if (lane < head) g[lane] = sb[lane];
@@ -196,11 +201,13 @@ size_t tile_smem_bytes(const TileGeom& g) {
            (size_t(g.max_tile_rows) + size_t(g.max_tile_cols)) * sizeof(int2) + size_t(g.max_tile_rows) * g.out_pitch_b;
 }
 
-cudaError_t launch_tile(const DevJob* jobs, const WorkItem* items, const TileGeom& geom, cudaStream_t stream) {
+cudaError_t launch_tile(int bytes_per_sample, const DevJob* jobs, const WorkItem* items, const TileGeom& geom,
+                        cudaStream_t stream) {
     const size_t smem = tile_smem_bytes(geom);
-    cudaError_t e = cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    const auto kernel = bytes_per_sample == 2 ? tile_kernel<uint16_t> : tile_kernel<uint8_t>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    tile_kernel<<<geom.n_items, kTileThreads, smem, stream>>>(jobs, items, geom);
+    kernel<<<geom.n_items, kTileThreads, smem, stream>>>(jobs, items, geom);
     return cudaGetLastError();
 }
 

@@ -355,3 +355,24 @@ def test_registered_host_memory_is_used_in_place(ctx, ik, oracle):
         assert L.ikc_host_unregister(src.ctypes.data) == 0
         assert L.ikc_host_unregister(dst.ctypes.data) == 0
     assert L.ikc_host_register(None, 16) != 0
+
+
+# ---- 16-bit rasters on the tile kernel (Luma16 / LumaA16 / Rgb16 / Rgba16 from PNG) ---------------
+@pytest.mark.parametrize("shape", [(90, 120, 3, 50, 41), (200, 300, 1, 150, 100), (64, 48, 4, 96, 128), (120, 160, 2, 161, 119),
+                                   (300, 400, 3, 200, 150), (37, 53, 4, 100, 80)])
+@pytest.mark.parametrize("filt", [1, 2, 4])
+def test_u16_rasters_single_launch(ctx, ik, oracle, shape, filt):
+    h, w, c, dw, dh = shape
+    rng = np.random.default_rng(h * 7 + filt)
+    src = rng.integers(0, 65536, (h, w, c), dtype=np.uint16)
+    src[: h // 4] = 65535                      # saturated and black bands: overshoot must clamp at both ends
+    src[h // 4: h // 2, : w // 2] = 0
+    _fast(ctx, ik)
+    before = ctx.kernel_launches
+    got = ctx.resize(src, dw, dh, filt)
+    assert ctx.kernel_launches - before == 1, "expected the single-launch tile kernel"
+    want = oracle.resize_exact(src, dw, dh, filt)
+    assert np.abs(got.astype(np.int64) - want.astype(np.int64)).max() <= 1
+    ctx.set_mode(ik.MODE_EXACT)
+    assert np.array_equal(ctx.resize(src, dw, dh, filt), want)
+    ctx.set_mode(ik.MODE_FAST)
