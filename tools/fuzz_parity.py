@@ -41,6 +41,8 @@ for case in range(n_cases):
     if rng.random() < 0.25: co = int(rng.choice([3, 4]))
     exact = rng.random() < 0.15
     src = (checker if rng.random() < 0.2 else splitmix_noise)((h, w, c))
+    if co is None and rng.random() < 0.15:  # 16-bit rasters (tile / generic kernels)
+        src = (src.astype(np.uint16) * 257) ^ rng.integers(0, 256, src.shape, dtype=np.uint16)
     ctx.set_mode(ik.MODE_EXACT if exact else ik.MODE_FAST)
     got = ctx.resize(src, dw, dh, filt, out_channels=co)
     want = oracle.resize_exact(src, dw, dh, filt)
