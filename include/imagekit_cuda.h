@@ -136,6 +136,13 @@ IKC_API int ikc_version(void);                               /* major*1000 + min
 IKC_API int ikc_target_dims(uint32_t ow, uint32_t oh, int has_w, uint32_t w, int has_h, uint32_t h,
                             uint32_t* tw, uint32_t* th);
 
+/* The library's size guard, callable before any buffer is allocated: IKC_OK, or IKC_ERR_TOO_LARGE when a
+ * source or destination side exceeds IKC_MAX_DIM or an area exceeds IKC_MAX_PIXELS.  The reference has
+ * no upper bound on w / h (src/lib.rs:61-63): the Rust wrapper calls this on the ikc_target_dims result
+ * BEFORE sizing its output Vec, so an absurd request becomes a TransformError (HTTP 400, src/lib.rs:182)
+ * instead of an allocation abort.  Needs no context and no GPU. */
+IKC_API int ikc_check_dims(uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh);
+
 /* Inspection of the window/weight table of one separable pass n_in -> n_out (the host-built table
  * the kernels consume; image 0.25.8 imageops/sample.rs window + weight loop).  With weights == NULL
  * returns the per-output stride needed; otherwise fills left[n_out], count[n_out] and

@@ -37,6 +37,7 @@ extern "C" {
     pub fn ikc_destroy(ctx: *mut ikc_ctx);
     pub fn ikc_device_count(ctx: *const ikc_ctx) -> c_int;
     pub fn ikc_last_error() -> *const c_char;
+    pub fn ikc_check_dims(sw: u32, sh: u32, dw: u32, dh: u32) -> c_int;
     pub fn ikc_target_dims(ow: u32, oh: u32, has_w: c_int, w: u32, has_h: c_int, h: u32, tw: *mut u32, th: *mut u32) -> c_int;
     pub fn ikc_resize_u8(ctx: *mut ikc_ctx, src: *const u8, sw: u32, sh: u32, src_pitch: usize, channels: c_int,
                          dst: *mut u8, dw: u32, dh: u32, dst_pitch: usize, filter: c_int) -> c_int;

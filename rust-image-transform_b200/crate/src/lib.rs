@@ -32,20 +32,36 @@ fn ctx() -> Result<*mut ffi::ikc_ctx, String> {
     .map_err(|e| e.clone())
 }
 
+/// The reference puts no upper bound on `w` / `h` (src/lib.rs:61-63), so a request for w = 4e9 reaches
+/// this crate.  The library's own bound (IKC_MAX_DIM / IKC_MAX_PIXELS) is checked here, BEFORE the
+/// output vector is allocated: the request then fails with a TransformError (HTTP 400) instead of
+/// aborting the process in `vec!`.
+fn check_dims(sw: u32, sh: u32, dw: u32, dh: u32) -> Result<(), String> {
+    let rc = unsafe { ffi::ikc_check_dims(sw, sh, dw, dh) };
+    if rc == ffi::IKC_OK { Ok(()) } else { Err(last_error()) }
+}
+
+/// Bytes of one tight row, in usize (a u32 product would wrap for wide 16-bit rasters).
+fn row_bytes(width: u32, ch: u32, bytes_per_sample: usize) -> usize {
+    width as usize * ch as usize * bytes_per_sample
+}
+
 fn resize_u8(raw: &[u8], sw: u32, sh: u32, ch: u32, dw: u32, dh: u32) -> Result<Vec<u8>, String> {
-    let mut out = vec![0u8; dw as usize * dh as usize * ch as usize];
+    check_dims(sw, sh, dw, dh)?;
+    let mut out = vec![0u8; row_bytes(dw, ch, 1) * dh as usize];
     let rc = unsafe {
-        ffi::ikc_resize_u8(ctx()?, raw.as_ptr(), sw, sh, (sw * ch) as usize, ch as i32, out.as_mut_ptr(), dw, dh,
-                           (dw * ch) as usize, ffi::IKC_FILTER_LANCZOS3)
+        ffi::ikc_resize_u8(ctx()?, raw.as_ptr(), sw, sh, row_bytes(sw, ch, 1), ch as i32, out.as_mut_ptr(), dw, dh,
+                           row_bytes(dw, ch, 1), ffi::IKC_FILTER_LANCZOS3)
     };
     if rc == ffi::IKC_OK { Ok(out) } else { Err(last_error()) }
 }
 
 fn resize_u16(raw: &[u16], sw: u32, sh: u32, ch: u32, dw: u32, dh: u32) -> Result<Vec<u16>, String> {
-    let mut out = vec![0u16; dw as usize * dh as usize * ch as usize];
+    check_dims(sw, sh, dw, dh)?;
+    let mut out = vec![0u16; dw as usize * ch as usize * dh as usize];
     let rc = unsafe {
-        ffi::ikc_resize_u16(ctx()?, raw.as_ptr(), sw, sh, (sw * ch * 2) as usize, ch as i32, out.as_mut_ptr(), dw, dh,
-                            (dw * ch * 2) as usize, ffi::IKC_FILTER_LANCZOS3)
+        ffi::ikc_resize_u16(ctx()?, raw.as_ptr(), sw, sh, row_bytes(sw, ch, 2), ch as i32, out.as_mut_ptr(), dw, dh,
+                            row_bytes(dw, ch, 2), ffi::IKC_FILTER_LANCZOS3)
     };
     if rc == ffi::IKC_OK { Ok(out) } else { Err(last_error()) }
 }
@@ -117,10 +133,11 @@ pub fn resize_image_for(img: DynamicImage, w: Option<u32>, h: Option<u32>, rgba:
     if (w.is_none() && h.is_none()) || code != ffi::IKC_DIMS_RESAMPLE || co == ch {
         return resize_image(img, w, h);
     }
-    let mut out = vec![0u8; tw as usize * th as usize * co as usize];
+    check_dims(ow, oh, tw, th)?;  // before the allocation: see check_dims
+    let mut out = vec![0u8; row_bytes(tw, co, 1) * th as usize];
     let rc = unsafe {
-        ffi::ikc_resize_convert_u8(ctx()?, raw.as_ptr(), ow, oh, (ow * ch) as usize, ch as i32, out.as_mut_ptr(), tw, th,
-                                   (tw * co) as usize, co as i32, ffi::IKC_FILTER_LANCZOS3)
+        ffi::ikc_resize_convert_u8(ctx()?, raw.as_ptr(), ow, oh, row_bytes(ow, ch, 1), ch as i32, out.as_mut_ptr(), tw, th,
+                                   row_bytes(tw, co, 1), co as i32, ffi::IKC_FILTER_LANCZOS3)
     };
     if rc != ffi::IKC_OK {
         return Err(last_error());
@@ -142,7 +159,7 @@ pub fn resize_batch(images: Vec<DynamicImage>, targets: &[(Option<u32>, Option<u
         Ok(c) => c,
         Err(e) => return images.iter().map(|_| Err(e.clone())).collect(),
     };
-    struct Slot { job: Option<usize>, ch: u32, tw: u32, th: u32, out: Vec<u8> }
+    struct Slot { job: Option<usize>, ch: u32, tw: u32, th: u32, out: Vec<u8>, err: Option<String> }
     let mut slots: Vec<Slot> = Vec::with_capacity(images.len());
     let mut jobs: Vec<ffi::ikc_job> = Vec::new();
     for (img, &(w, h)) in images.iter().zip(targets) {
@@ -160,21 +177,26 @@ pub fn resize_batch(images: Vec<DynamicImage>, targets: &[(Option<u32>, Option<u
         };
         match raw {
             Some((bytes, ch)) if (w.is_some() || h.is_some()) && code == ffi::IKC_DIMS_RESAMPLE => {
-                let mut out = vec![0u8; tw as usize * th as usize * ch as usize];
+                if let Err(e) = check_dims(ow, oh, tw, th) {  // before the allocation: see check_dims
+                    slots.push(Slot { job: None, ch, tw, th, out: Vec::new(), err: Some(e) });
+                    continue;
+                }
+                let mut out = vec![0u8; row_bytes(tw, ch, 1) * th as usize];
                 jobs.push(ffi::ikc_job {
                     src: bytes.as_ptr() as *const _, dst: out.as_mut_ptr() as *mut _, sw: ow, sh: oh, dw: tw, dh: th,
-                    src_pitch: (ow * ch) as usize, dst_pitch: (tw * ch) as usize, channels: ch as i32,
+                    src_pitch: row_bytes(ow, ch, 1), dst_pitch: row_bytes(tw, ch, 1), channels: ch as i32,
                     filter: ffi::IKC_FILTER_LANCZOS3, status: 0, device: 0,
                 });
-                slots.push(Slot { job: Some(jobs.len() - 1), ch, tw, th, out });
+                slots.push(Slot { job: Some(jobs.len() - 1), ch, tw, th, out, err: None });
             }
-            _ => slots.push(Slot { job: None, ch: 0, tw, th, out: Vec::new() }),
+            _ => slots.push(Slot { job: None, ch: 0, tw, th, out: Vec::new(), err: None }),
         }
     }
     if !jobs.is_empty() {
         unsafe { ffi::ikc_resize_batch(ctx, jobs.as_mut_ptr(), jobs.len()) };  // per-job results are in jobs[i].status
     }
     images.into_iter().zip(targets).zip(slots).map(|((img, &(w, h)), s)| match s.job {
+        None if s.err.is_some() => Err(s.err.unwrap()),
         None => resize_image(img, w, h),  // passthrough, clone, 16-bit: the single-image path
         Some(j) if jobs[j].status != ffi::IKC_OK => Err(format!("resize failed with status {}", jobs[j].status)),
         Some(_) => {

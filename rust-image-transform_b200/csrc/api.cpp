@@ -94,6 +94,15 @@ int ikc_target_dims(uint32_t ow, uint32_t oh, int has_w, uint32_t w, int has_h, 
     return target_dims(ow, oh, has_w != 0, w, has_h != 0, h, tw, th);
 }
 
+int ikc_check_dims(uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh) {
+    return guarded([&] {
+        if (sw > IKC_MAX_DIM || sh > IKC_MAX_DIM || dw > IKC_MAX_DIM || dh > IKC_MAX_DIM)
+            fail(kTooLarge, "image dimension exceeds IKC_MAX_DIM");
+        if (uint64_t(sw) * sh > IKC_MAX_PIXELS || uint64_t(dw) * dh > IKC_MAX_PIXELS)
+            fail(kTooLarge, "image area exceeds IKC_MAX_PIXELS");
+    });
+}
+
 uint32_t ikc_pass_table(int filter, uint32_t n_in, uint32_t n_out, uint32_t* left, uint32_t* count, float* weights,
                         uint32_t stride) {
     uint32_t need = 0;

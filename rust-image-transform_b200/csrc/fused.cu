@@ -48,6 +48,7 @@ constexpr int kHeaderBytes = 512;                // mbarriers, then the uniform 
 constexpr int kTapOffsetV = 128, kTapOffsetH = 320;  // byte offsets of the (duplicated) tap weights, <= 24 pairs each
 constexpr int kMaxStages = 8;
 constexpr int kMaxStripOut = 272;                // outputs of one strip (256) + ring pre-roll, in the left/right table
+constexpr size_t kFusedMaxSmem = 113 * 1024;     // the planner's budget (context.cpp): two CTAs per SM
 
 constexpr int max_src_bytes(int channels) {
     return channels == 4 ? 1024 : channels == 3 ? 864 : channels == 2 ? 512 : 256;
@@ -738,9 +739,12 @@ bool fused_has_uniform(int channels, int kv, int kh, int step_v, int step_h) {
 template <int C, int KV, int KH, int SV, int SH>
 static cudaError_t launch_one(const DevJob* jobs, const WorkItem* items, const FusedGeom& geom, cudaStream_t stream) {
     const size_t smem = fused_smem_bytes(C, KV, KH, geom);
-    // Opt in to > 48 KB dynamic shared memory (per device; cheap, so done on every launch).
+    if (smem > kFusedMaxSmem) return cudaErrorInvalidValue;
+    // Opt in to > 48 KB dynamic shared memory.  The attribute belongs to the (kernel, device) pair, which
+    // concurrent callers share: it is always set to the same planner-wide maximum, never to this launch's
+    // own size, so two threads launching different geometries cannot lower it under each other.
     cudaError_t e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH, SV, SH, kConv>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFusedMaxSmem));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(fused_ring_kernel<C, KV, KH, SV, SH, kConv>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);

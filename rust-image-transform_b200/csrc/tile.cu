@@ -205,7 +205,10 @@ cudaError_t launch_tile(int bytes_per_sample, const DevJob* jobs, const WorkItem
                         cudaStream_t stream) {
     const size_t smem = tile_smem_bytes(geom);
     const auto kernel = bytes_per_sample == 2 ? tile_kernel<uint16_t> : tile_kernel<uint8_t>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    constexpr size_t kTileMaxSmem = 110 * 1024;  // the planner's budget (context.cpp: plan_tiles)
+    if (smem > kTileMaxSmem) return cudaErrorInvalidValue;
+    // always the same value: the attribute is shared by every thread launching on this device
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileMaxSmem));
     if (e != cudaSuccess) return e;
     kernel<<<geom.n_items, kTileThreads, smem, stream>>>(jobs, items, geom);
     return cudaGetLastError();

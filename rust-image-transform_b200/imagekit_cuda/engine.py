@@ -34,6 +34,11 @@ def target_dims(ow: int, oh: int, w: int | None, h: int | None):
     return tw.value, th.value, code
 
 
+def check_dims(sw: int, sh: int, dw: int, dh: int) -> None:
+    """The library's size guard (ikc_check_dims): raises too-large before anything is allocated."""
+    _check(_lib.load().ikc_check_dims(sw, sh, dw, dh))
+
+
 def pass_table(filt: int, n_in: int, n_out: int):
     """(left, count, weights[n_out, stride]) of one pass, as the kernels consume it."""
     L = _lib.load()
@@ -135,9 +140,8 @@ class Context:
         if not (s.strides[2] == s.itemsize and s.strides[1] == s.itemsize * s.shape[2]):
             s = np.ascontiguousarray(s)
         sh, sw, ch = s.shape
-        if out is None and (dw > _lib.MAX_DIM or dh > _lib.MAX_DIM or dw * dh > _lib.MAX_PIXELS):
-            # same bound the library enforces (IKC_ERR_TOO_LARGE); checked here before allocating the result
-            raise ImageKitError(_lib.ERR_TOO_LARGE, "requested size exceeds IKC_MAX_DIM / IKC_MAX_PIXELS")
+        if out is None:
+            check_dims(min(sw, 0xFFFFFFFF), min(sh, 0xFFFFFFFF), min(dw, 0xFFFFFFFF), min(dh, 0xFFFFFFFF))  # before allocating the result
         dst = out if out is not None else np.empty((dh, dw, ch), s.dtype)
         d3 = dst[:, :, None] if dst.ndim == 2 else dst
         assert d3.shape == (dh, dw, ch) and d3.dtype == s.dtype
@@ -157,8 +161,7 @@ class Context:
         if s.ndim != 3 or s.dtype != np.uint8:
             raise ImageKitError(_lib.ERR_UNSUPPORTED, "channel conversion needs an 8-bit HxW or HxWxC array")
         sh, sw, ch = s.shape
-        if dw > _lib.MAX_DIM or dh > _lib.MAX_DIM or dw * dh > _lib.MAX_PIXELS:
-            raise ImageKitError(_lib.ERR_TOO_LARGE, "requested size exceeds IKC_MAX_DIM / IKC_MAX_PIXELS")
+        check_dims(sw, sh, min(dw, 0xFFFFFFFF), min(dh, 0xFFFFFFFF))  # before allocating the result
         dst = out if out is not None else np.empty((dh, dw, co), np.uint8)
         assert dst.shape == (dh, dw, co) and dst.dtype == np.uint8 and dst.flags.c_contiguous
         _check(_lib.load().ikc_resize_convert_u8(self._h, s.ctypes.data, sw, sh, sw * ch, ch, dst.ctypes.data, dw, dh,
