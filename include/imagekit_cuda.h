@@ -78,10 +78,14 @@ enum ikc_dims_code {
 
 /* Arithmetic mode of the resampling kernels. */
 enum ikc_mode {
-    IKC_MODE_FAST = 0,   /* fused single-launch kernels, FMA accumulation: max |delta| <= 1 LSB  */
-    IKC_MODE_EXACT = 1   /* two-launch verification path: separate mul/add in ascending tap order,
+    IKC_MODE_FAST = 0,   /* fused single-launch kernels, FMA accumulation: max |delta| <= 1 LSB; downscales run
+                            their vertical pass on the tensor cores (f16 hi + lo weights, f32 accumulation) */
+    IKC_MODE_EXACT = 1,  /* two-launch verification path: separate mul/add in ascending tap order,
                             vertical then horizontal, f32 intermediate in HBM: delta == 0 vs the
                             CPU restatement of image 0.25.8                                      */
+    IKC_MODE_FAST_FP32 = 2  /* FAST without the tensor cores: downscales take the CUDA-core ring kernel
+                            (the round-1 path; kept for A/B measurements and as the north-star's
+                            "no tensor cores" variant); same +-1 LSB bound                        */
 };
 
 #define IKC_MAX_DIM 65535u              /* per-axis bound on source and destination             */
@@ -163,6 +167,16 @@ typedef struct ikc_pass_info_t {
     int32_t up2_taps, up2_off, up2_uni_lo, up2_uni_hi;
 } ikc_pass_info_t;
 IKC_API int ikc_pass_info(int filter, uint32_t n_in, uint32_t n_out, ikc_pass_info_t* out);
+
+/* Band form of a downscale pass (n_in >= n_out), as the tensor-core vertical pass consumes it (inspection for
+ * tests; no GPU needed).  The source indices are cut into chunks of 16; chunk k only touches the *band_n
+ * (32 or 48) outputs starting at output 16 * gbase[k]; gbase[n_chunks] = number of 16-output groups.
+ * tiles: per chunk two f16 operand tiles (hi, then lo) of band_n x 16 elements each, element (output n, index k)
+ * at (k / 8) * band_n * 8 + (n / 8) * 64 + (n % 8) * 8 + (k % 8): the weight * 2^14 rounded to f16, and the f16 of the
+ * rounding error.  Returns the number of chunks (0: the pass has no band form, or a buffer is too small);
+ * with gbase == NULL and tiles == NULL only *band_n and the chunk count are returned. */
+IKC_API uint32_t ikc_pass_band(int filter, uint32_t n_in, uint32_t n_out, uint32_t* band_n, int32_t* gbase,
+                               uint16_t* tiles, size_t tiles_cap);
 
 /* ---- host-buffer entry points (the drop-in path; include H2D + D2H) -------------------------- */
 

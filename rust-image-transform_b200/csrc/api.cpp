@@ -75,7 +75,7 @@ void ikc_destroy(ikc_ctx* ctx) {
 int ikc_device_count(const ikc_ctx* ctx) { return ctx ? ctx->impl.device_count() : 0; }
 
 int ikc_set_mode(ikc_ctx* ctx, int mode) {
-    if (!ctx || (mode != IKC_MODE_FAST && mode != IKC_MODE_EXACT)) {
+    if (!ctx || (mode != IKC_MODE_FAST && mode != IKC_MODE_EXACT && mode != IKC_MODE_FAST_FP32)) {
         set_last_error("bad context or mode");
         return IKC_ERR_INVALID_ARG;
     }
@@ -124,6 +124,24 @@ uint32_t ikc_pass_table(int filter, uint32_t n_in, uint32_t n_out, uint32_t* lef
         need = stride;
     });
     return need;
+}
+
+uint32_t ikc_pass_band(int filter, uint32_t n_in, uint32_t n_out, uint32_t* band_n, int32_t* gbase, uint16_t* tiles,
+                       size_t tiles_cap) {
+    uint32_t chunks = 0;
+    guarded([&] {
+        auto p = build_pass(filter, n_in, n_out);
+        if (!p || p->band_n == 0) return;
+        const uint32_t n = uint32_t(p->band_gbase.size()) - 1;
+        if (band_n) *band_n = uint32_t(p->band_n);
+        if (gbase || tiles) {
+            if (!gbase || !tiles || tiles_cap < p->band_tiles.size()) return;
+            std::memcpy(gbase, p->band_gbase.data(), sizeof(int32_t) * p->band_gbase.size());
+            std::memcpy(tiles, p->band_tiles.data(), sizeof(uint16_t) * p->band_tiles.size());
+        }
+        chunks = n;
+    });
+    return chunks;
 }
 
 int ikc_pass_info(int filter, uint32_t n_in, uint32_t n_out, ikc_pass_info_t* out) {
@@ -350,7 +368,8 @@ int ikc_batch_describe(const ikc_batch* b, char* out, size_t cap) {
     std::string s;
     for (auto& g : b->impl.lp.groups) {
         if (!s.empty()) s += "; ";
-        if (g.up_taps) s += "up2_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.up_taps) + ">";
+        if (g.band_n) s += "banded_kernel<" + std::to_string(g.channels) + (g.convert ? ",conv" : "") + "> (band_n " + std::to_string(g.band_n) + ")";
+        else if (g.up_taps) s += "up2_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.up_taps) + ">";
         else if (g.kv == 0) s += g.bps == 2 ? "tile_kernel<u16>" : "tile_kernel";
         else s += "fused_ring_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.kv) + "," + std::to_string(g.kh) + "," + std::to_string(g.sv) + "," + std::to_string(g.sh) + ">";
         s += " x " + std::to_string(g.items.size()) + (g.up_taps ? " tiles (persistent CTAs)" : " CTAs");

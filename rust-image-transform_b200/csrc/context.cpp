@@ -144,11 +144,13 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     const size_t b_w = up(sizeof(float) * host->w.size());
     const size_t b_ring = up(sizeof(float) * host->ring_v.size());
     const size_t b_up2 = up(sizeof(float) * host->up2_pairs.size());
+    const size_t b_band = up(sizeof(uint16_t) * host->band_tiles.size());
+    const size_t b_gbase = up(sizeof(int32_t) * host->band_gbase.size());
     auto t = std::make_shared<DevTables>();
     t->device = ordinal_;
     t->host = host;
     check_cuda(cudaSetDevice(ordinal_), "cudaSetDevice");
-    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + 2 * b_ring + 2 * b_up2 + 256), "cudaMalloc(weight tables)");
+    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + 2 * b_ring + 2 * b_up2 + b_band + b_gbase + 256), "cudaMalloc(weight tables)");
     uint8_t* p = static_cast<uint8_t*>(t->base);
     auto put = [&](const void* src, size_t bytes, size_t slot) {
         uint8_t* at = p;
@@ -173,6 +175,11 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     const uint8_t* up2_h = put(scaled.data(), sizeof(float) * scaled.size(), b_up2);
     t->pass.up2_pairs_v = scaled.empty() ? nullptr : reinterpret_cast<const float2*>(up2_v);
     t->pass.up2_pairs_h = scaled.empty() ? nullptr : reinterpret_cast<const float2*>(up2_h);
+    const uint8_t* band = put(host->band_tiles.data(), sizeof(uint16_t) * host->band_tiles.size(), b_band);
+    const uint8_t* gbase = put(host->band_gbase.data(), sizeof(int32_t) * host->band_gbase.size(), b_gbase);
+    t->pass.band_tiles = host->band_n ? reinterpret_cast<const uint16_t*>(band) : nullptr;
+    t->pass.band_gbase = host->band_n ? reinterpret_cast<const int32_t*>(gbase) : nullptr;
+    t->pass.band_n = host->band_n;
     t->pass.up2_off = host->up2_off;
     t->pass.up2_taps = host->up2_taps;
     t->pass.up2_uni_lo = host->up2_uni_lo;
@@ -333,6 +340,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         int ch, kv, kh;
         int sv, sh;  // uniform steps the ring kernel has a specialised loop for, else 0
         bool convert;
+        int band_n;  // > 0: goes to the banded (tensor-core) kernel instead of the ring kernel
     };
     std::vector<Cand> cands;
     std::vector<WorkItem> tile_items[2];  // [bytes per sample - 1]: one tile-kernel launch per sample type
@@ -364,11 +372,29 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
             lp.keepalive.push_back(tv);
             lp.keepalive.push_back(th);
 
+            const bool tma_ok = (reinterpret_cast<uintptr_t>(d.src) & 15) == 0 && (d.src_pitch & 15) == 0 &&
+                                (d.oc() != 4 || ((reinterpret_cast<uintptr_t>(d.dst) | d.dst_pitch) & 3) == 0);
             bool fused = !exact && d.bps == 1 && d.sh >= d.dh && d.sw >= d.dw &&
-                         fused_supported(d.channels, tv->pass.ring_k, th->pass.ring_k) &&
-                         (reinterpret_cast<uintptr_t>(d.src) & 15) == 0 && (d.src_pitch & 15) == 0 &&
-                         (d.oc() != 4 || ((reinterpret_cast<uintptr_t>(d.dst) | d.dst_pitch) & 3) == 0);
-            Cand c{idx, {}, d.channels, tv->pass.ring_k, th->pass.ring_k, 0, 0, d.oc() != d.channels};
+                         fused_supported(d.channels, tv->pass.ring_k, th->pass.ring_k) && tma_ok;
+            Cand c{idx, {}, d.channels, tv->pass.ring_k, th->pass.ring_k, 0, 0, d.oc() != d.channels, 0};
+            // First choice for downscales: the banded kernel (vertical pass on the tensor cores).  The strip's
+            // horizontal tables must fit what its other shared-memory tenants leave.
+            bool banded = !exact && mode.load() != 2 && d.bps == 1 && d.sh >= d.dh && d.sw >= d.dw && tma_ok && tv->pass.band_tiles &&
+                          banded_supported(d.channels, tv->pass.band_n);
+            if (banded) {
+                BandGeom probe{tv->pass.band_n, 0, 0, 0};
+                const size_t fixed = banded_smem_bytes(d.channels, probe);
+                const size_t room = banded_max_smem() > fixed ? banded_max_smem() - fixed : 0;
+                const int max_out = int(std::min<size_t>(room / (8 * (size_t(th->pass.stride) + 1)), 512));
+                banded = max_out >= 1 &&
+                         cut_strips(*th->host, d.channels, int(d.sw), banded_max_src_bytes(), max_out, &c.strips);
+                if (banded) {
+                    c.band_n = tv->pass.band_n;
+                    cands.push_back(std::move(c));
+                    continue;
+                }
+                c.strips.clear();
+            }
             if (fused_has_uniform(d.channels, c.kv, c.kh, tv->pass.uni_step, th->pass.uni_step)) {
                 c.sv = tv->pass.uni_step;
                 c.sh = th->pass.uni_step;
@@ -420,14 +446,15 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
     size_t total_strips = 0;
     for (auto& c : cands) total_strips += c.strips.size();
     const size_t slots = size_t(dev.sm_count()) * 2;
-    const int group_rows = fused_group_rows();
     for (auto& c : cands) {
         const DevJob& j = lp.jobs[c.job];
+        const int group_rows = c.band_n ? banded_group_rows() : fused_group_rows();
         // Pick the chunk count that minimises (tail-wave waste) x (vertical halo recompute), assuming
         // the other jobs of the batch are cut the same way.
         const PassPlan& vp = *lp.keepalive[size_t(c.job) * 2]->host;
         const double ratio_v = double(j.sh) / double(j.dh);
-        const double halo_rows = std::max(0.0, double(vp.max_count) - ratio_v);
+        // the banded kernel reads whole 16-row chunks and pays a fixed prologue (TMEM allocation, tables) per item
+        const double halo_rows = std::max(0.0, double(vp.max_count) - ratio_v) + (c.band_n ? 16.0 + 24.0 * ratio_v : 0.0);
         const int max_chunks = std::max(1, std::min(64, int(j.dh) / (2 * group_rows)));
         int n_chunks = 1;
         double best = 1e30;
@@ -441,20 +468,33 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         }
         FusedGroup* g = nullptr;
         for (auto& gg : lp.groups)
-            if (gg.channels == c.ch && gg.kv == c.kv && gg.kh == c.kh && gg.sv == c.sv && gg.sh == c.sh &&
-                gg.convert == c.convert)
+            if (gg.channels == c.ch && gg.convert == c.convert &&
+                (c.band_n ? gg.band_n == c.band_n
+                          : (gg.band_n == 0 && gg.kv == c.kv && gg.kh == c.kh && gg.sv == c.sv && gg.sh == c.sh)))
                 g = &gg;
         if (!g) {
-            lp.groups.push_back(FusedGroup{c.ch, c.kv, c.kh, {}, {}, {}, c.sv, c.sh, c.convert});
+            lp.groups.push_back(FusedGroup{c.ch, c.band_n ? -1 : c.kv, c.band_n ? -1 : c.kh, {}, {}, {}, c.sv, c.sh, c.convert});
             g = &lp.groups.back();
+            g->band_n = c.band_n;
+            g->bgeom.band_n = c.band_n;
         }
         const PassPlan& hp = *lp.keepalive[size_t(c.job) * 2 + 1]->host;
         for (int k = 0; k < n_chunks; ++k) {
-            const int oy0 = int(int64_t(j.dh) * k / n_chunks);
-            const int oy1 = int(int64_t(j.dh) * (k + 1) / n_chunks);
+            // banded kernel: chunk boundaries on multiples of the 16-row group, so no group straddles two items
+            int oy0 = int(int64_t(j.dh) * k / n_chunks);
+            int oy1 = int(int64_t(j.dh) * (k + 1) / n_chunks);
+            if (c.band_n) {
+                oy0 = k == 0 ? 0 : (oy0 + group_rows / 2) / group_rows * group_rows;
+                oy1 = k == n_chunks - 1 ? int(j.dh) : (oy1 + group_rows / 2) / group_rows * group_rows;
+            }
             if (oy1 <= oy0) continue;
             for (auto& s : c.strips) {
                 g->items.push_back(WorkItem{c.job, s.first, s.second, oy0, oy1});
+                if (c.band_n) {
+                    g->bgeom.max_out = std::max(g->bgeom.max_out, s.second - s.first);
+                    g->bgeom.hw_pairs = std::max(g->bgeom.hw_pairs, (s.second - s.first) * int(hp.stride));
+                    continue;
+                }
                 // tmp row capacity: every staged source byte of the strip lands in some pixel slot
                 const int xl = hp.left[s.first];
                 const int b0 = (xl * c.ch) & ~15;
@@ -465,6 +505,12 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         }
     }
     for (auto& g : lp.groups) {
+        if (g.band_n) {
+            g.bgeom.n_items = int(g.items.size());
+            if (banded_smem_bytes(g.channels, g.bgeom) > banded_max_smem())
+                fail(kUnsupported, "internal: banded kernel shared-memory budget exceeded");
+            continue;
+        }
         if (g.kv == 0) continue;   // tile-kernel / 2x-upscale launch: geometry already final
         g.geom.tmp_px |= 1;        // odd pixel pitch: conflict-free float4 column walks
         g.geom.n_items = int(g.items.size());
@@ -496,7 +542,8 @@ void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, 
     size_t off = (sizeof(DevJob) * lp.jobs.size() + 15) & ~size_t(15);
     for (auto& g : lp.groups) {
         const WorkItem* d_items = reinterpret_cast<const WorkItem*>(d_desc_base + off);
-        if (g.up_taps) check_cuda(launch_up2(g.channels, g.up_taps, d_jobs, d_items, int(g.items.size()), stream), "launch up2_kernel");
+        if (g.band_n) check_cuda(launch_banded(g.channels, g.convert, d_jobs, d_items, g.bgeom, stream), "launch banded_kernel");
+        else if (g.up_taps) check_cuda(launch_up2(g.channels, g.up_taps, d_jobs, d_items, int(g.items.size()), stream), "launch up2_kernel");
         else if (g.kv == 0) check_cuda(launch_tile(g.bps, d_jobs, d_items, g.tgeom, stream), "launch tile_kernel");
         else check_cuda(launch_fused(g.channels, g.kv, g.kh, g.sv, g.sh, g.convert, d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");
         off += (sizeof(WorkItem) * g.items.size() + 15) & ~size_t(15);

@@ -62,6 +62,8 @@ struct FusedGroup {  // one kernel launch over a list of work items
     bool convert = false;  // ring kernel: the jobs store another channel count than they read
     int up_taps = 0;       // > 0 (with kv == 0): an exact-2x upscale launch (up2.cu) with this tap frame
     int bps = 1;           // tile-kernel launch: bytes per sample of its jobs (1 or 2)
+    int band_n = 0;        // > 0: a banded (tensor-core) launch whose weight tiles span band_n output rows
+    BandGeom bgeom{};
 };
 
 // Everything needed to enqueue a set of device-resident jobs.

@@ -31,6 +31,10 @@ struct DevPass {
     const float2* up2_pairs_h;  // and * kRingScaleH (up2.cu feeds bytes as denormals too); nullptr if not a 2x upscale
     int32_t up2_off, up2_taps;
     int32_t up2_uni_lo, up2_uni_hi;  // source indices with bit-identical pairs
+    // Band form (plan.hpp: PassPlan::band_*), used when the pass runs vertically on the tensor cores (banded.cu).
+    const uint16_t* band_tiles;      // [n_chunks][2][band_n * 16] f16, shared-memory operand layout; nullptr if none
+    const int32_t* band_gbase;       // [n_chunks + 1]
+    int32_t band_n;                  // output rows per operand tile (32 or 48); 0 if none
 };
 
 // One image resize, device pointers.
@@ -58,6 +62,14 @@ struct WorkItem {
 // Launch-wide shared-memory geometry of the fused kernel (max over the batch's items).
 struct FusedGeom {
     int32_t tmp_px;        // tmp row capacity in pixels (float4 each); odd
+    int32_t n_items;
+};
+
+// Launch-wide shared-memory geometry of the banded (tensor-core) kernel (max over the batch's items).
+struct BandGeom {
+    int32_t band_n;        // output rows per weight tile of the vertical pass (all jobs of a launch share it)
+    int32_t max_out;       // outputs of the widest strip (rows of the staged left/right + weight table)
+    int32_t hw_pairs;      // staged horizontal weights (one duplicated pair per output and tap) of the largest strip
     int32_t n_items;
 };
 

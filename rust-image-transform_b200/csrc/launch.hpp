@@ -23,6 +23,15 @@ bool fused_has_uniform(int channels, int ring_k_v, int ring_k_h, int step_v, int
 cudaError_t launch_fused(int channels, int ring_k_v, int ring_k_h, int step_v, int step_h, bool convert,
                          const DevJob* jobs, const WorkItem* items, const FusedGeom& geom, cudaStream_t stream);
 
+// Banded kernel (banded.cu / banded_conv.cu): downscales with the vertical pass on the tensor cores.
+bool banded_supported(int channels, int band_n);
+int banded_max_src_bytes();              // source bytes of one strip row the kernel stages
+int banded_group_rows();                 // intermediate rows per group
+size_t banded_smem_bytes(int channels, const BandGeom& geom);
+size_t banded_max_smem();                // the kernel's shared-memory budget (two CTAs per SM)
+cudaError_t launch_banded(int channels, bool convert, const DevJob* jobs, const WorkItem* items, const BandGeom& geom,
+                          cudaStream_t stream);
+
 // Tile kernel (tile.cu): output-stationary fused passes over shared-memory tiles.
 size_t tile_smem_bytes(const TileGeom& geom);
 cudaError_t launch_tile(int bytes_per_sample, const DevJob* jobs, const WorkItem* items, const TileGeom& geom,

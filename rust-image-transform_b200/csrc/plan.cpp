@@ -103,6 +103,43 @@ bool lookup_filter(int filter, FilterDef* out) {
 
 }  // namespace
 
+// IEEE binary32 -> binary16, round to nearest even, with denormals and overflow to infinity.
+uint16_t f32_to_f16_rn(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    const uint32_t a = x & 0x7fffffffu;
+    if (a >= 0x7f800000u) return uint16_t(sign | 0x7c00u | ((a > 0x7f800000u) ? 0x200u : 0u));  // inf / nan
+    if (a >= 0x477ff000u) return uint16_t(sign | 0x7c00u);                                      // rounds to inf
+    if (a < 0x33000001u) return uint16_t(sign);                                                 // below half the smallest denormal
+    const int e = int(a >> 23) - 127;
+    uint32_t mant = (a & 0x7fffffu) | 0x800000u;  // 24 bits
+    int shift;                                   // bits dropped from the 24-bit mantissa
+    uint32_t base;
+    if (e >= -14) { shift = 13; base = uint32_t(e + 15) << 10; mant &= 0x7fffffu; }
+    else { shift = 13 + (-14 - e); base = 0; }
+    const uint32_t kept = mant >> shift;
+    const uint32_t rem = mant & ((1u << shift) - 1u);
+    const uint32_t half = 1u << (shift - 1);
+    uint32_t h = base + kept;
+    if (rem > half || (rem == half && (kept & 1u))) ++h;  // carries ripple into the exponent correctly
+    return uint16_t(sign | h);
+}
+
+float f16_to_f32(uint16_t h) {
+    const uint32_t sign = uint32_t(h & 0x8000u) << 16;
+    const uint32_t e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+    float v;
+    if (e == 0) v = std::ldexp(float(m), -24);
+    else if (e == 31) v = m ? std::numeric_limits<float>::quiet_NaN() : std::numeric_limits<float>::infinity();
+    else v = std::ldexp(float(m | 0x400u), int(e) - 25);
+    uint32_t x;
+    std::memcpy(&x, &v, 4);
+    x |= sign;
+    std::memcpy(&v, &x, 4);
+    return v;
+}
+
 float filter_support(int filter) {
     FilterDef f;
     return lookup_filter(filter, &f) ? f.support : -1.0f;
@@ -242,6 +279,50 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
             }
             p.up2_uni_lo = int(best_lo);
             p.up2_uni_hi = int(best_lo + best_len);
+        }
+    }
+    // Band form for the tensor-core vertical pass (downscales and 1:1 only).
+    if (n_in >= n_out && n_in >= uint32_t(kBandChunk)) {
+        const uint32_t n_chunks = (n_in + kBandChunk - 1) / kBandChunk;
+        const uint32_t n_groups = (n_out + kBandGroup - 1) / kBandGroup;
+        std::vector<int32_t> gbase(n_chunks + 1, 0), ghi(n_chunks, 0);
+        uint32_t o_lo = 0;  // first output whose window reaches index 16k or beyond
+        int n_max = 0;
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const int32_t y0 = int32_t(c) * kBandChunk, y1 = y0 + kBandChunk;
+            while (o_lo < n_out && p.right[o_lo] <= y0) ++o_lo;
+            uint32_t o_hi = o_lo;  // one past the last output whose window starts before y1
+            while (o_hi < n_out && p.left[o_hi] < y1) ++o_hi;
+            gbase[c] = int32_t(std::min(o_lo, n_out - 1) / kBandGroup);
+            ghi[c] = o_hi > o_lo ? int32_t((o_hi - 1) / kBandGroup) : gbase[c];
+            n_max = std::max(n_max, (ghi[c] - gbase[c] + 1) * kBandGroup);
+        }
+        gbase[n_chunks] = int32_t(n_groups);
+        if (n_max <= kBandMaxN) {
+            n_max = std::max(n_max, 2 * kBandGroup);
+            p.band_n = n_max;
+            p.band_gbase = gbase;
+            const size_t tile = size_t(n_max) * kBandChunk;  // f16 elements of one operand tile
+            p.band_tiles.assign(size_t(n_chunks) * 2 * tile, 0);
+            const size_t kgroup_stride = size_t(n_max) * 8;  // elements between the two halves of the 16 indices
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+                uint16_t* hi = p.band_tiles.data() + size_t(c) * 2 * tile;
+                uint16_t* lo = hi + tile;
+                for (int n = 0; n < n_max; ++n) {
+                    const int64_t o = int64_t(gbase[c]) * kBandGroup + n;
+                    if (o >= int64_t(n_out)) break;
+                    for (int kk = 0; kk < kBandChunk; ++kk) {
+                        const int32_t y = int32_t(c) * kBandChunk + kk;
+                        if (y < p.left[o] || y >= p.right[o]) continue;
+                        const float ws = ragged[size_t(o)][size_t(y - p.left[o])] * kBandScaleW;  // exact: a power of two
+                        const uint16_t h = f32_to_f16_rn(ws);
+                        const uint16_t l = f32_to_f16_rn(ws - f16_to_f32(h));                     // the difference is exact in f32
+                        const size_t at = size_t(kk / 8) * kgroup_stride + size_t(n / 8) * 64 + size_t(n % 8) * 8 + size_t(kk % 8);
+                        hi[at] = h;
+                        lo[at] = l;
+                    }
+                }
+            }
         }
     }
     if (k >= 1 && k <= 8) {  // only the fused kernels use it; they handle ring_k <= 8

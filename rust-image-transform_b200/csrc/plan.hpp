@@ -48,7 +48,29 @@ struct PassPlan {
     int up2_off = 0, up2_taps = 0;
     std::vector<float> up2_pairs;       // [n_in * up2_taps * 2]
     int up2_uni_lo = 0, up2_uni_hi = 0; // source indices [lo, hi) whose pairs are bit-identical (the interior)
+    // Band form (downscales; csrc/banded.cu runs the vertical pass as a banded matrix product on the
+    // tensor cores).  The source indices are cut into chunks of kBandChunk (the K of one f16 MMA); chunk k
+    // only touches the outputs of band_n / 16 consecutive groups of 16, starting at group band_gbase[k]
+    // (band_gbase[n_chunks] = number of groups; groups below band_gbase[k + 1] are final after chunk k).
+    // band_tiles holds, per chunk, two K-major f16 operand tiles [band_n outputs x 16 indices] in the
+    // shared-memory layout the MMA reads (no swizzle: 8x8 core matrices, index-group stride band_n * 16 B,
+    // output-group stride 128 B): the weights * 2^14 rounded to f16 ("hi"), then the f16 of what that
+    // rounding lost ("lo"); hi + lo carries 22 bits of every weight.  band_n == 0: not applicable.
+    int band_n = 0;
+    std::vector<int32_t> band_gbase;    // [n_chunks + 1]
+    std::vector<uint16_t> band_tiles;   // [n_chunks][2][band_n * 16] f16 bit patterns
 };
+
+constexpr int kBandChunk = 16;          // source indices per chunk (K of tcgen05.mma kind::f16)
+constexpr int kBandGroup = 16;          // outputs per group
+constexpr int kBandMaxN = 48;           // widest chunk window the kernel's accumulator ring takes
+constexpr float kBandScaleW = 16384.0f; // 2^14: weights are stored as f16 of w * 2^14
+// A byte dropped into an f16 word is the denormal b * 2^-24, so the f32 intermediate of the band kernel is the
+// reference's times 2^-10; its horizontal weights carry the compensating 2^10 (exact).
+constexpr float kBandScaleH = 1024.0f;
+
+uint16_t f32_to_f16_rn(float f);        // IEEE binary16, round to nearest even (host)
+float f16_to_f32(uint16_t h);
 
 std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n_out);
 

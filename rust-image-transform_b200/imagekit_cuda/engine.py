@@ -54,6 +54,25 @@ def pass_table(filt: int, n_in: int, n_out: int):
     return left, cnt, w
 
 
+def pass_band(filt: int, n_in: int, n_out: int):
+    """(band_n, gbase[n_chunks + 1], hi[n_chunks, band_n, 16], lo[...]) of a downscale pass: the f16 weight tiles of
+    the tensor-core vertical pass, un-laid-out to [chunk][output][index]; None if the pass has no band form."""
+    L = _lib.load()
+    bn = C.c_uint32()
+    chunks = L.ikc_pass_band(filt, n_in, n_out, C.byref(bn), None, None, 0)
+    if chunks == 0:
+        return None
+    n = bn.value
+    gbase = np.zeros(chunks + 1, np.int32)
+    raw = np.zeros(chunks * 2 * n * 16, np.uint16)
+    got = L.ikc_pass_band(filt, n_in, n_out, C.byref(bn), gbase.ctypes.data_as(C.POINTER(C.c_int32)),
+                          raw.ctypes.data_as(C.POINTER(C.c_uint16)), raw.size)
+    assert got == chunks
+    t = raw.view(np.float16).reshape(chunks, 2, 2, n // 8, 8, 8)   # [chunk][hi/lo][k / 8][n / 8][n % 8][k % 8]
+    t = t.transpose(0, 1, 3, 4, 2, 5).reshape(chunks, 2, n, 16)    # [chunk][hi/lo][n][k]
+    return n, gbase, t[:, 0], t[:, 1]
+
+
 def pass_info(filt: int, n_in: int, n_out: int) -> dict:
     """What the planner derived for one pass (ring size, uniform stretch, 2x-upscale frame): ikc_pass_info."""
     info = _lib.PassInfo()

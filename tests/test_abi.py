@@ -136,3 +136,42 @@ def test_header_is_plain_c_and_links(tmp_path):
     subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
                            str(src), "-o", str(exe), "-L", lib_dir, "-limagekit_cuda", f"-Wl,-rpath,{lib_dir}"])
     assert subprocess.call([str(exe)]) == 0
+
+
+# ---- band form of a downscale pass: the weight tiles of the tensor-core vertical pass (host logic) ----
+@pytest.mark.parametrize("filt,n_in,n_out", [(4, 2160, 1080), (4, 3024, 300), (4, 1080, 225), (4, 1080, 1080), (4, 1000, 999),
+                                             (4, 777, 388), (2, 500, 250), (1, 640, 123), (3, 333, 100), (0, 100, 37),
+                                             (4, 16, 16), (4, 17, 1), (4, 4032, 400)])
+def test_band_tiles_reproduce_the_pass(ik, oracle, filt, n_in, n_out):
+    from imagekit_cuda import engine
+    band = engine.pass_band(filt, n_in, n_out)
+    assert band is not None
+    n, gbase, hi, lo = band
+    assert n in (32, 48)
+    chunks = hi.shape[0]
+    assert chunks == (n_in + 15) // 16 and gbase[-1] == (n_out + 15) // 16
+    assert np.all(np.diff(gbase[:-1]) >= 0)
+    left, count, w = oracle.pass_table(filt, n_in, n_out)
+    # dense matrix rebuilt from the tiles: (hi + lo) * 2^-14, accumulated where the tiles put it
+    dense = np.zeros((n_out + 64, chunks * 16), np.float64)
+    for c in range(chunks):
+        rows = slice(16 * gbase[c], 16 * gbase[c] + n)
+        dense[rows, 16 * c:16 * c + 16] += (hi[c].astype(np.float64) + lo[c].astype(np.float64)) / 16384.0
+    want = np.zeros_like(dense)
+    for o in range(n_out):
+        want[o, left[o]:left[o] + count[o]] = w[o, :count[o]]
+    assert np.all(dense[n_out:] == 0) and np.all(dense[:, n_in:] == 0)
+    # hi + lo carries the weight to ~2^-22 of its own size (f16 hi: 11 bits, lo: 11 more)
+    err = np.abs(dense - want)
+    assert np.all(err <= np.abs(want) * 2.0 ** -21 + 2.0 ** -38), float(err.max())
+    # a chunk's window never reaches a group that earlier chunks had already finished
+    right = left.astype(np.int64) + count
+    for c in range(chunks):
+        done_before = [g for g in range(gbase[-1]) if right[min(16 * g + 15, n_out - 1)] <= 16 * c]
+        assert all(g < gbase[c] for g in done_before)
+
+
+def test_upscale_pass_has_no_band_form(ik):
+    from imagekit_cuda import engine
+    assert engine.pass_band(4, 100, 200) is None
+    assert engine.pass_band(4, 8, 4) is None      # fewer source indices than one chunk

@@ -34,11 +34,13 @@ def test_prepared_batch_on_torch_stream(ctx, ik, oracle):
     batch.free()
 
 
-def test_prepared_batch_mixes_every_kernel(ctx, ik, oracle):
-    """One prepared batch whose jobs need the ring kernel (plain, uniform, converting), the 2x upscale kernel,
-    the tile kernel and the generic kernels: one launch per kernel variant, every job within +-1."""
+@pytest.mark.parametrize("mode", ["tc", "fp32"])
+def test_prepared_batch_mixes_every_kernel(ctx, ik, oracle, mode):
+    """One prepared batch whose jobs need the downscale kernel (banded tensor-core kernel, or the CUDA-core ring
+    kernel in FAST_FP32 mode; plain, uniform, converting), the 2x upscale kernel, the tile kernel and the generic
+    kernels: one launch per kernel variant, every job within +-1."""
     import torch
-    ctx.set_mode(ik.MODE_FAST)
+    ctx.set_mode(ik.MODE_FAST_FP32 if mode == "fp32" else ik.MODE_FAST)
     dev = torch.device("cuda:0")
     cases = [  # (h, w, c, dw, dh, filter, out_channels)
         (480, 640, 3, 200, 150, 4, 3), (600, 800, 4, 400, 300, 4, 4), (600, 800, 4, 400, 300, 4, 3),
@@ -57,8 +59,10 @@ def test_prepared_batch_mixes_every_kernel(ctx, ik, oracle):
     batch = ctx.prepare_batch(0, jobs)
     assert all(j.status == 0 for j in batch.jobs), [j.status for j in batch.jobs]
     desc = batch.describe()
-    for name in ("fused_ring_kernel", "up2_kernel", "tile_kernel"):
+    ctx.set_mode(ik.MODE_FAST)
+    for name in ("fused_ring_kernel" if mode == "fp32" else "banded_kernel", "up2_kernel", "tile_kernel"):
         assert name in desc, desc
+    assert ("banded_kernel" in desc) == (mode == "tc")
     stream = torch.cuda.Stream()
     batch.launch(stream.cuda_stream)
     stream.synchronize()

@@ -1,5 +1,6 @@
 """GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
-Bars: EXACT mode (two-launch generic kernels) is bit-equal; FAST mode (fused ring kernel, FMA) is
+Bars: EXACT mode (two-launch generic kernels) is bit-equal; FAST mode (fused kernels: banded tensor-core
+kernel for downscales, FMA) and FAST_FP32 mode (the same without tensor cores: CUDA-core ring kernel) are
 within max |delta| <= 1 per u8 sample (north-star tolerance), with the delta histogram checked."""
 import numpy as np
 import pytest
@@ -10,8 +11,11 @@ pytestmark = pytest.mark.gpu
 TOL = 1  # max |delta| per u8 channel, BASELINE.json north_star
 
 
-def _fast(ctx, ik):
-    ctx.set_mode(ik.MODE_FAST)
+def _fast(ctx, ik, fp32=False):
+    ctx.set_mode(ik.MODE_FAST_FP32 if fp32 else ik.MODE_FAST)
+
+
+FAST_MODES = ["tc", "fp32"]  # downscales: banded tensor-core kernel / CUDA-core ring kernel
 
 
 def _check_fast(got, want, label, max_off=0.002):
@@ -65,14 +69,16 @@ FUSED_SHAPES = [  # Lanczos3 downscales that take the fused ring kernel: (h, w, 
 
 @pytest.mark.parametrize("shape", FUSED_SHAPES)
 @pytest.mark.parametrize("content", ["noise", "edges", "photo"])
-def test_fused_kernel_parity(ctx, ik, oracle, shape, content):
+@pytest.mark.parametrize("mode", FAST_MODES)
+def test_fused_kernel_parity(ctx, ik, oracle, shape, content, mode):
     h, w, c, dw, dh = shape
     if content != "noise" and h * w > 2_000_000:
         pytest.skip("large shapes run on noise only")
     src = {"noise": splitmix_noise, "edges": checker, "photo": photo_like}[content]((h, w, c))
-    _fast(ctx, ik)
+    _fast(ctx, ik, mode == "fp32")
     before = ctx.kernel_launches
     got = ctx.resize(src, dw, dh, ik.FILTER_LANCZOS3)
+    _fast(ctx, ik)
     assert ctx.kernel_launches - before == 1, "expected the single-launch fused kernel"
     want = oracle.resize_exact(src, dw, dh, oracle.LANCZOS3)
     # checkerboards on integer ratios put many sums exactly on x.5, where FMA contraction decides the tie
@@ -209,13 +215,13 @@ CONVERT_CASES = [  # (h, w, c, dw, dh, filter, out_channels): ring kernel, tile 
 
 
 @pytest.mark.parametrize("case", CONVERT_CASES)
-@pytest.mark.parametrize("mode", ["fast", "exact"])
+@pytest.mark.parametrize("mode", ["fast", "fast_fp32", "exact"])
 def test_resize_with_fused_channel_conversion(ctx, ik, oracle, case, mode):
     h, w, c, dw, dh, filt, co = case
     if mode == "exact" and h * w > 2_000_000:
         pytest.skip("large shapes run in fast mode only")
     src = splitmix_noise((h, w, c), image_id=co)
-    ctx.set_mode(ik.MODE_EXACT if mode == "exact" else ik.MODE_FAST)
+    ctx.set_mode({"exact": ik.MODE_EXACT, "fast": ik.MODE_FAST, "fast_fp32": ik.MODE_FAST_FP32}[mode])
     got = ctx.resize(src, dw, dh, filt, out_channels=co)
     resized = oracle.resize_exact(src, dw, dh, filt)
     want = oracle.to_rgb8(resized) if co == 3 else oracle.to_rgba8(resized)
@@ -280,12 +286,14 @@ LUMA_RING_CASES = [  # (h, w, c, dw, dh, out_channels or None)
 
 
 @pytest.mark.parametrize("case", LUMA_RING_CASES)
-def test_luma_downscales_on_the_ring_kernel(ctx, ik, oracle, case):
+@pytest.mark.parametrize("mode", FAST_MODES)
+def test_luma_downscales_on_the_ring_kernel(ctx, ik, oracle, case, mode):
     h, w, c, dw, dh, co = case
     src = splitmix_noise((h, w, c), image_id=c)
-    _fast(ctx, ik)
+    _fast(ctx, ik, mode == "fp32")
     before = ctx.kernel_launches
     got = ctx.resize(src, dw, dh, ik.FILTER_LANCZOS3, out_channels=co)
+    _fast(ctx, ik)
     assert ctx.kernel_launches - before == 1, "expected the single-launch fused kernel"
     want = oracle.resize_exact(src, dw, dh, oracle.LANCZOS3)
     if co == 3: want = oracle.to_rgb8(want)
@@ -326,7 +334,7 @@ def test_randomised_parity_sweep(ctx, ik, oracle):
         co = int(rng.choice([3, 4])) if rng.random() < 0.25 else None
         exact = rng.random() < 0.15
         src = (checker if rng.random() < 0.2 else splitmix_noise)((h, w, c))
-        ctx.set_mode(ik.MODE_EXACT if exact else ik.MODE_FAST)
+        ctx.set_mode(ik.MODE_EXACT if exact else (ik.MODE_FAST if rng.random() < 0.7 else ik.MODE_FAST_FP32))
         got = ctx.resize(src, dw, dh, filt, out_channels=co)
         want = oracle.resize_exact(src, dw, dh, filt)
         if co == 3:

@@ -124,6 +124,56 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* a_img, con
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
 }
 
+// MMA issue rate with everything precomputed: 8 A tiles (4 KB apart), one B tile, fully unrolled.
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(uint32_t idesc, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_type, uint32_t b_lbo,
+                                                          int reps, int same_a, long long* cycles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (uint32_t i = tid; i < (40 * 1024) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        uint64_t da[8];
+        for (int i = 0; i < 8; ++i) da[i] = make_desc(smem_u32(smem) + (same_a ? (i >> 1) : i) * 4096, a_lbo, a_sbo, a_type);
+        const uint64_t db = make_desc(smem_u32(smem) + 32768, b_lbo, 128, 0);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile(
+                    "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + uint32_t((i & 3) * 64)),
+                    "l"(da[i]), "l"(db), "r"(idesc), "r"(1u));
+            }
+        }
+        const long long t1 = clock64();
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)));
+        asm volatile(
+            "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(
+                smem_u32(&bar))
+            : "memory");
+        const long long t2 = clock64();
+        cycles[0] = t2 - t0;
+        cycles[1] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+}
+
 // tcgen05.ld throughput: 4 warps x `iters` loads of 32 columns each.
 __global__ void __launch_bounds__(128, 1) ldtm_kernel(int iters, long long* cycles, uint32_t* sink) {
     __shared__ uint32_t tmem_base_s;
@@ -357,6 +407,23 @@ int main() {
         printf("timing M=128 N=%d K=16: %lld cycles for %d MMAs = %.1f cycles/MMA (A bytes/MMA 4096, B bytes %d)\n", N, R.cyc[0],
                c.n_mma * c.reps, double(R.cyc[0]) / (c.n_mma * c.reps), N * K * 2);
     }
+    CHECK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+    for (int a_sw = 0; a_sw < 2; ++a_sw)
+        for (int same_a = 0; same_a < 2; ++same_a)
+            for (int N : {16, 32, 64, 128, 256}) {
+                long long* d_cyc;
+                CHECK(cudaMalloc(&d_cyc, 16));
+                const int reps = 128;
+                mma_rate_kernel<<<1, 128, 48 * 1024>>>(make_idesc(128, N, 1, 0), a_sw ? 1024 : 2048, a_sw ? 2048 : 128, a_sw ? 2 : 0,
+                                                      uint32_t(N / 8) * 128, reps, same_a, d_cyc);
+                CHECK(cudaDeviceSynchronize());
+                long long cyc[2];
+                CHECK(cudaMemcpy(cyc, d_cyc, 16, cudaMemcpyDeviceToHost));
+                printf("mma rate (precomputed descriptors) A=%s %s M=128 N=%d K=16: %.1f cycles/MMA to completion, %.1f to issue\n",
+                       a_sw ? "MN-sw128" : "MN-none", same_a ? "pairs share A" : "distinct A", N, double(cyc[0]) / (8 * reps),
+                       double(cyc[1]) / (8 * reps));
+                CHECK(cudaFree(d_cyc));
+            }
     {
         long long* d_cyc; uint32_t* d_sink;
         CHECK(cudaMalloc(&d_cyc, 8));
