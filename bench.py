@@ -158,15 +158,116 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "images_per_step": per_step, "filter": FILTER_NAMES[filt],
-                   "note": "CPU port of image 0.25.8 imageops::resize (oracle/imageops_oracle.c); the Rust "
-                           "reference cannot be built here (no cargo/rustc, crate not vendored)"},
+        "config": {"workload": f"{args.workload}: {desc}", "filter": FILTER_NAMES[filt]},
+        "run": {"images_per_step": per_step,
+                "note": "CPU port of image 0.25.8 imageops::resize (oracle/imageops_oracle.c); the Rust "
+                        "reference cannot be built here (no cargo/rustc, crate not vendored)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{per_step} images/step x {args.steps} steps, one image per thread"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_cfg3_shard(ik, ctx, torch, dev, dist, rank, world, barrier, args):
+    """BASELINE configs[2]: a batch of 1024 synthetic 4032x3024 RGB8 rasters -> 400x300 Lanczos3 thumbnails, sharded
+    round robin over the ranks (image i -> rank i mod N, no collective): strong scaling.  Device-resident time
+    (CUDA events, max over ranks) and end to end from pinned host memory (H2D + kernel + D2H)."""
+    from imagekit_cuda.sharding import aggregate_throughput, shard_indices
+    sw, sh, ch, dw, dh, filt = 4032, 3024, 3, 400, 300, LANCZOS3
+    total = args.shard_images
+    mine = shard_indices(total, world, rank)
+    n = len(mine)
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    distinct = n if n * sw * sh * ch < 0.6 * free_b else max(8, int(0.4 * free_b) // (sw * sh * ch))
+    g = torch.Generator(device=dev)
+    g.manual_seed(0xC0FFEE + rank)
+    src = torch.empty((distinct, sh, sw, ch), dtype=torch.uint8, device=dev)
+    for a in range(0, distinct, 16):
+        b = min(distinct, a + 16)
+        src[a:b] = torch.randint(0, 256, (b - a, sh, sw, ch), dtype=torch.uint8, device=dev, generator=g)
+    dst = torch.zeros((n, dh, dw, ch), dtype=torch.uint8, device=dev)
+    jobs = [(src[i % distinct].data_ptr(), sw, sh, sw * ch, dst[i].data_ptr(), dw, dh, dw * ch, ch, filt) for i in range(n)]
+    prepared = ctx.prepare_batch(0, jobs)
+    stream = torch.cuda.Stream(device=dev)
+    for _ in range(2):
+        prepared.launch(stream.cuda_stream)
+    barrier()
+    steps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        prepared.launch(stream.cuda_stream)
+    e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1)
+    barrier()
+    _, ms_max, value = aggregate_throughput(n * steps * dw * dh / 1e6, ms, dist, dev)
+    kernel = prepared.describe()
+    per_img_us = ms / steps / max(1, n) * 1e3
+    prepared.free()
+    # end to end: the rank's share pushed through ikc_resize_batch from 8 pinned source buffers used in turn
+    h_src = [ik.PinnedArray((sh, sw, ch)) for _ in range(8)]
+    rng = np.random.default_rng(100 + rank)
+    for a in h_src:
+        a.array[...] = rng.integers(0, 256, a.shape, dtype=np.uint8)
+    h_dst = ik.PinnedArray((n, dh, dw, ch))
+    srcs = [h_src[i % 8].array for i in range(n)]
+    outs = [h_dst.array[i] for i in range(n)]
+    ctx.resize_batch(srcs[:16], [(dw, dh)] * min(n, 16), filt, outs=outs[:16])
+    barrier()
+    t0 = time.perf_counter()
+    ctx.resize_batch(srcs, [(dw, dh)] * n, filt, outs=outs)
+    dt = time.perf_counter() - t0
+    _, _, e2e = aggregate_throughput(n * dw * dh / 1e6, dt * 1e3, dist, dev)
+    algo = sw * sh * ch + dw * dh * ch
+    peak, _ = measured_peak()
+    del src, dst
+    torch.cuda.empty_cache()
+    return {"workload": f"cfg3: batch of {total} x 4032x3024 RGB8 -> 400x300 Lanczos3, sharded over {world} GPU(s)",
+            "scaling": "strong", "images_total": total, "images_this_rank": n, "distinct_sources_this_rank": distinct,
+            "value": value, "unit": UNIT, "thumbnails_per_s": value / (dw * dh / 1e6), "ms_batch": ms_max / steps,
+            "us_per_image_this_rank": per_img_us, "kernel": kernel,
+            "roofline_frac_this_rank": algo / (per_img_us * 1e-6) / 1e9 / peak,
+            "e2e": {"value": e2e, "unit": UNIT, "thumbnails_per_s": e2e / (dw * dh / 1e6), "s_batch": dt,
+                    "h2d_bytes": n * sw * sh * ch, "d2h_bytes": n * dw * dh * ch,
+                    "api": "one ikc_resize_batch call per rank over its shard, pinned host buffers"}}
+
+
+def run_inprocess(ik, n_dev, sw, sh, ch, dw, dh, filt, args):
+    """Rank 0 only, the other ranks idle at a barrier: ONE context over all the box's GPUs, one ikc_resize_batch over
+    8 images per device.  Checks the round-robin placement (job i -> device i mod N) and that every device returns
+    the oracle's pixels (+-1) for the same source."""
+    from oracle import oracle
+    ctx = ik.Context(list(range(n_dev)))
+    per_dev = 8
+    n = per_dev * n_dev
+    uniq = [ik.PinnedArray((sh, sw, ch)) for _ in range(per_dev)]   # image i uses source i // n_dev: every device sees all 8
+    rng = np.random.default_rng(7)
+    for a in uniq:
+        a.array[...] = rng.integers(0, 256, a.shape, dtype=np.uint8)
+    h_dst = [ik.PinnedArray((dh, dw, ch)) for _ in range(n)]
+    srcs = [uniq[i // n_dev].array for i in range(n)]
+    outs = [a.array for a in h_dst]
+    sizes = [(dw, dh)] * n
+    _, jobs = ctx.resize_batch(srcs, sizes, filt, outs=outs)
+    placement_ok = all(jobs[i].device == i % n_dev and jobs[i].status == 0 for i in range(n))
+    want = oracle.resize_exact(uniq[0].array, dw, dh, filt).astype(np.int32)
+    max_delta = max(int(np.abs(outs[d].astype(np.int32) - want).max()) for d in range(n_dev))   # jobs 0..N-1: source 0 on each device
+    same_across_devices = all(np.array_equal(outs[d], outs[0]) for d in range(n_dev))
+    steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ctx.resize_batch(srcs, sizes, filt, outs=outs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ctx.resize_batch(srcs, sizes, filt, outs=outs)
+    dt = time.perf_counter() - t0
+    ctx.close()
+    return {"value": n * steps * dw * dh / 1e6 / dt, "unit": UNIT, "devices": n_dev, "images_per_step": n, "steps": steps,
+            "placement_round_robin_ok": bool(placement_ok), "max_abs_delta_vs_oracle_per_device": max_delta,
+            "bit_identical_across_devices": bool(same_across_devices),
+            "api": "one process, Context() over all devices, ikc_resize_batch (job i -> device i mod N), pinned host buffers"}
 
 
 def main():
@@ -180,6 +281,8 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-shard", action="store_true", help="skip the cfg3_shard leg (1024 thumbnails, strong scaling)")
+    ap.add_argument("--shard-images", type=int, default=1024)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -276,26 +379,75 @@ def main():
     _, cnt_h, _ = ik.pass_table(filt, sw, dw)
     algo_fma = batch * ch * (sw * int(cnt_v.sum()) + dh * int(cnt_h.sum()))
 
-    # ---- end to end through the C ABI with pinned HOST buffers (H2D + kernel + D2H inside the timed region)
+    # ---- end to end through the C ABI with HOST buffers (H2D + kernel + D2H inside the timed region)
     eb = max(1, min(args.e2e_batch, batch))
     h_src = [ik.PinnedArray((sh, sw, ch)) for _ in range(eb)]
     h_dst = [ik.PinnedArray((dh, dw, ch)) for _ in range(eb)]
     rng = np.random.default_rng(rank)
     for a in h_src:
         a.array[...] = rng.integers(0, 256, a.shape, dtype=np.uint8)
-    srcs = [a.array for a in h_src]
-    outs = [a.array for a in h_dst]
     sizes = [(dw, dh)] * eb
     e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_leg(srcs, outs, steps):
+        """Wall clock around `steps` synchronous ikc_resize_batch calls, all ranks at once; whole-job MP/s."""
+        for _ in range(3):
+            ctx.resize_batch(srcs, sizes, filt, outs=outs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.resize_batch(srcs, sizes, filt, outs=outs)   # synchronous: returns with results in host memory
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        return aggregate_throughput(eb * steps * dw * dh / 1e6, dt * 1e3, dist, dev)[2]
+
+    e2e_value = e2e_leg([a.array for a in h_src], [a.array for a in h_dst], e2e_steps)
+    # The same through PAGEABLE host memory -- what the Rust wrapper's Vec<u8> is (crate/src/lib.rs): the library
+    # stages it through pinned buffers in chunks, the copy pool sharing each chunk's memcpy.
+    p_src = [np.array(a.array) for a in h_src]
+    p_dst = [np.empty((dh, dw, ch), np.uint8) for _ in range(eb)]
+    e2e_pageable = e2e_leg(p_src, p_dst, max(3, e2e_steps // 2))
+
+    # ---- what the host <-> device link allows: the step's H2D and D2H bytes as plain concurrent cudaMemcpyAsync,
+    # every rank at once (the ceiling of any host-resident drop-in on this box at this rank count)
+    t_in = torch.empty((eb, sh, sw, ch), dtype=torch.uint8).pin_memory()
+    t_out = torch.empty((eb, dh, dw, ch), dtype=torch.uint8).pin_memory()
+    d_in = torch.empty_like(t_in, device=dev)
+    d_out = torch.empty_like(t_out, device=dev)
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def dma_step():
+        with torch.cuda.stream(s_in):
+            d_in.copy_(t_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            t_out.copy_(d_out, non_blocking=True)
+
     for _ in range(3):
-        ctx.resize_batch(srcs, sizes, filt, outs=outs)
+        dma_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.resize_batch(srcs, sizes, filt, outs=outs)   # synchronous: returns with results in host memory
+        dma_step()
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    _, _, e2e_value = aggregate_throughput(eb * e2e_steps * dw * dh / 1e6, e2e_s * 1e3, dist, dev)
+    dma_s = time.perf_counter() - t0
+    dma_ceiling = aggregate_throughput(eb * e2e_steps * dw * dh / 1e6, dma_s * 1e3, dist, dev)[2]
+    dma_gbs = eb * e2e_steps * (sw * sh * ch + dw * dh * ch) / dma_s / 1e9  # this rank's H2D + D2H rate
+    del t_in, t_out, d_in, d_out
+
+    # ---- BASELINE config 3 as it is stated: ONE batch of 1024 thumbnails (4032x3024 RGB8 -> 400x300) sharded
+    # round robin over the ranks (strong scaling; shard_indices is the rule ikc_resize_batch applies in-process)
+    cfg3_shard = None
+    if not args.no_shard:
+        cfg3_shard = run_cfg3_shard(ik, ctx, torch, dev, dist, rank, world, barrier, args)
+
+    # ---- the product's own multi-GPU entry point: ONE context over all N devices in ONE process (rank 0),
+    # ikc_resize_batch shards job i -> device i mod N with one worker thread per device
+    e2e_inprocess = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            e2e_inprocess = run_inprocess(ik, world, sw, sh, ch, dw, dh, filt, args)
+        barrier()
 
     if rank != 0:
         if dist is not None:
@@ -322,10 +474,10 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "images_per_step_per_gpu": batch,
-                   "filter": FILTER_NAMES[filt], "layout": "u8 interleaved, tight pitch, device-resident",
-                   "l2": f"working set {(algo_bytes) / 1e6:.0f} MB per step per GPU >> 126 MB L2 (inputs larger than L2)",
-                   "timing": "CUDA events on the launch stream, max over ranks"},
+        "config": {"workload": f"{args.workload}: {desc}", "filter": FILTER_NAMES[filt]},
+        "run": {"images_per_step_per_gpu": batch, "layout": "u8 interleaved, tight pitch, device-resident",
+                "l2": f"working set {(algo_bytes) / 1e6:.0f} MB per step per GPU >> 126 MB L2 (inputs larger than L2)",
+                "timing": "CUDA events on the launch stream, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": recorded_traffic(args.workload, batch), "peak_source": peak_src,
                      "kernel": prepared.describe(),
@@ -341,7 +493,17 @@ def main():
         "cpu_baseline_all_cores": cpu_mt,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": eb * sw * sh * ch,
                 "d2h_bytes_per_step": eb * dw * dh * ch, "images_per_step_per_gpu": eb, "steps": e2e_steps,
-                "api": "ikc_resize_batch (C ABI), pinned host buffers, wall clock around the synchronous call"},
+                "api": "ikc_resize_batch (C ABI), pinned host buffers, wall clock around the synchronous call",
+                "dma_ceiling": {"value": dma_ceiling, "unit": UNIT, "this_rank_gbs": dma_gbs,
+                                "how": "the same H2D + D2H bytes per step as plain concurrent cudaMemcpyAsync from / to "
+                                       "pinned memory, all ranks at once, no kernel"},
+                "frac_of_dma_ceiling": e2e_value / dma_ceiling},
+        "e2e_pageable": {"value": e2e_pageable, "unit": UNIT,
+                         "api": "ikc_resize_batch with pageable numpy buffers (what the Rust wrapper's Vec<u8> is): "
+                                "chunked staging through pinned memory, copy pool",
+                         "effective_h2d_gbs_per_gpu": e2e_pageable / world * 1e6 / (dw * dh) * sw * sh * ch / 1e9},
+        "e2e_inprocess": e2e_inprocess,
+        "cfg3_shard": cfg3_shard,
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "parity": parity,

@@ -24,7 +24,7 @@
 // otherwise.  clamp + round-half-away + u8 pack at its end, as in the reference.
 //
 // Warp roles of a CTA (256 threads, 2 CTAs per SM, 256 TMEM columns each):
-//   warp 0    producer: 1-D TMA bulk copies of source rows (16 rows per stage) and of the weight tiles
+//   warp 0    producer: one 2-D TMA box (16 source rows x 512 bytes) and one bulk copy of the weight tiles per stage
 //   warp 1    MMA issuer (one elected lane), owns the TMEM allocation
 //   warps 2-3 converters: staged u8 rows -> f16 operand tiles (LDS.128, 8 PRMT, 2 STS.128 per 16 bytes)
 //   warps 4-7 epilogue + horizontal pass (TMEM lane quarter = warp % 4)
@@ -46,7 +46,7 @@ namespace {
 
 constexpr int kBlocks = 4;                         // 128-byte column blocks per strip
 constexpr int kStripBytes = kBlocks * 128;         // staged source bytes per row
-constexpr int kURowPitch = kStripBytes + 16;       // u8 staging row pitch: spreads 8 rows over all banks (LDS.128)
+constexpr int kURowPitch = kStripBytes;            // u8 staging rows are dense: one 2-D TMA box (16 rows x 512 bytes) per stage
 constexpr int kChunk = kBandChunk;                 // source rows per stage = K of one MMA
 constexpr int kUStages = 3, kFStages = 2, kBStages = 4;
 constexpr int kRing = 4;                           // accumulator groups per block held in TMEM
@@ -60,6 +60,8 @@ constexpr int kEpiThreads = 128;
 constexpr int kSegs = 8;                           // horizontal segments: one per half warp of the epilogue warps
 constexpr int kHeaderBytes = 256;
 constexpr size_t kBandedMaxSmem = 113 * 1024;
+constexpr int kRegsIo = 72, kRegsEpi = 184;        // 128 x 72 + 128 x 184 = 256 x 128
+constexpr int kTmpPad = 64;                        // floats after the intermediate tile: the look-ahead loads of the last row end here
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -90,6 +92,13 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
                  "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
+// 2-D TMA tile load (SASS: UTMALDG): box at (x word, y row) of the tensor map -> shared memory, bytes counted on an mbarrier.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tensor_map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_addr(smem_dst)),
+                 "l"(tensor_map), "r"(x), "r"(y), "r"(smem_addr(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 // ---- tcgen05 wrappers
@@ -110,6 +119,11 @@ __device__ __forceinline__ void mma_f16_acc(uint32_t d_tmem, uint64_t a_desc, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(1u)
         : "memory");
+}
+__device__ __forceinline__ uint64_t make_u64(uint32_t lo, uint32_t hi) {
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+    return v;
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
@@ -142,9 +156,9 @@ __device__ __forceinline__ uint32_t pack_pixel(float4 v_plus_half) {
 }
 constexpr float kRoundBias = 0.5f;
 
+// Store one packed pixel (bytes: its C channels, then don't-care lanes) as `co` destination channels.
 template <int C>
-__device__ __forceinline__ void store_pixel(uint8_t* dst_px, float4 v_plus_half, int co) {
-    uint32_t w = pack_pixel(v_plus_half);
+__device__ __forceinline__ void store_word(uint8_t* dst_px, uint32_t w, int co) {
     if (C <= 2 && co >= 3) {  // grey (+ alpha) -> r, g, b (, a)
         const uint32_t grey = w & 0xffu;
         const uint32_t alpha = C == 2 ? (w >> 8) & 0xffu : 0xffu;
@@ -159,6 +173,10 @@ __device__ __forceinline__ void store_pixel(uint8_t* dst_px, float4 v_plus_half,
         if (co >= 2) dst_px[1] = uint8_t(w >> 8);
         if (co >= 3) dst_px[2] = uint8_t(w >> 16);
     }
+}
+template <int C>
+__device__ __forceinline__ void store_pixel(uint8_t* dst_px, float4 v_plus_half, int co) {
+    store_word<C>(dst_px, pack_pixel(v_plus_half), co);
 }
 
 // One intermediate pixel (C floats at `p`) as a float4; missing channels read as zero.
@@ -261,20 +279,24 @@ banded_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ item
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    // Register budget by role (2 CTAs x 256 threads x 128 registers fill the SM's file): the producer / MMA /
+    // converter warpgroup gives registers up, the epilogue warpgroup -- whose horizontal pass keeps a 12-pixel
+    // window, its look-ahead and 12 weight pairs in registers -- takes them.
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIo));
     if (warp == 0) {
         // ------------------------------------------------------------------------------ producer
         if (lane == 0) {
-            const uint8_t* const gsrc = J->src + b0;
-            const size_t src_pitch = J->src_pitch;
+            const void* const src_map = J->src_map;
+            asm volatile("prefetch.tensormap [%0];" ::"l"(src_map) : "memory");
             const uint8_t* const tiles = reinterpret_cast<const uint8_t*>(J->v.band_tiles);
             for (int i = 0; i < nchunks; ++i) {
                 const int k = k0 + i;
                 const int su = i % kUStages, sb = i % kBStages;
                 mbar_wait_parked(u_empty + su, ((i / kUStages) & 1) ^ 1);
-                const int r0 = max(k * kChunk, y_first), r1 = min((k + 1) * kChunk, y_last);  // rows outside carry zero weight for every live output
-                mbar_expect_tx(u_full + su, uint32_t(r1 - r0) * uint32_t(nb));
-                for (int r = r0; r < r1; ++r)
-                    bulk_load(ustage + (su * kChunk + (r - k * kChunk)) * kURowPitch, gsrc + size_t(r) * src_pitch, uint32_t(nb), u_full + su);
+                // one box = the chunk's 16 rows x 512 bytes of the strip; words past the raster's pitch or rows read as zero
+                mbar_expect_tx(u_full + su, uint32_t(kChunk * kStripBytes));
+                tma_load_2d(ustage + su * kChunk * kURowPitch, src_map, b0 >> 2, k * kChunk, u_full + su);
                 mbar_wait_parked(b_empty + sb, ((i / kBStages) & 1) ^ 1);
                 mbar_expect_tx(b_full + sb, btile);
                 bulk_load(bstage + sb * btile, tiles + size_t(k) * btile, btile, b_full + sb);
@@ -283,37 +305,50 @@ banded_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ item
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------------------------ MMA issuer
-        int acquired = g0;   // groups [g0, acquired) belong to the MMAs (zeroed by the epilogue warps)
-        int completed = g0;  // groups [g0, completed) have been committed to the epilogue
-        const uint32_t f_addr = smem_addr(fstage), b_addr = smem_addr(bstage);
-        int gb_next = g0;
-        for (int i = 0; i < nchunks; ++i) {
-            const int k = k0 + i;
-            const int gb = gb_next;
-            gb_next = (i + 1 < nchunks) ? __ldg(gbase + k + 1) : 0;
-            while (acquired < gb + NG) {
-                const int rel = acquired - g0;
-                mbar_wait(t_empty + (rel & (kRing - 1)), (rel / kRing) & 1);
-                ++acquired;
-            }
-            const int sf = i % kFStages, sb = i % kBStages;
-            mbar_wait(f_full + sf, (i / kFStages) & 1);
-            mbar_wait(b_full + sb, (i / kBStages) & 1);
-            tc_fence_after();
-            if (lane == 0) {
+        // One lane runs the whole role (waits included): tcgen05.mma / commit are single-thread instructions, and a
+        // converged 32-lane loop around them costs an election per instruction.  Everything an MMA needs is a 32-bit
+        // add away from values computed once: the descriptors' high words are constant (stride offset 128, version 1)
+        // and only the 14-bit address field of the low words moves.
+        if (lane == 0) {
+            int acquired = g0;   // groups [g0, acquired) belong to the MMAs (zeroed by the epilogue warps)
+            int completed = g0;  // groups [g0, completed) have been committed to the epilogue
+            constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+            const uint32_t a_lo0 = ((smem_addr(fstage) >> 4) & 0x3fffu) | ((2048u >> 4) << 16);
+            const uint32_t b_lo0 = ((smem_addr(bstage) >> 4) & 0x3fffu) | (((uint32_t(geom.band_n) * 16u) >> 4) << 16);
+            const uint32_t band_n = uint32_t(geom.band_n);
+            int gb_next = g0;
+            for (int i = 0; i < nchunks; ++i) {
+                const int k = k0 + i;
+                const int gb = gb_next;
+                gb_next = (i + 1 < nchunks) ? __ldg(gbase + k + 1) : 0;
+                while (acquired < gb + NG) {
+                    const int rel = acquired - g0;
+                    mbar_wait(t_empty + (rel & (kRing - 1)), (rel / kRing) & 1);
+                    ++acquired;
+                }
+                const int sf = i % kFStages, sb = i % kBStages;
+                mbar_wait(f_full + sf, (i / kFStages) & 1);
+                mbar_wait(b_full + sb, (i / kBStages) & 1);
+                tc_fence_after();
                 const int s0 = (gb - g0) & (kRing - 1);
-                const uint32_t n1 = uint32_t(min(NG, kRing - s0) * kGroup), n2 = uint32_t(geom.band_n) - n1;
+                const uint32_t n1 = uint32_t(min(NG, kRing - s0) * kGroup), n2 = band_n - n1;  // n2 > 0: the window wraps around the ring
                 const uint32_t id1 = instr_desc(n1), id2 = instr_desc(n2);
-                const uint32_t b_lbo = uint32_t(geom.band_n) * 16u;  // between the two halves of the 16 source rows
-#pragma unroll 1
-                for (int b = 0; b < nblk; ++b) {
-                    const uint64_t a_desc = smem_desc(f_addr + uint32_t(sf * kFStageBytes + b * kFBlockBytes), 2048u, 128u);
-                    const uint32_t d_col = tmem + uint32_t(b * kRing * kGroup);
+                const uint32_t a_lo = a_lo0 + uint32_t(sf) * (kFStageBytes >> 4);
+                const uint32_t bh_lo = b_lo0 + uint32_t(sb) * (btile >> 4);   // hi weights
+                const uint32_t bl_lo = bh_lo + (btile >> 5);                  // what f16 rounding lost of them
+                const uint32_t wrap = (n1 >> 3) * (128u >> 4);               // the wrapped part's first output row in the tile
+                const uint32_t d1 = tmem + uint32_t(s0 * kGroup);
 #pragma unroll
-                    for (int part = 0; part < 2; ++part) {  // hi weights, then what f16 rounding lost of them
-                        const uint32_t bt = b_addr + uint32_t(sb) * btile + uint32_t(part) * (btile >> 1);
-                        mma_f16_acc(d_col + uint32_t(s0 * kGroup), a_desc, smem_desc(bt, b_lbo, 128u), id1);
-                        if (n2) mma_f16_acc(d_col, a_desc, smem_desc(bt + (n1 >> 3) * 128u, b_lbo, 128u), id2);  // the window wraps around the ring
+                for (int b = 0; b < kBlocks; ++b) {
+                    if (b < nblk) {
+                        const uint64_t a_desc = make_u64(a_lo + uint32_t(b) * (kFBlockBytes >> 4), kDescHi);
+                        const uint32_t dc = uint32_t(b * kRing * kGroup);
+                        mma_f16_acc(d1 + dc, a_desc, make_u64(bh_lo, kDescHi), id1);
+                        mma_f16_acc(d1 + dc, a_desc, make_u64(bl_lo, kDescHi), id1);
+                        if (n2) {
+                            mma_f16_acc(tmem + dc, a_desc, make_u64(bh_lo + wrap, kDescHi), id2);
+                            mma_f16_acc(tmem + dc, a_desc, make_u64(bl_lo + wrap, kDescHi), id2);
+                        }
                     }
                 }
                 tc_commit(f_empty + sf);
@@ -321,31 +356,36 @@ banded_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ item
                 const int final_below = (i + 1 < nchunks) ? gb_next : acquired;  // groups below it get no more contributions
                 for (; completed < final_below; ++completed) tc_commit(t_full + ((completed - g0) & (kRing - 1)));
             }
-            __syncwarp();
         }
-    } else if (warp < 4) {
+        __syncwarp();
+    } else {
         // ------------------------------------------------------------------------------ converters
+        // Thread task t (0..7) of a stage: row (t / 4) * 8 + r8 of block t % 4, 16-byte piece (pc + r8) % 8 of the block's
+        // 128 bytes.  The skew makes both sides conflict-free: the 8 lanes of a quarter warp read 8 rows (dense 512-byte
+        // pitch) at 8 different 16-byte offsets, and write row r8 (16 bytes) of 8 different core matrices.
         const int ct = tid - 64;
-        const int npieces = nb >> 4;
+        const int r8 = ct & 7, pc = ((ct >> 3) + r8) & 7;
+        const int u_off = r8 * kURowPitch + pc * 16;
+        const int f_off = pc * 256 + r8 * 16;  // element (m, k) of a block: (k / 8) * 2048 + (m / 8) * 128 + (k % 8) * 16 + (m % 8) * 2
         for (int i = 0; i < nchunks; ++i) {
             const int su = i % kUStages, sf = i % kFStages;
             mbar_wait(u_full + su, (i / kUStages) & 1);
-            mbar_wait(f_empty + sf, ((i / kFStages) & 1) ^ 1);
-            const uint8_t* const ubase = ustage + su * kChunk * kURowPitch;
-            uint8_t* const fbase = fstage + sf * kFStageBytes;
+            const uint8_t* const ubase = ustage + su * kChunk * kURowPitch + u_off;
+            uint4 v[8];
 #pragma unroll
-            for (int t = 0; t < (kChunk * (kStripBytes / 16)) / kConvThreads; ++t) {
-                const int task = t * kConvThreads + ct;
-                const int r8 = task & 7, piece = (task >> 3) & 31, rg = task >> 8;  // 8 lanes: 8 rows of one 16-byte piece
-                if (piece < npieces) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(ubase + (rg * 8 + r8) * kURowPitch + piece * 16);
+            for (int t = 0; t < 8; ++t)
+                if ((t & 3) < nblk) v[t] = *reinterpret_cast<const uint4*>(ubase + (t >> 2) * 8 * kURowPitch + (t & 3) * 128);
+            mbar_wait(f_empty + sf, ((i / kFStages) & 1) ^ 1);
+            uint8_t* const fbase = fstage + sf * kFStageBytes + f_off;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if ((t & 3) < nblk) {
                     uint4 lo, hi;  // 16 bytes -> 16 f16 denormals: bytes 0-7, bytes 8-15
-                    lo.x = __byte_perm(v.x, 0u, 0x4140); lo.y = __byte_perm(v.x, 0u, 0x4342);
-                    lo.z = __byte_perm(v.y, 0u, 0x4140); lo.w = __byte_perm(v.y, 0u, 0x4342);
-                    hi.x = __byte_perm(v.z, 0u, 0x4140); hi.y = __byte_perm(v.z, 0u, 0x4342);
-                    hi.z = __byte_perm(v.w, 0u, 0x4140); hi.w = __byte_perm(v.w, 0u, 0x4342);
-                    // element (m, k) of a block lives at (k / 8) * 2048 + (m / 8) * 128 + (k % 8) * 16 + (m % 8) * 2
-                    uint8_t* const d = fbase + (piece >> 3) * kFBlockBytes + rg * 2048 + (piece & 7) * 256 + r8 * 16;
+                    lo.x = __byte_perm(v[t].x, 0u, 0x4140); lo.y = __byte_perm(v[t].x, 0u, 0x4342);
+                    lo.z = __byte_perm(v[t].y, 0u, 0x4140); lo.w = __byte_perm(v[t].y, 0u, 0x4342);
+                    hi.x = __byte_perm(v[t].z, 0u, 0x4140); hi.y = __byte_perm(v[t].z, 0u, 0x4342);
+                    hi.z = __byte_perm(v[t].w, 0u, 0x4140); hi.w = __byte_perm(v[t].w, 0u, 0x4342);
+                    uint8_t* const d = fbase + (t & 3) * kFBlockBytes + (t >> 2) * 2048;
                     *reinterpret_cast<uint4*>(d) = lo;
                     *reinterpret_cast<uint4*>(d + 128) = hi;
                 }
@@ -354,7 +394,9 @@ banded_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ item
             mbar_arrive(f_full + sf);
             mbar_arrive(u_empty + su);
         }
+    }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
         // ------------------------------------------------------------------------------ epilogue + horizontal pass
         const int q = warp & 3;                                  // TMEM lane quarter this warp may touch
         const uint32_t tlane = tmem + (uint32_t(q * 32) << 16);
@@ -378,6 +420,9 @@ banded_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ item
         // uniform interior of a 2:1 pass: every output of the segment has the same 12 weights and starts 2 pixels
         // after its predecessor
         const bool uni2 = os < oe && J->h.uni_step == 2 && hstride == 12 && os >= J->h.uni_lo && oe <= J->h.uni_hi;
+        float2 uw[12];  // the stretch's 12 tap weights (duplicated pairs)
+#pragma unroll
+        for (int t = 0; t < 12; ++t) uw[t] = uni2 ? hw[(os - ox0) * 12 + t] : make_float2(0.0f, 0.0f);
 
         for (int g = g0; g < g_end; ++g) {
             const int rel = g - g0;
@@ -388,13 +433,17 @@ banded_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ item
             const bool live = row0 < oy1 && row0 + kGroup > oy0;
             if (live) {  // TMEM -> registers -> intermediate tile (lane = byte column, so consecutive floats)
                 float* const tcol = tmp + q * 32 + lane;
-#pragma unroll 1
-                for (int b = 0; b < nblk; ++b) {
-                    float v[16];
-                    tmem_ld16(tlane + uint32_t(b * kRing * kGroup + slot * kGroup), v);
-                    tmem_ld_wait();
+                float v[kBlocks][16];
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) tcol[r * kTmpPitch + b * 128] = v[r];
+                for (int b = 0; b < kBlocks; ++b)
+                    if (b < nblk) tmem_ld16(tlane + uint32_t(b * kRing * kGroup + slot * kGroup), v[b]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int b = 0; b < kBlocks; ++b) {
+                    if (b < nblk) {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) tcol[r * kTmpPitch + b * 128] = v[b][r];
+                    }
                 }
             }
             for (int b = 0; b < nblk; ++b) tmem_zero16(tlane + uint32_t(b * kRing * kGroup + slot * kGroup));
@@ -410,32 +459,45 @@ banded_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ item
             uint8_t* const my_dst = dst_base + size_t(orow) * dst_pitch;
             if (os < oe) {
                 if (uni2) {
-                    float2 w[12];
+                    // Blocks of 8 outputs as straight-line code: the 26 pixels their windows span are loaded at once
+                    // (output j of the block reads pixels 2j .. 2j + 11), then 8 x 24 independent-enough FFMA2 chains.
+                    // Reads past the segment's last window stay inside the tile's padding and are never stored.
+                    for (int o = os; o < oe; o += 8) {
+                        const float* px = my_row + hlr[o - ox0].x * C;
+                        float4 p[26];
 #pragma unroll
-                    for (int t = 0; t < 12; ++t) w[t] = hw[(os - ox0) * 12 + t];
-                    const float* px = my_row + hlr[os - ox0].x * C;  // first pixel of the first window
-                    float4 p[12];
+                        for (int t = 0; t < 26; ++t) p[t] = load_px<C>(px + t * C);
+                        uint32_t word[8];
 #pragma unroll
-                    for (int t = 0; t < 10; ++t) p[t] = load_px<C>(px + t * C);
-                    px += 10 * C;
-                    for (int o = os; o < oe; o += 6) {
+                        for (int j = 0; j < 8; j += 2) {  // two outputs at a time: eight accumulation chains in flight
+                            float2 a01 = make_float2(kRoundBias, kRoundBias), a23 = a01, c01 = make_float2(0.0f, 0.0f), c23 = c01;
+                            float2 d01 = a01, d23 = a01, e01 = c01, e23 = c01;
 #pragma unroll
-                        for (int u = 0; u < 6; ++u) {
-                            if (o + u < oe) {
-                                p[(2 * u + 10) % 12] = load_px<C>(px);
-                                p[(2 * u + 11) % 12] = load_px<C>(px + C);
-                                px += 2 * C;
-                                float2 a01 = make_float2(kRoundBias, kRoundBias), a23 = a01;
-                                float2 c01 = make_float2(0.0f, 0.0f), c23 = c01;
+                            for (int t = 0; t < 12; t += 2) {
+                                const float4 x0 = p[2 * j + t], x1 = p[2 * j + t + 1], y0 = p[2 * j + 2 + t], y1 = p[2 * j + 3 + t];
+                                a01 = __ffma2_rn(uw[t], make_float2(x0.x, x0.y), a01);
+                                a23 = __ffma2_rn(uw[t], make_float2(x0.z, x0.w), a23);
+                                d01 = __ffma2_rn(uw[t], make_float2(y0.x, y0.y), d01);
+                                d23 = __ffma2_rn(uw[t], make_float2(y0.z, y0.w), d23);
+                                c01 = __ffma2_rn(uw[t + 1], make_float2(x1.x, x1.y), c01);
+                                c23 = __ffma2_rn(uw[t + 1], make_float2(x1.z, x1.w), c23);
+                                e01 = __ffma2_rn(uw[t + 1], make_float2(y1.x, y1.y), e01);
+                                e23 = __ffma2_rn(uw[t + 1], make_float2(y1.z, y1.w), e23);
+                            }
+                            a01 = __fadd2_rn(a01, c01); a23 = __fadd2_rn(a23, c23);
+                            d01 = __fadd2_rn(d01, e01); d23 = __fadd2_rn(d23, e23);
+                            word[j] = pack_pixel(make_float4(a01.x, a01.y, a23.x, a23.y));
+                            word[j + 1] = pack_pixel(make_float4(d01.x, d01.y, d23.x, d23.y));
+                        }
+                        if (row_live) {
+                            uint8_t* const d = my_dst + size_t(o) * CO;
+                            if (C == 4 && !CONV && o + 8 <= oe && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+                                *reinterpret_cast<uint4*>(d) = make_uint4(word[0], word[1], word[2], word[3]);
+                                *reinterpret_cast<uint4*>(d + 16) = make_uint4(word[4], word[5], word[6], word[7]);
+                            } else {
 #pragma unroll
-                                for (int t = 0; t < 12; t += 2) {
-                                    const float4 e = p[(2 * u + t) % 12], f = p[(2 * u + t + 1) % 12];
-                                    a01 = __ffma2_rn(w[t], make_float2(e.x, e.y), a01);
-                                    a23 = __ffma2_rn(w[t], make_float2(e.z, e.w), a23);
-                                    c01 = __ffma2_rn(w[t + 1], make_float2(f.x, f.y), c01);
-                                    c23 = __ffma2_rn(w[t + 1], make_float2(f.z, f.w), c23);
-                                }
-                                if (row_live) store_pixel<C>(my_dst + size_t(o + u) * CO, make_float4(a01.x + c01.x, a01.y + c01.y, a23.x + c23.x, a23.y + c23.y), CO);
+                                for (int j = 0; j < 8; ++j)
+                                    if (o + j < oe) store_word<C>(d + j * CO, word[j], CO);
                             }
                         }
                     }
@@ -487,7 +549,7 @@ size_t banded_smem_bytes(int channels, const BandGeom& g) {
     const size_t tmp_pitch = size_t(tmp_pitch_floats(channels));
     return size_t(kHeaderBytes) + size_t(kUStages) * kChunk * kURowPitch + size_t(kFStages) * kFStageBytes +
            size_t(kBStages) * size_t(g.band_n) * 64 + size_t((g.hw_pairs + 1) & ~1) * sizeof(float2) +
-           size_t((g.max_out + 1) & ~1) * sizeof(int2) + size_t(kGroup) * tmp_pitch * sizeof(float);
+           size_t((g.max_out + 1) & ~1) * sizeof(int2) + (size_t(kGroup) * tmp_pitch + kTmpPad) * sizeof(float);
 }
 size_t banded_max_smem() { return kBandedMaxSmem; }
 int banded_max_src_bytes() { return kStripBytes; }

@@ -7,7 +7,46 @@
 
 #include "launch.hpp"
 
+#include <cuda.h>  // CUtensorMap + cuTensorMapEncodeTiled's signature; the entry point is fetched at run time (no libcuda link)
+
 namespace ikc {
+
+// ---- TMA tensor maps ------------------------------------------------------------------------------
+
+namespace {
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q{};
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+}  // namespace
+
+// Source raster as [rows][pitch / 4] 32-bit words; box = box_rows x box_bytes.  False if the driver refuses.
+bool encode_src_map(uint8_t (&out)[128], const void* base, uint32_t rows, size_t pitch, uint32_t box_bytes, uint32_t box_rows) {
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    alignas(64) CUtensorMap map;
+    const cuuint64_t gdim[2] = {cuuint64_t(pitch / 4), cuuint64_t(rows)};
+    const cuuint64_t gstride[1] = {cuuint64_t(pitch)};
+    const cuuint32_t box[2] = {box_bytes / 4, box_rows};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    std::memcpy(out, &map, 128);
+    return true;
+}
 
 // ---- errors ---------------------------------------------------------------------------------------
 
@@ -49,6 +88,60 @@ DevTables::~DevTables() {
         cudaFree(base);
         cudaSetDevice(cur);
     }
+}
+
+// ---- copy pool ------------------------------------------------------------------------------------
+
+CopyPool::CopyPool(int helpers) {
+    for (int i = 0; i < helpers; ++i) threads_.emplace_back([this] { worker(); });
+}
+CopyPool::~CopyPool() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+}
+void CopyPool::worker() {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+        cv_.wait(lk, [&] { return stop_ || (epoch_ != seen && next_ < n_); });
+        if (stop_) return;
+        seen = epoch_;
+        ++running_;
+        while (next_ < n_) {
+            const size_t i = next_++;
+            const auto* fn = fn_;
+            lk.unlock();
+            try { (*fn)(i); } catch (...) {}
+            lk.lock();
+        }
+        if (--running_ == 0) done_cv_.notify_all();
+    }
+}
+void CopyPool::parallel_for(size_t n, const std::function<void(size_t)>& fn) {
+    if (n <= 1 || threads_.empty() || !run_mu_.try_lock()) {  // helpers busy with another caller: do it here
+        for (size_t i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::lock_guard<std::mutex> run_lock(run_mu_, std::adopt_lock);
+    std::unique_lock<std::mutex> lk(mu_);
+    fn_ = &fn;
+    n_ = n;
+    next_ = 0;
+    ++epoch_;
+    cv_.notify_all();
+    while (next_ < n_) {  // the caller works too
+        const size_t i = next_++;
+        lk.unlock();
+        fn(i);
+        lk.lock();
+    }
+    done_cv_.wait(lk, [&] { return running_ == 0; });
+    fn_ = nullptr;
+    n_ = next_ = 0;
 }
 
 // ---- validation -----------------------------------------------------------------------------------
@@ -109,6 +202,7 @@ Device::~Device() {
             cudaStreamSynchronize(l->stream);
             cudaStreamDestroy(l->stream);
         }
+        for (cudaEvent_t e : l->out_events) cudaEventDestroy(e);
         l->h_in.release(); l->h_out.release(); l->h_desc.release();
         l->d_in.release(); l->d_out.release(); l->d_scratch.release(); l->d_desc.release();
     }
@@ -208,7 +302,12 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
 
 // ---- context --------------------------------------------------------------------------------------
 
-Context::Context(const int* ids, int n) {
+static int copy_helpers() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    return int(std::min(4u, hw > 4 ? hw / 4 : 0u));
+}
+
+Context::Context(const int* ids, int n) : copy_pool(copy_helpers()) {
     int visible = 0;
     cudaError_t e = cudaGetDeviceCount(&visible);
     if (e != cudaSuccess || visible <= 0)
@@ -257,7 +356,10 @@ int strip_bytes(const PassPlan& h, int a, int b, int ch, int sw) {
 }
 
 // Cut [0, dw) into column strips whose source footprint fits the kernel's staging row.
-bool cut_strips(const PassPlan& h, int ch, int sw, int max_src, int max_out, std::vector<std::pair<int, int>>* out) {
+// `align` > 1: interior strip boundaries fall on multiples of it where a strip is wide enough (the banded kernel
+// then stores whole 16-byte groups of pixels).
+bool cut_strips(const PassPlan& h, int ch, int sw, int max_src, int max_out, std::vector<std::pair<int, int>>* out,
+                int align = 1) {
     const int dw = int(h.n_out);
     auto greedy = [&](int cap, std::vector<std::pair<int, int>>* res) {
         res->clear();
@@ -266,6 +368,7 @@ bool cut_strips(const PassPlan& h, int ch, int sw, int max_src, int max_out, std
             if (strip_bytes(h, a, a + 1, ch, sw) > max_src) return false;
             int b = a + 1;
             while (b < dw && b - a < cap && strip_bytes(h, a, b + 1, ch, sw) <= max_src) ++b;
+            if (align > 1 && b < dw && b / align * align > a) b = b / align * align;
             res->emplace_back(a, b);
             a = b;
         }
@@ -382,12 +485,15 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
             bool banded = !exact && mode.load() != 2 && d.bps == 1 && d.sh >= d.dh && d.sw >= d.dw && tma_ok && tv->pass.band_tiles &&
                           banded_supported(d.channels, tv->pass.band_n);
             if (banded) {
-                BandGeom probe{tv->pass.band_n, 0, 0, 0};
-                const size_t fixed = banded_smem_bytes(d.channels, probe);
+                BandGeom probe{tv->pass.band_n, 2, 2, 0};
+                const size_t fixed = banded_smem_bytes(d.channels, probe);  // (with the rounding slack of both tables)
                 const size_t room = banded_max_smem() > fixed ? banded_max_smem() - fixed : 0;
+                // per output: its weights (8 bytes per tap) and its (left, right)
                 const int max_out = int(std::min<size_t>(room / (8 * (size_t(th->pass.stride) + 1)), 512));
                 banded = max_out >= 1 &&
                          cut_strips(*th->host, d.channels, int(d.sw), banded_max_src_bytes(), max_out, &c.strips);
+                if (banded) banded = encode_src_map(lp.jobs[size_t(idx)].src_map, d.src, d.sh, d.src_pitch,
+                                                    uint32_t(banded_max_src_bytes()), uint32_t(kBandChunk));
                 if (banded) {
                     c.band_n = tv->pass.band_n;
                     cands.push_back(std::move(c));
@@ -454,7 +560,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         const PassPlan& vp = *lp.keepalive[size_t(c.job) * 2]->host;
         const double ratio_v = double(j.sh) / double(j.dh);
         // the banded kernel reads whole 16-row chunks and pays a fixed prologue (TMEM allocation, tables) per item
-        const double halo_rows = std::max(0.0, double(vp.max_count) - ratio_v) + (c.band_n ? 16.0 + 24.0 * ratio_v : 0.0);
+        const double halo_rows = std::max(0.0, double(vp.max_count) - ratio_v) + (c.band_n ? 36.0 : 0.0);
         const int max_chunks = std::max(1, std::min(64, int(j.dh) / (2 * group_rows)));
         int n_chunks = 1;
         double best = 1e30;
@@ -527,9 +633,12 @@ size_t Context::desc_bytes(const LaunchPlan& lp) const {
 }
 
 void Context::fill_desc(const LaunchPlan& lp, uint8_t* host, float* scratch) const {
-    DevJob* jobs = reinterpret_cast<DevJob*>(host);
-    for (size_t i = 0; i < lp.jobs.size(); ++i) jobs[i] = lp.jobs[i];
-    for (int idx : lp.generic_jobs) jobs[idx].tmp = scratch;
+    // (byte copies: DevJob is 64-byte aligned for its tensor map, `host` need not be)
+    for (size_t i = 0; i < lp.jobs.size(); ++i) {
+        DevJob j = lp.jobs[i];
+        if (std::find(lp.generic_jobs.begin(), lp.generic_jobs.end(), int(i)) != lp.generic_jobs.end()) j.tmp = scratch;
+        std::memcpy(host + i * sizeof(DevJob), &j, sizeof(DevJob));
+    }
     size_t off = (sizeof(DevJob) * lp.jobs.size() + 15) & ~size_t(15);
     for (auto& g : lp.groups) {
         std::memcpy(host + off, g.items.data(), sizeof(WorkItem) * g.items.size());
@@ -588,7 +697,24 @@ struct HostJobState {  // one in-flight host job on a lane
     JobDesc d;
     size_t in_pitch = 0, out_pitch = 0;
     bool out_staged = false;
+    uint32_t out_chunk_rows = 0;  // staged output: rows per D2H chunk (one event each)
 };
+
+constexpr size_t kStageChunkBytes = size_t(4) << 20;   // DMA granule of the pageable staging pipeline
+constexpr size_t kCopyPieceBytes = size_t(512) << 10;  // memcpy granule handed to one copy-pool thread
+
+// rows [y0, y0 + rows) of a pitched raster <-> tight rows, split over the copy pool
+void pooled_copy_rows(CopyPool& pool, uint8_t* dst, size_t dst_pitch, const uint8_t* src, size_t src_pitch, size_t row_bytes,
+                      uint32_t rows) {
+    if (rows == 0 || row_bytes == 0) return;
+    const uint32_t piece_rows = uint32_t(std::max<size_t>(1, kCopyPieceBytes / row_bytes));
+    const size_t pieces = (rows + piece_rows - 1) / piece_rows;
+    pool.parallel_for(pieces, [&](size_t i) {
+        const uint32_t a = uint32_t(i) * piece_rows, b = std::min(rows, a + piece_rows);
+        if (dst_pitch == row_bytes && src_pitch == row_bytes) std::memcpy(dst + size_t(a) * row_bytes, src + size_t(a) * row_bytes, size_t(b - a) * row_bytes);
+        else for (uint32_t y = a; y < b; ++y) std::memcpy(dst + size_t(y) * dst_pitch, src + size_t(y) * src_pitch, row_bytes);
+    });
+}
 
 // Stage + H2D + kernels + D2H for one job on one lane; everything asynchronous on the lane stream
 // except the pageable staging memcpy.  finish_host_job() completes it.
@@ -600,19 +726,25 @@ void start_host_job(Context& ctx, Device& dev, Lane& l, const JobDesc& d, HostJo
     st->out_pitch = device_pitch(out_row);
     l.d_in.reserve(st->in_pitch * d.sh);
     l.d_out.reserve(st->out_pitch * d.dh);
-    const void* src = d.src;
-    size_t src_pitch = d.src_pitch;
-    if (!is_pinned(d.src)) {  // pageable: pack rows tightly into the lane's pinned staging
+    if (!is_pinned(d.src)) {
+        // Pageable source: rows are packed into the lane's pinned staging a few MB at a time (the copy pool shares
+        // each chunk's memcpy) and every chunk's DMA is queued as soon as it is staged, so the copy of chunk
+        // k + 1 overlaps the DMA of chunk k.
         l.h_in.reserve(in_row * d.sh);
         uint8_t* hp = static_cast<uint8_t*>(l.h_in.p);
-        if (d.src_pitch == in_row) std::memcpy(hp, d.src, in_row * d.sh);
-        else for (uint32_t y = 0; y < d.sh; ++y)
-            std::memcpy(hp + size_t(y) * in_row, static_cast<const uint8_t*>(d.src) + size_t(y) * d.src_pitch, in_row);
-        src = hp;
-        src_pitch = in_row;
+        const uint32_t chunk_rows = uint32_t(std::max<size_t>(1, kStageChunkBytes / std::max<size_t>(in_row, 1)));
+        for (uint32_t y0 = 0; y0 < d.sh; y0 += chunk_rows) {
+            const uint32_t rows = std::min(chunk_rows, d.sh - y0);
+            pooled_copy_rows(ctx.copy_pool, hp + size_t(y0) * in_row, in_row,
+                             static_cast<const uint8_t*>(d.src) + size_t(y0) * d.src_pitch, d.src_pitch, in_row, rows);
+            check_cuda(cudaMemcpy2DAsync(static_cast<uint8_t*>(l.d_in.p) + size_t(y0) * st->in_pitch, st->in_pitch,
+                                         hp + size_t(y0) * in_row, in_row, in_row, rows, cudaMemcpyHostToDevice, l.stream),
+                       "H2D copy (staged chunk)");
+        }
+    } else {
+        check_cuda(cudaMemcpy2DAsync(l.d_in.p, st->in_pitch, d.src, d.src_pitch, in_row, d.sh, cudaMemcpyHostToDevice, l.stream),
+                   "H2D copy");
     }
-    check_cuda(cudaMemcpy2DAsync(l.d_in.p, st->in_pitch, src, src_pitch, in_row, d.sh, cudaMemcpyHostToDevice, l.stream),
-               "H2D copy");
     JobDesc dj = d;
     dj.src = l.d_in.p;
     dj.dst = l.d_out.p;
@@ -623,30 +755,48 @@ void start_host_job(Context& ctx, Device& dev, Lane& l, const JobDesc& d, HostJo
     if (status != kOk) fail(Status(status), last_error());
     ctx.enqueue(dev, lp, l.h_desc, l.d_desc, l.d_scratch, l.stream, exact);
     st->out_staged = !is_pinned(d.dst);
-    void* dst = d.dst;
-    size_t dst_pitch = d.dst_pitch;
     if (st->out_staged) {
+        // Pageable destination: the result comes back in chunks, each followed by an event, so that
+        // finish_host_job can copy chunk k out of the pinned staging while chunk k + 1 is still in flight.
         l.h_out.reserve(out_row * d.dh);
-        dst = l.h_out.p;
-        dst_pitch = out_row;
+        uint8_t* hp = static_cast<uint8_t*>(l.h_out.p);
+        st->out_chunk_rows = uint32_t(std::max<size_t>(1, kStageChunkBytes / std::max<size_t>(out_row, 1)));
+        size_t c = 0;
+        for (uint32_t y0 = 0; y0 < d.dh; y0 += st->out_chunk_rows, ++c) {
+            const uint32_t rows = std::min(st->out_chunk_rows, d.dh - y0);
+            check_cuda(cudaMemcpy2DAsync(hp + size_t(y0) * out_row, out_row, static_cast<const uint8_t*>(l.d_out.p) + size_t(y0) * st->out_pitch,
+                                         st->out_pitch, out_row, rows, cudaMemcpyDeviceToHost, l.stream),
+                       "D2H copy (staged chunk)");
+            if (c >= l.out_events.size()) {
+                cudaEvent_t e;
+                check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+                l.out_events.push_back(e);
+            }
+            check_cuda(cudaEventRecord(l.out_events[c], l.stream), "cudaEventRecord");
+        }
+    } else {
+        check_cuda(cudaMemcpy2DAsync(d.dst, d.dst_pitch, l.d_out.p, st->out_pitch, out_row, d.dh, cudaMemcpyDeviceToHost, l.stream),
+                   "D2H copy");
     }
-    check_cuda(cudaMemcpy2DAsync(dst, dst_pitch, l.d_out.p, st->out_pitch, out_row, d.dh, cudaMemcpyDeviceToHost, l.stream),
-               "D2H copy");
     // `lp` (and the table references it keeps alive) may go away now: the cache still holds the
     // tables, and kernels already enqueued only need the device memory, which eviction frees with a
     // synchronising cudaFree.
 }
 
-void finish_host_job(Lane& l, const HostJobState& st) {
-    check_cuda(cudaStreamSynchronize(l.stream), "resize (stream sync)");
+void finish_host_job(Context& ctx, Lane& l, const HostJobState& st) {
     if (st.out_staged) {
         const JobDesc& d = st.d;
         const size_t out_row = size_t(d.dw) * d.oc() * d.bps;
         const uint8_t* hp = static_cast<const uint8_t*>(l.h_out.p);
-        if (d.dst_pitch == out_row) std::memcpy(d.dst, hp, out_row * d.dh);
-        else for (uint32_t y = 0; y < d.dh; ++y)
-            std::memcpy(static_cast<uint8_t*>(d.dst) + size_t(y) * d.dst_pitch, hp + size_t(y) * out_row, out_row);
+        size_t c = 0;
+        for (uint32_t y0 = 0; y0 < d.dh; y0 += st.out_chunk_rows, ++c) {
+            const uint32_t rows = std::min(st.out_chunk_rows, d.dh - y0);
+            check_cuda(cudaEventSynchronize(l.out_events[c]), "resize (chunk sync)");
+            pooled_copy_rows(ctx.copy_pool, static_cast<uint8_t*>(d.dst) + size_t(y0) * d.dst_pitch, d.dst_pitch,
+                             hp + size_t(y0) * out_row, out_row, out_row, rows);
+        }
     }
+    check_cuda(cudaStreamSynchronize(l.stream), "resize (stream sync)");
 }
 
 // Cases imageops::resize answers without resampling.  Returns true if handled.
@@ -697,7 +847,7 @@ void Context::resize_host(const JobDesc& d, int* device_index_out) {
     try {
         HostJobState st;
         start_host_job(*this, dev, *l, d, &st, mode.load() == 1);
-        finish_host_job(*l, st);
+        finish_host_job(*this, *l, st);
     } catch (...) {
         cudaStreamSynchronize(l->stream);
         dev.release_lane(l);
@@ -728,7 +878,7 @@ void Context::resize_batch_host(JobDesc* descs, size_t n, int* status, int* devi
             if (inflight[size_t(k)] < 0) return;
             const size_t i = size_t(inflight[size_t(k)]);
             try {
-                finish_host_job(*lanes[size_t(k)], st[size_t(k)]);
+                finish_host_job(*this, *lanes[size_t(k)], st[size_t(k)]);
             } catch (const Error& e) {
                 status[i] = e.status;
                 errors[size_t(g)] = e.what;

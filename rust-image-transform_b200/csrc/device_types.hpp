@@ -50,6 +50,9 @@ struct DevJob {
                            // applies DynamicImage::to_rgb8() / to_rgba8() (8-bit only)
     int32_t bps;           // bytes per sample: 1 or 2
     DevPass v, h;
+    // Banded kernel only: a 2-D TMA tensor map (CUtensorMap, 128 bytes) of the source raster seen as
+    // [sh rows][src_pitch / 4 words]; box = 16 rows x 512 bytes, out-of-bounds words read as zero.
+    alignas(64) uint8_t src_map[128];
 };
 
 // One CTA's share of a job in the fused kernel: output columns [ox0,ox1) x rows [oy0,oy1).
