@@ -79,13 +79,16 @@ enum ikc_dims_code {
 /* Arithmetic mode of the resampling kernels. */
 enum ikc_mode {
     IKC_MODE_FAST = 0,   /* fused single-launch kernels, FMA accumulation: max |delta| <= 1 LSB; downscales run
-                            their vertical pass on the tensor cores (f16 hi + lo weights, f32 accumulation) */
+                            their vertical pass on the tensor cores as an exact integer product (u8 source bytes x
+                            15-bit fixed-point weights, s32 accumulation)                             */
     IKC_MODE_EXACT = 1,  /* two-launch verification path: separate mul/add in ascending tap order,
                             vertical then horizontal, f32 intermediate in HBM: delta == 0 vs the
                             CPU restatement of image 0.25.8                                      */
-    IKC_MODE_FAST_FP32 = 2  /* FAST without the tensor cores: downscales take the CUDA-core ring kernel
+    IKC_MODE_FAST_FP32 = 2, /* FAST without the tensor cores: downscales take the CUDA-core ring kernel
                             (the round-1 path; kept for A/B measurements and as the north-star's
                             "no tensor cores" variant); same +-1 LSB bound                        */
+    IKC_MODE_FAST_F16 = 3   /* FAST with the f16 tensor-core kernel for downscales (f16 hi + lo weights = 22 bits,
+                            f32 accumulation; a converter pass feeds it): finer weights, ~2x slower  */
 };
 
 #define IKC_MAX_DIM 65535u              /* per-axis bound on source and destination             */
@@ -177,6 +180,16 @@ IKC_API int ikc_pass_info(int filter, uint32_t n_in, uint32_t n_out, ikc_pass_in
  * with gbase == NULL and tiles == NULL only *band_n and the chunk count are returned. */
 IKC_API uint32_t ikc_pass_band(int filter, uint32_t n_in, uint32_t n_out, uint32_t* band_n, int32_t* gbase,
                                uint16_t* tiles, size_t tiles_cap);
+
+/* 8-bit band form of a downscale pass, as the integer tensor-core vertical pass consumes it (inspection for tests; no
+ * GPU needed).  Chunks of 32 source indices; chunk k only touches the 32 outputs starting at output 8 * gbase[k]
+ * (gbase[n_chunks] = number of 8-output groups).  Every weight is the integer round(w * 2^*shift), each output's
+ * weights nudged to sum to exactly 2^*shift, split into *limbs signed base-128 digits.  tiles: per chunk one s8 operand
+ * tile of (*limbs * 32) rows x 32 indices, row = digit * 32 + (output mod 32) with the most significant digit first,
+ * element (row n, index k) at (k / 16) * (*limbs * 512) + (n / 8) * 128 + (n % 8) * 16 + (k % 16).  Returns the number of chunks
+ * (0: the pass has no such form, or a buffer is too small); gbase == tiles == NULL: only *limbs, *shift and the count. */
+IKC_API uint32_t ikc_pass_band8(int filter, uint32_t n_in, uint32_t n_out, uint32_t* limbs, uint32_t* shift, int32_t* gbase,
+                                int8_t* tiles, size_t tiles_cap);
 
 /* ---- host-buffer entry points (the drop-in path; include H2D + D2H) -------------------------- */
 

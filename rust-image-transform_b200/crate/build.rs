@@ -7,7 +7,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     let lib = out.join("libimagekit_cuda.so");
-    let sources = ["plan.cpp", "context.cpp", "api.cpp", "generic.cu", "fused.cu", "fused_conv.cu", "tile.cu", "up2.cu", "banded.cu", "banded_conv.cu"];
+    let sources = ["plan.cpp", "context.cpp", "api.cpp", "generic.cu", "fused.cu", "fused_conv.cu", "tile.cu", "up2.cu", "banded.cu", "banded_conv.cu", "banded8.cu", "banded8_conv.cu"];
     let mut cmd = Command::new(&nvcc);
     cmd.args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo"])
         .args(["-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-fno-fast-math"])

@@ -75,7 +75,7 @@ void ikc_destroy(ikc_ctx* ctx) {
 int ikc_device_count(const ikc_ctx* ctx) { return ctx ? ctx->impl.device_count() : 0; }
 
 int ikc_set_mode(ikc_ctx* ctx, int mode) {
-    if (!ctx || (mode != IKC_MODE_FAST && mode != IKC_MODE_EXACT && mode != IKC_MODE_FAST_FP32)) {
+    if (!ctx || (mode != IKC_MODE_FAST && mode != IKC_MODE_EXACT && mode != IKC_MODE_FAST_FP32 && mode != IKC_MODE_FAST_F16)) {
         set_last_error("bad context or mode");
         return IKC_ERR_INVALID_ARG;
     }
@@ -140,6 +140,24 @@ uint32_t ikc_pass_band(int filter, uint32_t n_in, uint32_t n_out, uint32_t* band
             std::memcpy(tiles, p->band_tiles.data(), sizeof(uint16_t) * p->band_tiles.size());
         }
         chunks = n;
+    });
+    return chunks;
+}
+
+uint32_t ikc_pass_band8(int filter, uint32_t n_in, uint32_t n_out, uint32_t* limbs, uint32_t* shift, int32_t* gbase, int8_t* tiles,
+                        size_t tiles_cap) {
+    uint32_t chunks = 0;
+    guarded([&] {
+        auto p = build_pass(filter, n_in, n_out);
+        if (!p || p->band8.limbs == 0) return;
+        if (limbs) *limbs = uint32_t(p->band8.limbs);
+        if (shift) *shift = uint32_t(p->band8.shift);
+        if (gbase || tiles) {
+            if (!gbase || !tiles || tiles_cap < p->band8.tiles.size()) return;
+            std::memcpy(gbase, p->band8.gbase.data(), sizeof(int32_t) * p->band8.gbase.size());
+            std::memcpy(tiles, p->band8.tiles.data(), p->band8.tiles.size());
+        }
+        chunks = uint32_t(p->band8.gbase.size()) - 1;
     });
     return chunks;
 }
@@ -368,7 +386,8 @@ int ikc_batch_describe(const ikc_batch* b, char* out, size_t cap) {
     std::string s;
     for (auto& g : b->impl.lp.groups) {
         if (!s.empty()) s += "; ";
-        if (g.band_n) s += "banded_kernel<" + std::to_string(g.channels) + (g.convert ? ",conv" : "") + "> (band_n " + std::to_string(g.band_n) + ")";
+        if (g.band8_limbs) s += "banded8_kernel<" + std::to_string(g.channels) + (g.convert ? ",conv" : "") + "> (" + std::to_string(g.band8_limbs) + " digits)";
+        else if (g.band_n) s += "banded_kernel<" + std::to_string(g.channels) + (g.convert ? ",conv" : "") + "> (band_n " + std::to_string(g.band_n) + ")";
         else if (g.up_taps) s += "up2_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.up_taps) + ">";
         else if (g.kv == 0) s += g.bps == 2 ? "tile_kernel<u16>" : "tile_kernel";
         else s += "fused_ring_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.kv) + "," + std::to_string(g.kh) + "," + std::to_string(g.sv) + "," + std::to_string(g.sh) + ">";

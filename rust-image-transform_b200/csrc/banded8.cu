@@ -1,0 +1,434 @@
+// banded8.cu -- fused single-launch resize kernel for 8-bit downscales whose VERTICAL pass is an INTEGER banded
+// matrix product on the 5th-generation tensor cores (tcgen05.mma kind::i8, s32 accumulators in TMEM) -- sm_100a.
+//
+// Why a second tensor-core kernel: banded.cu (f16 operands) is bound by shared-memory bandwidth -- the converter
+// warps read every staged byte and write it back as two (f16), and the MMA reads those twice (hi + lo weights).
+// Here the source bytes are the A operand AS THEY ARE: a 2-D TMA box (32 rows x 128 bytes, 128-byte swizzle) lands
+// in shared memory in exactly the MN-major layout kind::i8 reads, so no thread touches the source at all.
+//
+//   A (M x K) = u8 source bytes, M = 128 byte columns, K = 32 source rows, straight from TMA.
+//   B (N x K) = the weights of the <= 32 output rows those source rows can touch, as integers
+//               W = round(w * 2^S) split into L signed base-128 digits (host-built tiles, plan.hpp: Band8);
+//               N = L * 32: one MMA per block and chunk computes every digit's partial sums.
+//   D (M x N) = s32 accumulators in TMEM: lane = byte column, column = digit * 32 + (output row mod 32).  The 32 rows are
+//               a ring of 4 groups of 8; a finished group is read with tcgen05.ld, its digits recombined in f32
+//               ((d1 * 128 + d0) -- exact products, one rounding), written to the shared-memory intermediate tile,
+//               zeroed and handed back.  The integer sums are exact, so the vertical pass is deterministic
+//               fixed-point arithmetic with 2^-S weight resolution (each output's weights sum to exactly one).
+//
+// The HORIZONTAL pass is banded.cu's: CUDA cores, output-stationary, lane = intermediate row, half warp = x segment.
+//
+// Warp roles (256 threads, 2 CTAs per SM, 256 TMEM columns each): warp 0 producer (TMA), warp 1 MMA issuer,
+// warps 2-3 idle (they only give their registers to the epilogue), warps 4-7 epilogue + horizontal pass.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "banded_common.cuh"
+#include "device_types.hpp"
+#include "launch.hpp"
+#include "plan.hpp"
+
+#ifndef IKC_BANDED8_CONV
+#define IKC_BANDED8_CONV 0
+#endif
+
+namespace ikc {
+namespace {
+
+constexpr int k8Blocks = 4;                          // 128-byte column blocks per strip
+constexpr int k8StripBytes = k8Blocks * 128;
+constexpr int k8Chunk = kBand8Chunk;                 // source rows per stage = K of one i8 MMA
+constexpr int k8BlockBytes = 128 * k8Chunk;          // one operand tile: 32 rows x 128 bytes
+constexpr int k8UStageBytes = k8Blocks * k8BlockBytes;
+constexpr int k8UStages = 3, k8BStages = 4;
+constexpr int k8Ring = 4;                            // accumulator groups in TMEM: the ring IS the chunk window
+constexpr int k8Group = kBand8Group;                 // output rows per group
+constexpr int k8Window = kBand8Window;               // output rows in the ring
+constexpr int k8TileRows = 16;                       // intermediate rows per horizontal phase (two groups)
+constexpr int k8Threads = 256;
+constexpr int k8Segs = 8;
+constexpr int k8HeaderBytes = 1024;                  // mbarriers; the operand stages behind it stay 1024-byte aligned (swizzle atoms)
+constexpr size_t k8MaxSmem = 113 * 1024;
+constexpr int k8RegsIo = 40, k8RegsEpi = 216;        // 128 x 40 + 128 x 216 = 256 x 128
+constexpr int k8TmpPad = 64;
+
+__host__ __device__ constexpr int tmp8_pitch_floats(int channels) {
+    return channels == 4 ? k8StripBytes + 4 : channels == 2 ? k8StripBytes + 2 : k8StripBytes + 1;
+}
+
+// Shared-memory descriptor of the A tile: MN-major, 128-byte swizzle, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint32_t a8_desc_hi() { return (1024u >> 4) | (1u << 14) | (2u << 29); }  // SBO, version, SWIZZLE_128B
+// Instruction descriptor: D = s32, A = u8 (MN-major), B = s8 (K-major), M = 128, N = n.
+__device__ __forceinline__ uint32_t instr_desc_i8(uint32_t n) {
+    return (2u << 4) | (0u << 7) | (1u << 10) | (1u << 15) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_i8_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(1u)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, int (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void tmem_zero8(uint32_t addr) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
+}
+// s32 -> f32, exact for |v| < 2^22, without the quarter-rate I2F: add the integer to the bits of 1.5 * 2^23, subtract it as a float.
+__device__ __forceinline__ float int_to_float_small(int v) { return __int_as_float(v + 0x4B400000) - 12582912.0f; }
+
+constexpr bool k8Conv = IKC_BANDED8_CONV != 0;
+
+}  // namespace
+
+// Shared memory: [mbarriers (1 KB) | operand ring: 3 stages x 4 blocks x (32 rows x 128 B, swizzled) | weight-tile ring
+//                (4 x L * 1 KB) | horizontal weights of the strip | (left, right) of the strip's outputs |
+//                intermediate tile: 16 rows x pitch floats]
+template <int C, int L, bool CONV>
+__global__ void __launch_bounds__(k8Threads, 2)
+banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, const Band8Geom geom) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int kTmpPitch = tmp8_pitch_floats(C);
+    constexpr int kN = L * k8Window;                // MMA N = TMEM columns per block
+    constexpr int kTmemCols = k8Blocks * kN;        // 256 for L = 2
+    constexpr uint32_t kBTile = uint32_t(kN) * k8Chunk;  // bytes of one chunk's weight tile
+
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* const u_full = bars;                   // [k8UStages] source boxes landed (tx bytes)
+    uint64_t* const u_empty = u_full + k8UStages;    // [k8UStages] the MMAs that read the stage have completed
+    uint64_t* const b_full = u_empty + k8UStages;    // [k8BStages]
+    uint64_t* const b_empty = b_full + k8BStages;    // [k8BStages]
+    uint64_t* const t_full = b_empty + k8BStages;    // [k8Ring] every MMA into the group has completed
+    uint64_t* const t_empty = t_full + k8Ring;       // [k8Ring] the 4 epilogue warps have drained and zeroed the group
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
+    uint8_t* const ustage = smem + k8HeaderBytes;
+    uint8_t* const bstage = ustage + k8UStages * k8UStageBytes;
+    float2* const hw = reinterpret_cast<float2*>(bstage + k8BStages * kBTile);
+    int2* const hlr = reinterpret_cast<int2*>(hw + ((geom.hw_pairs + 1) & ~1));
+    float* const tmp = reinterpret_cast<float*>(hlr + ((geom.max_out + 1) & ~1));
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    const WorkItem it = items[blockIdx.x];
+    const DevJob* __restrict__ J = jobs + it.job;
+    const int ox0 = it.ox0, ox1 = it.ox1, oy0 = it.oy0, oy1 = it.oy1;
+    const int32_t* __restrict__ hleft = J->h.left;
+    const int32_t* __restrict__ hright = J->h.right;
+    const int32_t* __restrict__ gbase = J->v.band8_gbase;
+
+    // Strip geometry along x: source bytes [b0, b0 + nb), 16-byte aligned at both ends.
+    const int xl = __ldg(hleft + ox0);
+    const int xr = __ldg(hright + ox1 - 1);
+    const int row_bytes = int(J->sw) * C;
+    const int b0 = (xl * C) & ~15;
+    const int b1 = min((xr * C + 15) & ~15, (row_bytes + 15) & ~15);
+    const int nb = b1 - b0;
+    const int nblk = (nb + 127) >> 7;
+    // Chunk geometry along y: source rows [y_first, y_last) -> chunks [k0, k1] of the pass's global chunk grid.
+    const int y_first = __ldg(J->v.left + oy0);
+    const int y_last = __ldg(J->v.right + oy1 - 1);
+    const int k0 = y_first / k8Chunk, k1 = (y_last - 1) / k8Chunk;
+    const int nchunks = k1 - k0 + 1;
+    const int g0 = __ldg(gbase + k0);                // first group (of 8 outputs) any MMA of this item touches
+    const int g_end = __ldg(gbase + k1) + k8Ring;    // one past the last
+
+    if (tid == 0) {
+        if (smem_addr(smem) & 1023u) __trap();  // the swizzled operand tiles need 1024-byte aligned shared memory
+        for (int s = 0; s < k8UStages; ++s) { mbar_init(u_full + s, 1); mbar_init(u_empty + s, 1); }
+        for (int s = 0; s < k8BStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < k8Ring; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // Horizontal tables of the strip: (left, right) and the weights (x 2^-shift, duplicated for FFMA2) of every output.
+    const int n_out = ox1 - ox0;
+    const int hstride = J->h.stride;
+    for (int i = tid; i < n_out; i += k8Threads) hlr[i] = make_int2(__ldg(hleft + ox0 + i), __ldg(hright + ox0 + i));
+    {
+        const float* __restrict__ wsrc = J->h.w + size_t(ox0) * hstride;
+        const float unscale = __int_as_float((127 - J->v.band8_shift) << 23);  // 2^-shift: the vertical sums are integers x 2^shift
+        for (int i = tid; i < n_out * hstride; i += k8Threads) {
+            const float w = __ldg(wsrc + i) * unscale;
+            hw[i] = make_float2(w, w);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(k8RegsIo));
+    if (warp == 0) {
+        // ------------------------------------------------------------------------------ producer
+        if (lane == 0) {
+            const void* const src_map = J->src_map8;
+            asm volatile("prefetch.tensormap [%0];" ::"l"(src_map) : "memory");
+            const uint8_t* const tiles = reinterpret_cast<const uint8_t*>(J->v.band8_tiles);
+            for (int i = 0; i < nchunks; ++i) {
+                const int k = k0 + i;
+                const int su = i % k8UStages, sb = i % k8BStages;
+                mbar_wait_parked(u_empty + su, ((i / k8UStages) & 1) ^ 1);
+                // one box per 128-byte block: 32 rows x 128 bytes, swizzled into the MMA's operand layout; bytes past the
+                // raster's pitch or rows read as zero
+                mbar_expect_tx(u_full + su, uint32_t(nblk) * k8BlockBytes);
+                for (int b = 0; b < nblk; ++b)
+                    tma_load_2d(ustage + su * k8UStageBytes + b * k8BlockBytes, src_map, b0 + b * 128, k * k8Chunk, u_full + su);
+                mbar_wait_parked(b_empty + sb, ((i / k8BStages) & 1) ^ 1);
+                mbar_expect_tx(b_full + sb, kBTile);
+                bulk_load(bstage + sb * kBTile, tiles + size_t(k) * kBTile, kBTile, b_full + sb);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------ MMA issuer (one lane)
+        if (lane == 0) {
+            int acquired = g0;   // groups [g0, acquired) belong to the MMAs (zeroed by the epilogue warps)
+            int completed = g0;  // groups [g0, completed) have been committed to the epilogue
+            const uint32_t a_lo0 = ((smem_addr(ustage) >> 4) & 0x3fffu) | ((1024u >> 4) << 16);
+            const uint32_t b_lo0 = ((smem_addr(bstage) >> 4) & 0x3fffu) | (((uint32_t(kN) * 16u) >> 4) << 16);
+            constexpr uint32_t kBDescHi = (128u >> 4) | (1u << 14);
+            const uint32_t idesc = instr_desc_i8(uint32_t(kN));
+            int gb_next = g0;
+            for (int i = 0; i < nchunks; ++i) {
+                const int k = k0 + i;
+                const int gb = gb_next;
+                gb_next = (i + 1 < nchunks) ? __ldg(gbase + k + 1) : 0;
+                while (acquired < gb + k8Ring) {  // ring slot = absolute group & 3, use count = how often the item reached it
+                    mbar_wait(t_empty + (acquired & (k8Ring - 1)), ((acquired - g0) / k8Ring) & 1);
+                    ++acquired;
+                }
+                const int su = i % k8UStages, sb = i % k8BStages;
+                mbar_wait(u_full + su, (i / k8UStages) & 1);
+                mbar_wait(b_full + sb, (i / k8BStages) & 1);
+                tc_fence_after();
+                const uint32_t a_lo = a_lo0 + uint32_t(su) * (k8UStageBytes >> 4);
+                const uint64_t b_desc = make_u64(b_lo0 + uint32_t(sb) * (kBTile >> 4), kBDescHi);
+#pragma unroll
+                for (int b = 0; b < k8Blocks; ++b)
+                    if (b < nblk)
+                        mma_i8_acc(tmem + uint32_t(b * kN), make_u64(a_lo + uint32_t(b) * (k8BlockBytes >> 4), a8_desc_hi()), b_desc, idesc);
+                tc_commit(u_empty + su);
+                tc_commit(b_empty + sb);
+                const int final_below = (i + 1 < nchunks) ? gb_next : acquired;  // groups below it get no more contributions
+                for (; completed < final_below; ++completed) tc_commit(t_full + (completed & (k8Ring - 1)));
+            }
+        }
+        __syncwarp();
+    }
+    // (warps 2 and 3 have no role: they gave their registers up and wait for the teardown)
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(k8RegsEpi));
+        // ------------------------------------------------------------------------------ epilogue + horizontal pass
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may touch
+        const uint32_t tlane = tmem + (uint32_t(q * 32) << 16);
+        for (int c = 0; c < kTmemCols; c += 8) tmem_zero8(tlane + uint32_t(c));
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0)
+            for (int s = 0; s < k8Ring; ++s) mbar_arrive(t_empty + s);
+
+        const int hrow = lane & 15;
+        const int seg = 2 * q + (lane >> 4);
+        const int per = (n_out + k8Segs - 1) / k8Segs;
+        const int os = ox0 + seg * per;
+        const int oe = min(os + per, ox1);
+        const int CO = CONV ? J->out_channels : C;
+        uint8_t* const dst_base = J->dst;
+        const size_t dst_pitch = J->dst_pitch;
+        const float* const my_row = tmp + hrow * kTmpPitch - b0;   // indexed by source byte column x * C + c
+        const bool uni2 = os < oe && J->h.uni_step == 2 && hstride == 12 && os >= J->h.uni_lo && oe <= J->h.uni_hi;
+        float2 uw[12];
+#pragma unroll
+        for (int t = 0; t < 12; ++t) uw[t] = uni2 ? hw[(os - ox0) * 12 + t] : make_float2(0.0f, 0.0f);
+        float* const tcol = tmp + q * 32 + lane;
+
+        for (int g = g0; g < g_end; ++g) {
+            const int slot = g & (k8Ring - 1);
+            mbar_wait(t_full + slot, ((g - g0) / k8Ring) & 1);
+            tc_fence_after();
+            const int tile_row0 = (g >> 1) * k8TileRows;          // output row of the intermediate tile's first row
+            const bool live = tile_row0 < oy1 && tile_row0 + k8TileRows > oy0;
+            if (live) {  // TMEM -> registers (digits recombined) -> intermediate tile rows (g & 1) * 8 ..
+                int v[k8Blocks][L][8];
+#pragma unroll
+                for (int b = 0; b < k8Blocks; ++b)
+                    if (b < nblk) {
+#pragma unroll
+                        for (int d = 0; d < L; ++d) tmem_ld8(tlane + uint32_t(b * kN + d * k8Window + slot * k8Group), v[b][d]);
+                    }
+                tmem_ld_wait();
+                float* const trow = tcol + (g & 1) * k8Group * kTmpPitch;
+#pragma unroll
+                for (int b = 0; b < k8Blocks; ++b) {
+                    if (b < nblk) {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            float t = int_to_float_small(v[b][0][r]);                       // most significant digit first
+#pragma unroll
+                            for (int d = 1; d < L; ++d) t = fmaf(t, 128.0f, int_to_float_small(v[b][d][r]));
+                            trow[r * kTmpPitch + b * 128] = t;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < k8Blocks; ++b)
+                if (b < nblk) {
+#pragma unroll
+                    for (int d = 0; d < L; ++d) tmem_zero8(tlane + uint32_t(b * kN + d * k8Window + slot * k8Group));
+                }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + slot);
+            if (!live || (!(g & 1) && g + 1 < g_end)) continue;  // the tile's second group is still to come
+            epi_barrier();  // the whole tile is in shared memory
+
+            const int orow = tile_row0 + hrow;
+            const bool row_live = orow >= oy0 && orow < oy1;
+            uint8_t* const my_dst = dst_base + size_t(orow) * dst_pitch;
+            if (os < oe) {
+                if (uni2) {
+                    // Blocks of 8 outputs as straight-line code: the 26 pixels their windows span are loaded at once
+                    // (output j of the block reads pixels 2j .. 2j + 11).  Reads past the segment's last window stay
+                    // inside the tile's padding and are never stored.
+                    for (int o = os; o < oe; o += 8) {
+                        const float* px = my_row + hlr[o - ox0].x * C;
+                        float4 p[26];
+#pragma unroll
+                        for (int t = 0; t < 26; ++t) p[t] = load_px<C>(px + t * C);
+                        uint32_t word[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2) {  // two outputs at a time: eight accumulation chains in flight
+                            float2 a01 = make_float2(kRoundBias, kRoundBias), a23 = a01, c01 = make_float2(0.0f, 0.0f), c23 = c01;
+                            float2 d01 = a01, d23 = a01, e01 = c01, e23 = c01;
+#pragma unroll
+                            for (int t = 0; t < 12; t += 2) {
+                                const float4 x0 = p[2 * j + t], x1 = p[2 * j + t + 1], y0 = p[2 * j + 2 + t], y1 = p[2 * j + 3 + t];
+                                a01 = __ffma2_rn(uw[t], make_float2(x0.x, x0.y), a01);
+                                a23 = __ffma2_rn(uw[t], make_float2(x0.z, x0.w), a23);
+                                d01 = __ffma2_rn(uw[t], make_float2(y0.x, y0.y), d01);
+                                d23 = __ffma2_rn(uw[t], make_float2(y0.z, y0.w), d23);
+                                c01 = __ffma2_rn(uw[t + 1], make_float2(x1.x, x1.y), c01);
+                                c23 = __ffma2_rn(uw[t + 1], make_float2(x1.z, x1.w), c23);
+                                e01 = __ffma2_rn(uw[t + 1], make_float2(y1.x, y1.y), e01);
+                                e23 = __ffma2_rn(uw[t + 1], make_float2(y1.z, y1.w), e23);
+                            }
+                            a01 = __fadd2_rn(a01, c01); a23 = __fadd2_rn(a23, c23);
+                            d01 = __fadd2_rn(d01, e01); d23 = __fadd2_rn(d23, e23);
+                            word[j] = pack_pixel(make_float4(a01.x, a01.y, a23.x, a23.y));
+                            word[j + 1] = pack_pixel(make_float4(d01.x, d01.y, d23.x, d23.y));
+                        }
+                        if (row_live) {
+                            uint8_t* const d = my_dst + size_t(o) * CO;
+                            if (C == 4 && !CONV && o + 8 <= oe && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+                                *reinterpret_cast<uint4*>(d) = make_uint4(word[0], word[1], word[2], word[3]);
+                                *reinterpret_cast<uint4*>(d + 16) = make_uint4(word[4], word[5], word[6], word[7]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (o + j < oe) store_word<C>(d + j * CO, word[j], CO);
+                            }
+                        }
+                    }
+                } else {
+                    for (int o = os; o < oe; ++o) {
+                        const int2 lr = hlr[o - ox0];
+                        const float2* wrow = hw + (o - ox0) * hstride;
+                        const float* px = my_row + lr.x * C;
+                        const int n = lr.y - lr.x;
+                        float2 a01 = make_float2(kRoundBias, kRoundBias), a23 = a01;
+                        float2 c01 = make_float2(0.0f, 0.0f), c23 = c01;
+                        int t = 0;
+                        for (; t + 1 < n; t += 2) {
+                            const float4 e = load_px<C>(px + t * C), f = load_px<C>(px + (t + 1) * C);
+                            const float2 we = wrow[t], wf = wrow[t + 1];
+                            a01 = __ffma2_rn(we, make_float2(e.x, e.y), a01);
+                            a23 = __ffma2_rn(we, make_float2(e.z, e.w), a23);
+                            c01 = __ffma2_rn(wf, make_float2(f.x, f.y), c01);
+                            c23 = __ffma2_rn(wf, make_float2(f.z, f.w), c23);
+                        }
+                        if (t < n) {
+                            const float4 e = load_px<C>(px + t * C);
+                            const float2 we = wrow[t];
+                            a01 = __ffma2_rn(we, make_float2(e.x, e.y), a01);
+                            a23 = __ffma2_rn(we, make_float2(e.z, e.w), a23);
+                        }
+                        if (row_live) store_pixel<C>(my_dst + size_t(o) * CO, make_float4(a01.x + c01.x, a01.y + c01.y, a23.x + c23.x, a23.y + c23.y), CO);
+                    }
+                }
+            }
+            __syncwarp();
+            epi_barrier();  // the tile may be overwritten
+        }
+    }
+
+    // ---------------------------------------------------------------------------------- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
+    }
+}
+
+// ---- launcher ---------------------------------------------------------------------------------
+
+#if !IKC_BANDED8_CONV
+size_t banded8_smem_bytes(int channels, const Band8Geom& g) {
+    const size_t tmp_pitch = size_t(tmp8_pitch_floats(channels));
+    return size_t(k8HeaderBytes) + size_t(k8UStages) * k8UStageBytes + size_t(k8BStages) * size_t(g.limbs) * k8Window * k8Chunk +
+           size_t((g.hw_pairs + 1) & ~1) * sizeof(float2) + size_t((g.max_out + 1) & ~1) * sizeof(int2) +
+           (size_t(k8TileRows) * tmp_pitch + k8TmpPad) * sizeof(float);
+}
+size_t banded8_max_smem() { return k8MaxSmem; }
+int banded8_max_src_bytes() { return k8StripBytes; }
+int banded8_tile_rows() { return k8TileRows; }
+bool banded8_supported(int channels, int limbs) { return channels >= 1 && channels <= 4 && limbs == 2; }
+#endif
+
+template <int C, int L>
+static cudaError_t launch_one8(const DevJob* jobs, const WorkItem* items, const Band8Geom& geom, cudaStream_t stream) {
+    const size_t smem = banded8_smem_bytes(C, geom);
+    if (smem > k8MaxSmem) return cudaErrorInvalidValue;
+    // always the planner-wide maximum: the attribute is shared by every thread launching on this device
+    cudaError_t e = cudaFuncSetAttribute(banded8_kernel<C, L, k8Conv>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k8MaxSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(banded8_kernel<C, L, k8Conv>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    banded8_kernel<C, L, k8Conv><<<geom.n_items, k8Threads, smem, stream>>>(jobs, items, geom);
+    return cudaGetLastError();
+}
+
+#if IKC_BANDED8_CONV
+cudaError_t launch_banded8_conv(int channels, const DevJob* jobs, const WorkItem* items, const Band8Geom& geom, cudaStream_t stream) {
+#else
+cudaError_t launch_banded8_conv(int channels, const DevJob* jobs, const WorkItem* items, const Band8Geom& geom, cudaStream_t stream);  // banded8_conv.cu
+
+cudaError_t launch_banded8(int channels, bool convert, const DevJob* jobs, const WorkItem* items, const Band8Geom& geom,
+                           cudaStream_t stream) {
+    if (convert) return launch_banded8_conv(channels, jobs, items, geom, stream);
+#endif
+    if (geom.limbs != 2) return cudaErrorInvalidValue;
+    switch (channels) {
+        case 1: return launch_one8<1, 2>(jobs, items, geom, stream);
+        case 2: return launch_one8<2, 2>(jobs, items, geom, stream);
+        case 3: return launch_one8<3, 2>(jobs, items, geom, stream);
+        case 4: return launch_one8<4, 2>(jobs, items, geom, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace ikc

@@ -48,6 +48,23 @@ bool encode_src_map(uint8_t (&out)[128], const void* base, uint32_t rows, size_t
     return true;
 }
 
+// Source raster as [rows][pitch] bytes; box = 32 rows x 128 bytes with the 128-byte swizzle (banded8's operand tiles).
+bool encode_src_map8(uint8_t (&out)[128], const void* base, uint32_t rows, size_t pitch) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    alignas(64) CUtensorMap map;
+    const cuuint64_t gdim[2] = {cuuint64_t(pitch), cuuint64_t(rows)};
+    const cuuint64_t gstride[1] = {cuuint64_t(pitch)};
+    const cuuint32_t box[2] = {128, uint32_t(kBand8Chunk)};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    std::memcpy(out, &map, 128);
+    return true;
+}
+
 // ---- errors ---------------------------------------------------------------------------------------
 
 static thread_local std::string g_last_error;
@@ -240,11 +257,13 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     const size_t b_up2 = up(sizeof(float) * host->up2_pairs.size());
     const size_t b_band = up(sizeof(uint16_t) * host->band_tiles.size());
     const size_t b_gbase = up(sizeof(int32_t) * host->band_gbase.size());
+    const size_t b_band8 = up(host->band8.tiles.size());
+    const size_t b_gbase8 = up(sizeof(int32_t) * host->band8.gbase.size());
     auto t = std::make_shared<DevTables>();
     t->device = ordinal_;
     t->host = host;
     check_cuda(cudaSetDevice(ordinal_), "cudaSetDevice");
-    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + 2 * b_ring + 2 * b_up2 + b_band + b_gbase + 256), "cudaMalloc(weight tables)");
+    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + 2 * b_ring + 2 * b_up2 + b_band + b_gbase + b_band8 + b_gbase8 + 256), "cudaMalloc(weight tables)");
     uint8_t* p = static_cast<uint8_t*>(t->base);
     auto put = [&](const void* src, size_t bytes, size_t slot) {
         uint8_t* at = p;
@@ -274,6 +293,12 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     t->pass.band_tiles = host->band_n ? reinterpret_cast<const uint16_t*>(band) : nullptr;
     t->pass.band_gbase = host->band_n ? reinterpret_cast<const int32_t*>(gbase) : nullptr;
     t->pass.band_n = host->band_n;
+    const uint8_t* band8 = put(host->band8.tiles.data(), host->band8.tiles.size(), b_band8);
+    const uint8_t* gbase8 = put(host->band8.gbase.data(), sizeof(int32_t) * host->band8.gbase.size(), b_gbase8);
+    t->pass.band8_tiles = host->band8.limbs ? reinterpret_cast<const int8_t*>(band8) : nullptr;
+    t->pass.band8_gbase = host->band8.limbs ? reinterpret_cast<const int32_t*>(gbase8) : nullptr;
+    t->pass.band8_limbs = host->band8.limbs;
+    t->pass.band8_shift = host->band8.shift;
     t->pass.up2_off = host->up2_off;
     t->pass.up2_taps = host->up2_taps;
     t->pass.up2_uni_lo = host->up2_uni_lo;
@@ -444,6 +469,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         int sv, sh;  // uniform steps the ring kernel has a specialised loop for, else 0
         bool convert;
         int band_n;  // > 0: goes to the banded (tensor-core) kernel instead of the ring kernel
+        int band8;   // > 0: goes to the banded8 (integer tensor-core) kernel; digits per weight
     };
     std::vector<Cand> cands;
     std::vector<WorkItem> tile_items[2];  // [bytes per sample - 1]: one tile-kernel launch per sample type
@@ -479,7 +505,26 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
                                 (d.oc() != 4 || ((reinterpret_cast<uintptr_t>(d.dst) | d.dst_pitch) & 3) == 0);
             bool fused = !exact && d.bps == 1 && d.sh >= d.dh && d.sw >= d.dw &&
                          fused_supported(d.channels, tv->pass.ring_k, th->pass.ring_k) && tma_ok;
-            Cand c{idx, {}, d.channels, tv->pass.ring_k, th->pass.ring_k, 0, 0, d.oc() != d.channels, 0};
+            Cand c{idx, {}, d.channels, tv->pass.ring_k, th->pass.ring_k, 0, 0, d.oc() != d.channels, 0, 0};
+            // First choice for downscales: the banded8 kernel (vertical pass as an integer product on the tensor cores,
+            // source bytes used as they are).
+            bool banded8 = !exact && mode.load() == 0 && d.bps == 1 && d.sh >= d.dh && d.sw >= d.dw && tma_ok &&
+                           tv->pass.band8_tiles && banded8_supported(d.channels, tv->pass.band8_limbs);
+            if (banded8) {
+                Band8Geom probe{tv->pass.band8_limbs, 2, 2, 0};
+                const size_t fixed = banded8_smem_bytes(d.channels, probe);
+                const size_t room = banded8_max_smem() > fixed ? banded8_max_smem() - fixed : 0;
+                const int max_out = int(std::min<size_t>(room / (8 * (size_t(th->pass.stride) + 1)), 512));
+                banded8 = max_out >= 1 &&
+                          cut_strips(*th->host, d.channels, int(d.sw), banded8_max_src_bytes(), max_out, &c.strips) &&
+                          encode_src_map8(lp.jobs[size_t(idx)].src_map8, d.src, d.sh, d.src_pitch);
+                if (banded8) {
+                    c.band8 = tv->pass.band8_limbs;
+                    cands.push_back(std::move(c));
+                    continue;
+                }
+                c.strips.clear();
+            }
             // First choice for downscales: the banded kernel (vertical pass on the tensor cores).  The strip's
             // horizontal tables must fit what its other shared-memory tenants leave.
             bool banded = !exact && mode.load() != 2 && d.bps == 1 && d.sh >= d.dh && d.sw >= d.dw && tma_ok && tv->pass.band_tiles &&
@@ -554,13 +599,13 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
     const size_t slots = size_t(dev.sm_count()) * 2;
     for (auto& c : cands) {
         const DevJob& j = lp.jobs[c.job];
-        const int group_rows = c.band_n ? banded_group_rows() : fused_group_rows();
+        const int group_rows = c.band8 ? banded8_tile_rows() : c.band_n ? banded_group_rows() : fused_group_rows();
         // Pick the chunk count that minimises (tail-wave waste) x (vertical halo recompute), assuming
         // the other jobs of the batch are cut the same way.
         const PassPlan& vp = *lp.keepalive[size_t(c.job) * 2]->host;
         const double ratio_v = double(j.sh) / double(j.dh);
         // the banded kernel reads whole 16-row chunks and pays a fixed prologue (TMEM allocation, tables) per item
-        const double halo_rows = std::max(0.0, double(vp.max_count) - ratio_v) + (c.band_n ? 36.0 : 0.0);
+        const double halo_rows = std::max(0.0, double(vp.max_count) - ratio_v) + (c.band_n ? 36.0 : c.band8 ? 52.0 : 0.0);
         const int max_chunks = std::max(1, std::min(64, int(j.dh) / (2 * group_rows)));
         int n_chunks = 1;
         double best = 1e30;
@@ -574,28 +619,37 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         }
         FusedGroup* g = nullptr;
         for (auto& gg : lp.groups)
-            if (gg.channels == c.ch && gg.convert == c.convert &&
-                (c.band_n ? gg.band_n == c.band_n
-                          : (gg.band_n == 0 && gg.kv == c.kv && gg.kh == c.kh && gg.sv == c.sv && gg.sh == c.sh)))
+            if (gg.channels == c.ch && gg.convert == c.convert && gg.band8_limbs == c.band8 &&
+                (c.band8 ? true
+                 : c.band_n ? gg.band_n == c.band_n
+                            : (gg.band_n == 0 && gg.kv == c.kv && gg.kh == c.kh && gg.sv == c.sv && gg.sh == c.sh)))
                 g = &gg;
         if (!g) {
-            lp.groups.push_back(FusedGroup{c.ch, c.band_n ? -1 : c.kv, c.band_n ? -1 : c.kh, {}, {}, {}, c.sv, c.sh, c.convert});
+            const bool tc = c.band_n || c.band8;
+            lp.groups.push_back(FusedGroup{c.ch, tc ? -1 : c.kv, tc ? -1 : c.kh, {}, {}, {}, c.sv, c.sh, c.convert});
             g = &lp.groups.back();
             g->band_n = c.band_n;
             g->bgeom.band_n = c.band_n;
+            g->band8_limbs = c.band8;
+            g->b8geom.limbs = c.band8;
         }
         const PassPlan& hp = *lp.keepalive[size_t(c.job) * 2 + 1]->host;
         for (int k = 0; k < n_chunks; ++k) {
             // banded kernel: chunk boundaries on multiples of the 16-row group, so no group straddles two items
             int oy0 = int(int64_t(j.dh) * k / n_chunks);
             int oy1 = int(int64_t(j.dh) * (k + 1) / n_chunks);
-            if (c.band_n) {
+            if (c.band_n || c.band8) {
                 oy0 = k == 0 ? 0 : (oy0 + group_rows / 2) / group_rows * group_rows;
                 oy1 = k == n_chunks - 1 ? int(j.dh) : (oy1 + group_rows / 2) / group_rows * group_rows;
             }
             if (oy1 <= oy0) continue;
             for (auto& s : c.strips) {
                 g->items.push_back(WorkItem{c.job, s.first, s.second, oy0, oy1});
+                if (c.band8) {
+                    g->b8geom.max_out = std::max(g->b8geom.max_out, s.second - s.first);
+                    g->b8geom.hw_pairs = std::max(g->b8geom.hw_pairs, (s.second - s.first) * int(hp.stride));
+                    continue;
+                }
                 if (c.band_n) {
                     g->bgeom.max_out = std::max(g->bgeom.max_out, s.second - s.first);
                     g->bgeom.hw_pairs = std::max(g->bgeom.hw_pairs, (s.second - s.first) * int(hp.stride));
@@ -611,6 +665,12 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         }
     }
     for (auto& g : lp.groups) {
+        if (g.band8_limbs) {
+            g.b8geom.n_items = int(g.items.size());
+            if (banded8_smem_bytes(g.channels, g.b8geom) > banded8_max_smem())
+                fail(kUnsupported, "internal: banded8 kernel shared-memory budget exceeded");
+            continue;
+        }
         if (g.band_n) {
             g.bgeom.n_items = int(g.items.size());
             if (banded_smem_bytes(g.channels, g.bgeom) > banded_max_smem())
@@ -651,7 +711,8 @@ void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, 
     size_t off = (sizeof(DevJob) * lp.jobs.size() + 15) & ~size_t(15);
     for (auto& g : lp.groups) {
         const WorkItem* d_items = reinterpret_cast<const WorkItem*>(d_desc_base + off);
-        if (g.band_n) check_cuda(launch_banded(g.channels, g.convert, d_jobs, d_items, g.bgeom, stream), "launch banded_kernel");
+        if (g.band8_limbs) check_cuda(launch_banded8(g.channels, g.convert, d_jobs, d_items, g.b8geom, stream), "launch banded8_kernel");
+        else if (g.band_n) check_cuda(launch_banded(g.channels, g.convert, d_jobs, d_items, g.bgeom, stream), "launch banded_kernel");
         else if (g.up_taps) check_cuda(launch_up2(g.channels, g.up_taps, d_jobs, d_items, int(g.items.size()), stream), "launch up2_kernel");
         else if (g.kv == 0) check_cuda(launch_tile(g.bps, d_jobs, d_items, g.tgeom, stream), "launch tile_kernel");
         else check_cuda(launch_fused(g.channels, g.kv, g.kh, g.sv, g.sh, g.convert, d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");

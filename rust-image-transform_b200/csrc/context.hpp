@@ -66,6 +66,8 @@ struct FusedGroup {  // one kernel launch over a list of work items
     int bps = 1;           // tile-kernel launch: bytes per sample of its jobs (1 or 2)
     int band_n = 0;        // > 0: a banded (tensor-core) launch whose weight tiles span band_n output rows
     BandGeom bgeom{};
+    int band8_limbs = 0;   // > 0: a banded8 (integer tensor-core) launch with this many digits per weight
+    Band8Geom b8geom{};
 };
 
 // Everything needed to enqueue a set of device-resident jobs.

@@ -35,6 +35,11 @@ struct DevPass {
     const uint16_t* band_tiles;      // [n_chunks][2][band_n * 16] f16, shared-memory operand layout; nullptr if none
     const int32_t* band_gbase;       // [n_chunks + 1]
     int32_t band_n;                  // output rows per operand tile (32 or 48); 0 if none
+    // 8-bit band form (plan.hpp: Band8), used when the pass runs vertically as an integer product (banded8.cu).
+    const int8_t* band8_tiles;       // [n_chunks][limbs * 32 x 32] s8, shared-memory operand layout; nullptr if none
+    const int32_t* band8_gbase;      // [n_chunks + 1], groups of 8 outputs
+    int32_t band8_limbs;             // base-128 digits per weight (2 or 3); 0 if none
+    int32_t band8_shift;             // weights are round(w * 2^shift)
 };
 
 // One image resize, device pointers.
@@ -53,6 +58,9 @@ struct DevJob {
     // Banded kernel only: a 2-D TMA tensor map (CUtensorMap, 128 bytes) of the source raster seen as
     // [sh rows][src_pitch / 4 words]; box = 16 rows x 512 bytes, out-of-bounds words read as zero.
     alignas(64) uint8_t src_map[128];
+    // banded8 kernel: the same raster as [sh rows][src_pitch bytes] of u8, box = 32 rows x 128 bytes, 128-byte swizzle
+    // (the box lands in shared memory as the MN-major operand tile the integer MMA reads).
+    alignas(64) uint8_t src_map8[128];
 };
 
 // One CTA's share of a job in the fused kernel: output columns [ox0,ox1) x rows [oy0,oy1).
@@ -73,6 +81,14 @@ struct BandGeom {
     int32_t band_n;        // output rows per weight tile of the vertical pass (all jobs of a launch share it)
     int32_t max_out;       // outputs of the widest strip (rows of the staged left/right + weight table)
     int32_t hw_pairs;      // staged horizontal weights (one duplicated pair per output and tap) of the largest strip
+    int32_t n_items;
+};
+
+// Launch-wide geometry of the banded8 (integer tensor-core) kernel.
+struct Band8Geom {
+    int32_t limbs;         // digits per weight: all jobs of a launch share it
+    int32_t max_out;
+    int32_t hw_pairs;
     int32_t n_items;
 };
 

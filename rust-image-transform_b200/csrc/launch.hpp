@@ -32,6 +32,16 @@ size_t banded_max_smem();                // the kernel's shared-memory budget (t
 cudaError_t launch_banded(int channels, bool convert, const DevJob* jobs, const WorkItem* items, const BandGeom& geom,
                           cudaStream_t stream);
 
+// Banded8 kernel (banded8.cu / banded8_conv.cu): downscales with the vertical pass as an integer product on the tensor
+// cores, the source bytes used as they are (no conversion pass).
+bool banded8_supported(int channels, int limbs);
+int banded8_max_src_bytes();
+int banded8_tile_rows();                 // intermediate rows per horizontal phase: row chunks are cut on multiples of it
+size_t banded8_smem_bytes(int channels, const Band8Geom& geom);
+size_t banded8_max_smem();
+cudaError_t launch_banded8(int channels, bool convert, const DevJob* jobs, const WorkItem* items, const Band8Geom& geom,
+                           cudaStream_t stream);
+
 // Tile kernel (tile.cu): output-stationary fused passes over shared-memory tiles.
 size_t tile_smem_bytes(const TileGeom& geom);
 cudaError_t launch_tile(int bytes_per_sample, const DevJob* jobs, const WorkItem* items, const TileGeom& geom,

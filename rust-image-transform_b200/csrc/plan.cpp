@@ -325,6 +325,68 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
             }
         }
     }
+    // 8-bit band form: integer weights in base-128 digits.
+    if (n_in >= n_out && n_in >= uint32_t(kBand8Chunk) && p.max_count <= 240) {
+        const int limbs = kBand8DefaultLimbs;
+        const uint32_t n_chunks = (n_in + kBand8Chunk - 1) / kBand8Chunk;
+        const uint32_t n_groups = (n_out + kBand8Group - 1) / kBand8Group;
+        std::vector<int32_t> gbase(n_chunks + 1, 0);
+        bool fits = true;
+        uint32_t o_lo = 0;
+        for (uint32_t c = 0; c < n_chunks && fits; ++c) {
+            const int32_t y0 = int32_t(c) * kBand8Chunk, y1 = y0 + kBand8Chunk;
+            while (o_lo < n_out && p.right[o_lo] <= y0) ++o_lo;
+            uint32_t o_hi = o_lo;
+            while (o_hi < n_out && p.left[o_hi] < y1) ++o_hi;
+            gbase[c] = int32_t(std::min(o_lo, n_out - 1) / kBand8Group);
+            if (o_hi > o_lo && int32_t(o_hi - 1) - gbase[c] * kBand8Group >= kBand8Window) fits = false;
+        }
+        gbase[n_chunks] = int32_t(n_groups);
+        float wmax = 0.0f;
+        for (auto& ws : ragged)
+            for (float wi : ws) wmax = std::max(wmax, std::fabs(wi));
+        if (fits && wmax > 0.0f) {
+            // digits: the top one in [-127, 127], the others in [-64, 63]  =>  |W| <= 127 * 128^(limbs-1) + 63 * (...)
+            const double top = 120.0 * std::pow(128.0, limbs - 1);  // (headroom for the sum correction)
+            int shift = int(std::floor(std::log2(top / double(wmax))));
+            shift = std::min(shift, 7 * limbs + 6);
+            p.band8.limbs = limbs;
+            p.band8.shift = shift;
+            p.band8.gbase = gbase;
+            const size_t tile = size_t(limbs) * kBand8Window * kBand8Chunk;
+            p.band8.tiles.assign(size_t(n_chunks) * tile, 0);
+            const double scale = std::ldexp(1.0, shift);
+            std::vector<int64_t> W;
+            for (uint32_t o = 0; o < n_out; ++o) {
+                const auto& ws = ragged[o];
+                W.resize(ws.size());
+                int64_t sum = 0;
+                size_t big = 0;
+                for (size_t i = 0; i < ws.size(); ++i) {
+                    W[i] = int64_t(std::llround(double(ws[i]) * scale));
+                    sum += W[i];
+                    if (std::fabs(ws[i]) > std::fabs(ws[big])) big = i;
+                }
+                W[big] += (int64_t(1) << shift) - sum;  // the weights sum to one: a flat area stays exactly flat
+                for (size_t i = 0; i < ws.size(); ++i) {
+                    const int32_t y = p.left[o] + int32_t(i);
+                    const uint32_t c = uint32_t(y) / kBand8Chunk;
+                    const int kk = y % kBand8Chunk;
+                    const int pos = int(o % kBand8Window);
+                    int8_t* t = p.band8.tiles.data() + size_t(c) * tile;
+                    int64_t v = W[i];
+                    for (int d = limbs - 1; d >= 0; --d) {   // least significant digit first
+                        int64_t digit;
+                        if (d > 0) { digit = ((v + 64) & 127) - 64; v = (v - digit) / 128; }
+                        else digit = v;                       // the top digit takes what is left (|digit| <= 127 by the choice of shift)
+                        const int n = d * kBand8Window + pos; // row of the tile: most significant digit first
+                        const size_t at = size_t(kk / 16) * (size_t(limbs) * kBand8Window * 16) + size_t(n / 8) * 128 + size_t(n % 8) * 16 + size_t(kk % 16);
+                        t[at] = int8_t(digit);
+                    }
+                }
+            }
+        }
+    }
     if (k >= 1 && k <= 8) {  // only the fused kernels use it; they handle ring_k <= 8
         p.ring_stride = (k + 1) & ~1;  // even: every ring row is a whole number of 16-byte loads
         p.ring_v.assign(size_t(n_in) * p.ring_stride * 2, 0.0f);

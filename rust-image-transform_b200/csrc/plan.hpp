@@ -19,6 +19,22 @@ enum Filter : int { kNearest = 0, kTriangle = 1, kCatmullRom = 2, kGaussian = 3,
 int target_dims(uint32_t ow, uint32_t oh, bool has_w, uint32_t w, bool has_h, uint32_t h,
                 uint32_t* tw, uint32_t* th);
 
+// Band form, 8-bit (csrc/banded8.cu: the vertical pass as an integer matrix product, tcgen05.mma kind::i8, the
+// source bytes used as they are).  Chunks of kBand8Chunk source indices (the K of one i8 MMA); chunk k touches at
+// most kBand8Window consecutive outputs starting at output 8 * band8_gbase[k] (groups of 8; band8_gbase[n_chunks]
+// = number of groups).  Every weight is the integer W = round(w * 2^band8_shift) (each output's weights are
+// nudged to sum to exactly 2^band8_shift), split into band8_limbs signed 8-bit digits, base 128, low digits in
+// [-64, 63].  band8_tiles: per chunk one K-major s8 operand tile of (band8_limbs * 32) rows x 32 indices in the
+// shared-memory layout the MMA reads; row = digit * 32 + (output mod 32), most significant digit first.
+// band8_limbs == 0: not applicable (upscale, a chunk window wider than 32 outputs, or too many taps).
+struct Band8 {
+    int limbs = 0, shift = 0;
+    std::vector<int32_t> gbase;   // [n_chunks + 1]
+    std::vector<int8_t> tiles;    // [n_chunks][limbs * 32 * 32]
+};
+constexpr int kBand8Chunk = 32, kBand8Group = 8, kBand8Window = 32;
+
+
 // One separable pass n_in -> n_out with a given filter.
 struct PassPlan {
     int filter = 0;
@@ -59,6 +75,7 @@ struct PassPlan {
     int band_n = 0;
     std::vector<int32_t> band_gbase;    // [n_chunks + 1]
     std::vector<uint16_t> band_tiles;   // [n_chunks][2][band_n * 16] f16 bit patterns
+    Band8 band8;                        // the 8-bit band form (see above)
 };
 
 constexpr int kBandChunk = 16;          // source indices per chunk (K of tcgen05.mma kind::f16)
@@ -73,6 +90,7 @@ uint16_t f32_to_f16_rn(float f);        // IEEE binary16, round to nearest even 
 float f16_to_f32(uint16_t h);
 
 std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n_out);
+constexpr int kBand8DefaultLimbs = 2;
 
 float filter_support(int filter);
 

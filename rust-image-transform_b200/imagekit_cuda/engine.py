@@ -73,6 +73,25 @@ def pass_band(filt: int, n_in: int, n_out: int):
     return n, gbase, t[:, 0], t[:, 1]
 
 
+def pass_band8(filt: int, n_in: int, n_out: int):
+    """(limbs, shift, gbase[n_chunks + 1], digits[n_chunks, limbs, 32 outputs, 32 indices]) of a downscale pass: the s8
+    weight tiles of the integer tensor-core vertical pass, un-laid-out; None if the pass has no such form."""
+    L = _lib.load()
+    limbs, shift = C.c_uint32(), C.c_uint32()
+    chunks = L.ikc_pass_band8(filt, n_in, n_out, C.byref(limbs), C.byref(shift), None, None, 0)
+    if chunks == 0:
+        return None
+    nl = limbs.value
+    gbase = np.zeros(chunks + 1, np.int32)
+    raw = np.zeros(chunks * nl * 32 * 32, np.int8)
+    got = L.ikc_pass_band8(filt, n_in, n_out, C.byref(limbs), C.byref(shift), gbase.ctypes.data_as(C.POINTER(C.c_int32)),
+                           raw.ctypes.data_as(C.POINTER(C.c_int8)), raw.size)
+    assert got == chunks
+    t = raw.reshape(chunks, 2, nl * 4, 8, 16)                      # [chunk][k / 16][n / 8][n % 8][k % 16]
+    t = t.transpose(0, 2, 3, 1, 4).reshape(chunks, nl, 32, 32)     # [chunk][digit][output mod 32][k]
+    return nl, shift.value, gbase, t
+
+
 def pass_info(filt: int, n_in: int, n_out: int) -> dict:
     """What the planner derived for one pass (ring size, uniform stretch, 2x-upscale frame): ikc_pass_info."""
     info = _lib.PassInfo()

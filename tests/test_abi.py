@@ -175,3 +175,47 @@ def test_upscale_pass_has_no_band_form(ik):
     from imagekit_cuda import engine
     assert engine.pass_band(4, 100, 200) is None
     assert engine.pass_band(4, 8, 4) is None      # fewer source indices than one chunk
+
+
+# ---- 8-bit band form: the integer weight tiles of the i8 tensor-core vertical pass (host logic) ----
+@pytest.mark.parametrize("filt,n_in,n_out", [(4, 2160, 1080), (4, 3024, 300), (4, 1080, 225), (4, 777, 388), (2, 500, 250),
+                                             (1, 640, 123), (3, 333, 100), (0, 100, 37), (4, 4032, 400), (4, 64, 32),
+                                             (4, 33, 1)])
+def test_band8_tiles_are_the_quantised_pass(ik, oracle, filt, n_in, n_out):
+    from imagekit_cuda import engine
+    band = engine.pass_band8(filt, n_in, n_out)
+    assert band is not None
+    limbs, shift, gbase, dig = band
+    chunks = dig.shape[0]
+    assert limbs == 2 and chunks == (n_in + 31) // 32 and gbase[-1] == (n_out + 7) // 8
+    assert np.all(np.diff(gbase[:-1]) >= 0)
+    assert dig[:, 1:].min() >= -64 and dig[:, 1:].max() <= 63          # low digits
+    left, count, w = oracle.pass_table(filt, n_in, n_out)
+    # integer weights rebuilt from the digits, accumulated where the tiles put them (ring position = output mod 32)
+    W = np.zeros((n_out + 64, chunks * 32), np.int64)
+    for c in range(chunks):
+        val = np.zeros((32, 32), np.int64)
+        for d in range(limbs):
+            val = val * 128 + dig[c, d].astype(np.int64)
+        for pos in range(32):
+            if not val[pos].any():
+                continue
+            o = 8 * gbase[c] + (pos - 8 * gbase[c]) % 32                # the window's output with this ring position
+            W[o, 32 * c:32 * c + 32] += val[pos]
+    assert not W[n_out:].any() and not W[:, n_in:].any()
+    scale = float(2 ** shift)
+    for o in range(n_out):
+        row = W[o]
+        nz = np.flatnonzero(row)
+        assert nz.size == 0 or (nz[0] >= left[o] and nz[-1] < left[o] + count[o])
+        assert row.sum() == 2 ** shift                                  # a flat area stays exactly flat
+        err = np.abs(row[left[o]:left[o] + count[o]] / scale - w[o, :count[o]].astype(np.float64))
+        assert err.max() <= (count[o] / 2 + 1) / scale                  # half an LSB, plus the sum correction on one tap
+    assert np.abs(W).max() <= 127 * 128 + 63
+
+
+def test_band8_needs_a_narrow_chunk_window(ik):
+    from imagekit_cuda import engine
+    assert engine.pass_band8(4, 100, 200) is None       # upscale
+    assert engine.pass_band8(4, 1080, 1080) is None     # 32 source rows touch more than 32 outputs
+    assert engine.pass_band8(4, 1000, 700) is None

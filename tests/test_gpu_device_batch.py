@@ -34,13 +34,13 @@ def test_prepared_batch_on_torch_stream(ctx, ik, oracle):
     batch.free()
 
 
-@pytest.mark.parametrize("mode", ["tc", "fp32"])
+@pytest.mark.parametrize("mode", ["tc", "f16", "fp32"])
 def test_prepared_batch_mixes_every_kernel(ctx, ik, oracle, mode):
     """One prepared batch whose jobs need the downscale kernel (banded tensor-core kernel, or the CUDA-core ring
     kernel in FAST_FP32 mode; plain, uniform, converting), the 2x upscale kernel, the tile kernel and the generic
     kernels: one launch per kernel variant, every job within +-1."""
     import torch
-    ctx.set_mode(ik.MODE_FAST_FP32 if mode == "fp32" else ik.MODE_FAST)
+    ctx.set_mode({"tc": ik.MODE_FAST, "f16": ik.MODE_FAST_F16, "fp32": ik.MODE_FAST_FP32}[mode])
     dev = torch.device("cuda:0")
     cases = [  # (h, w, c, dw, dh, filter, out_channels)
         (480, 640, 3, 200, 150, 4, 3), (600, 800, 4, 400, 300, 4, 4), (600, 800, 4, 400, 300, 4, 3),
@@ -60,9 +60,9 @@ def test_prepared_batch_mixes_every_kernel(ctx, ik, oracle, mode):
     assert all(j.status == 0 for j in batch.jobs), [j.status for j in batch.jobs]
     desc = batch.describe()
     ctx.set_mode(ik.MODE_FAST)
-    for name in ("fused_ring_kernel" if mode == "fp32" else "banded_kernel", "up2_kernel", "tile_kernel"):
+    for name in ({"tc": "banded8_kernel", "f16": "banded_kernel", "fp32": "fused_ring_kernel"}[mode], "up2_kernel", "tile_kernel"):
         assert name in desc, desc
-    assert ("banded_kernel" in desc) == (mode == "tc")
+    assert ("banded8_kernel" in desc) == (mode == "tc") and ("fused_ring_kernel" in desc) == (mode == "fp32")
     stream = torch.cuda.Stream()
     batch.launch(stream.cuda_stream)
     stream.synchronize()

@@ -11,14 +11,15 @@ pytestmark = pytest.mark.gpu
 TOL = 1  # max |delta| per u8 channel, BASELINE.json north_star
 
 
-def _fast(ctx, ik, fp32=False):
-    ctx.set_mode(ik.MODE_FAST_FP32 if fp32 else ik.MODE_FAST)
+def _fast(ctx, ik, mode="tc"):
+    ctx.set_mode({"tc": ik.MODE_FAST, "f16": ik.MODE_FAST_F16, "fp32": ik.MODE_FAST_FP32}[mode])
 
 
-FAST_MODES = ["tc", "fp32"]  # downscales: banded tensor-core kernel / CUDA-core ring kernel
+# downscales: integer tensor-core kernel (banded8) / f16 tensor-core kernel (banded) / CUDA-core ring kernel
+FAST_MODES = ["tc", "f16", "fp32"]
 
 
-def _check_fast(got, want, label, max_off=0.002):
+def _check_fast(got, want, label, max_off=0.016):
     hist = delta_histogram(got, want)
     assert max(abs(k) for k in hist) <= TOL, (label, hist)
     off = sum(v for k, v in hist.items() if k != 0) / got.size
@@ -75,14 +76,16 @@ def test_fused_kernel_parity(ctx, ik, oracle, shape, content, mode):
     if content != "noise" and h * w > 2_000_000:
         pytest.skip("large shapes run on noise only")
     src = {"noise": splitmix_noise, "edges": checker, "photo": photo_like}[content]((h, w, c))
-    _fast(ctx, ik, mode == "fp32")
+    _fast(ctx, ik, mode)
     before = ctx.kernel_launches
     got = ctx.resize(src, dw, dh, ik.FILTER_LANCZOS3)
     _fast(ctx, ik)
     assert ctx.kernel_launches - before == 1, "expected the single-launch fused kernel"
     want = oracle.resize_exact(src, dw, dh, oracle.LANCZOS3)
     # checkerboards on integer ratios put many sums exactly on x.5, where FMA contraction decides the tie
-    _check_fast(got, want, (shape, content), max_off={"noise": 0.002, "photo": 0.03, "edges": 0.06}[content])
+    # (the integer kernel's 15-bit weights move more samples across a .5 boundary than 22+-bit weights do)
+    scale = 8 if mode == "tc" else 1
+    _check_fast(got, want, (shape, content), max_off=scale * {"noise": 0.002, "photo": 0.03, "edges": 0.06}[content])
 
 
 def test_fused_gaussian_downscale(ctx, ik, oracle):
@@ -215,13 +218,13 @@ CONVERT_CASES = [  # (h, w, c, dw, dh, filter, out_channels): ring kernel, tile 
 
 
 @pytest.mark.parametrize("case", CONVERT_CASES)
-@pytest.mark.parametrize("mode", ["fast", "fast_fp32", "exact"])
+@pytest.mark.parametrize("mode", ["fast", "fast_f16", "fast_fp32", "exact"])
 def test_resize_with_fused_channel_conversion(ctx, ik, oracle, case, mode):
     h, w, c, dw, dh, filt, co = case
     if mode == "exact" and h * w > 2_000_000:
         pytest.skip("large shapes run in fast mode only")
     src = splitmix_noise((h, w, c), image_id=co)
-    ctx.set_mode({"exact": ik.MODE_EXACT, "fast": ik.MODE_FAST, "fast_fp32": ik.MODE_FAST_FP32}[mode])
+    ctx.set_mode({"exact": ik.MODE_EXACT, "fast": ik.MODE_FAST, "fast_f16": ik.MODE_FAST_F16, "fast_fp32": ik.MODE_FAST_FP32}[mode])
     got = ctx.resize(src, dw, dh, filt, out_channels=co)
     resized = oracle.resize_exact(src, dw, dh, filt)
     want = oracle.to_rgb8(resized) if co == 3 else oracle.to_rgba8(resized)
@@ -229,7 +232,7 @@ def test_resize_with_fused_channel_conversion(ctx, ik, oracle, case, mode):
     if mode == "exact":
         assert np.array_equal(got, want), delta_histogram(got, want)
     else:
-        _check_fast(got, want, (case, mode), max_off=0.002)
+        _check_fast(got, want, (case, mode), max_off=0.016 if mode == "fast" else 0.002)
     ctx.set_mode(ik.MODE_FAST)
 
 
@@ -290,7 +293,7 @@ LUMA_RING_CASES = [  # (h, w, c, dw, dh, out_channels or None)
 def test_luma_downscales_on_the_ring_kernel(ctx, ik, oracle, case, mode):
     h, w, c, dw, dh, co = case
     src = splitmix_noise((h, w, c), image_id=c)
-    _fast(ctx, ik, mode == "fp32")
+    _fast(ctx, ik, mode)
     before = ctx.kernel_launches
     got = ctx.resize(src, dw, dh, ik.FILTER_LANCZOS3, out_channels=co)
     _fast(ctx, ik)
@@ -299,7 +302,7 @@ def test_luma_downscales_on_the_ring_kernel(ctx, ik, oracle, case, mode):
     if co == 3: want = oracle.to_rgb8(want)
     if co == 4: want = oracle.to_rgba8(want)
     if want.ndim == 2: want = want[:, :, None]
-    _check_fast(got.reshape(want.shape), want, case, max_off=0.002)
+    _check_fast(got.reshape(want.shape), want, case, max_off=0.016 if mode == "tc" else 0.002)
 
 
 def test_randomised_parity_sweep(ctx, ik, oracle):
@@ -334,7 +337,7 @@ def test_randomised_parity_sweep(ctx, ik, oracle):
         co = int(rng.choice([3, 4])) if rng.random() < 0.25 else None
         exact = rng.random() < 0.15
         src = (checker if rng.random() < 0.2 else splitmix_noise)((h, w, c))
-        ctx.set_mode(ik.MODE_EXACT if exact else (ik.MODE_FAST if rng.random() < 0.7 else ik.MODE_FAST_FP32))
+        ctx.set_mode(ik.MODE_EXACT if exact else [ik.MODE_FAST, ik.MODE_FAST_F16, ik.MODE_FAST_FP32][int(rng.choice([0, 0, 1, 2]))])
         got = ctx.resize(src, dw, dh, filt, out_channels=co)
         want = oracle.resize_exact(src, dw, dh, filt)
         if co == 3:
