@@ -10,7 +10,7 @@
 //   B (N x K) = the weights of the <= 32 output rows those source rows can touch, as integers
 //               W = round(w * 2^S) split into L signed base-128 digits (host-built tiles, plan.hpp: Band8);
 //               N = L * 32: one MMA per block and chunk computes every digit's partial sums.
-//   D (M x N) = s32 accumulators in TMEM: lane = byte column, column = digit * 32 + (output row mod 32).  The 32 rows are
+//   D (M x N) = s32 accumulators in TMEM: lane = byte column, column = (output row mod 32) * L + digit.  The 32 rows are
 //               a ring of 4 groups of 8; a finished group is read with tcgen05.ld, its digits recombined in f32
 //               ((d1 * 128 + d0) -- exact products, one rounding), written to the shared-memory intermediate tile,
 //               zeroed and handed back.  The integer sums are exact, so the vertical pass is deterministic
@@ -70,16 +70,24 @@ __device__ __forceinline__ void mma_i8_acc(uint32_t d_tmem, uint64_t a_desc, uin
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(1u)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t addr, int (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+// N consecutive TMEM columns of this thread's lane in one instruction.
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t addr, int (&v)[N]) {
+    static_assert(N == 16, "one group of one block: 8 outputs x 2 digits");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(addr));
+}
+template <int N>
+__device__ __forceinline__ void tmem_zero_n(uint32_t addr) {
+    static_assert(N == 16, "one group of one block (L = 2)");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(addr), "r"(0u)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_zero8(uint32_t addr) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
 }
-// s32 -> f32, exact for |v| < 2^22, without the quarter-rate I2F: add the integer to the bits of 1.5 * 2^23, subtract it as a float.
-__device__ __forceinline__ float int_to_float_small(int v) { return __int_as_float(v + 0x4B400000) - 12582912.0f; }
 
 constexpr bool k8Conv = IKC_BANDED8_CONV != 0;
 
@@ -254,20 +262,20 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
         for (int t = 0; t < 12; ++t) uw[t] = uni2 ? hw[(os - ox0) * 12 + t] : make_float2(0.0f, 0.0f);
         float* const tcol = tmp + q * 32 + lane;
 
+        // Groups are drained one by one, as soon as they are final: the ring has no spare slot, the next chunk's MMAs wait
+        // for it.  The horizontal phase runs per intermediate tile = an even group and its successor.
         for (int g = g0; g < g_end; ++g) {
             const int slot = g & (k8Ring - 1);
             mbar_wait(t_full + slot, ((g - g0) / k8Ring) & 1);
             tc_fence_after();
             const int tile_row0 = (g >> 1) * k8TileRows;          // output row of the intermediate tile's first row
             const bool live = tile_row0 < oy1 && tile_row0 + k8TileRows > oy0;
-            if (live) {  // TMEM -> registers (digits recombined) -> intermediate tile rows (g & 1) * 8 ..
-                int v[k8Blocks][L][8];
+            const uint32_t gcol = uint32_t(slot * k8Group * L);   // the group's first column within a block
+            if (live) {  // TMEM -> registers (digits recombined: exact integer, one conversion) -> tile rows (g & 1) * 8 ..
+                int v[k8Blocks][8 * L];
 #pragma unroll
                 for (int b = 0; b < k8Blocks; ++b)
-                    if (b < nblk) {
-#pragma unroll
-                        for (int d = 0; d < L; ++d) tmem_ld8(tlane + uint32_t(b * kN + d * k8Window + slot * k8Group), v[b][d]);
-                    }
+                    if (b < nblk) tmem_ld_n<8 * L>(tlane + uint32_t(b * kN) + gcol, v[b]);
                 tmem_ld_wait();
                 float* const trow = tcol + (g & 1) * k8Group * kTmpPitch;
 #pragma unroll
@@ -275,20 +283,17 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                     if (b < nblk) {
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
-                            float t = int_to_float_small(v[b][0][r]);                       // most significant digit first
+                            int t = v[b][r * L];                                        // most significant digit first
 #pragma unroll
-                            for (int d = 1; d < L; ++d) t = fmaf(t, 128.0f, int_to_float_small(v[b][d][r]));
-                            trow[r * kTmpPitch + b * 128] = t;
+                            for (int d = 1; d < L; ++d) t = t * 128 + v[b][r * L + d];
+                            trow[r * kTmpPitch + b * 128] = __int2float_rn(t);
                         }
                     }
                 }
             }
 #pragma unroll
             for (int b = 0; b < k8Blocks; ++b)
-                if (b < nblk) {
-#pragma unroll
-                    for (int d = 0; d < L; ++d) tmem_zero8(tlane + uint32_t(b * kN + d * k8Window + slot * k8Group));
-                }
+                if (b < nblk) tmem_zero_n<8 * L>(tlane + uint32_t(b * kN) + gcol);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();

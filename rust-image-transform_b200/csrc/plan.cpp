@@ -379,7 +379,7 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
                         int64_t digit;
                         if (d > 0) { digit = ((v + 64) & 127) - 64; v = (v - digit) / 128; }
                         else digit = v;                       // the top digit takes what is left (|digit| <= 127 by the choice of shift)
-                        const int n = d * kBand8Window + pos; // row of the tile: most significant digit first
+                        const int n = pos * limbs + d;         // row of the tile: an output's digits are adjacent, most significant first
                         const size_t at = size_t(kk / 16) * (size_t(limbs) * kBand8Window * 16) + size_t(n / 8) * 128 + size_t(n % 8) * 16 + size_t(kk % 16);
                         t[at] = int8_t(digit);
                     }

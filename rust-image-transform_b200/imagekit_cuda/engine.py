@@ -88,7 +88,8 @@ def pass_band8(filt: int, n_in: int, n_out: int):
                            raw.ctypes.data_as(C.POINTER(C.c_int8)), raw.size)
     assert got == chunks
     t = raw.reshape(chunks, 2, nl * 4, 8, 16)                      # [chunk][k / 16][n / 8][n % 8][k % 16]
-    t = t.transpose(0, 2, 3, 1, 4).reshape(chunks, nl, 32, 32)     # [chunk][digit][output mod 32][k]
+    t = t.transpose(0, 2, 3, 1, 4).reshape(chunks, 32, nl, 32)     # [chunk][output mod 32][digit][k]
+    t = t.transpose(0, 2, 1, 3)                                    # [chunk][digit][output mod 32][k]
     return nl, shift.value, gbase, t
 
 
