@@ -18,8 +18,14 @@
 //
 // The HORIZONTAL pass is banded.cu's: CUDA cores, output-stationary, lane = intermediate row, half warp = x segment.
 //
-// Warp roles (256 threads, 2 CTAs per SM, 256 TMEM columns each): warp 0 producer (TMA), warp 1 MMA issuer,
-// warps 2-3 idle (they only give their registers to the epilogue), warps 4-7 epilogue + horizontal pass.
+// One CTA per SM (512 threads, all 512 TMEM columns, ~200 KB of shared memory):
+//   warp 0      producer (TMA): 5-stage ring of source boxes + ring of weight tiles
+//   warp 1      MMA issuer (one lane); warps 2-3 idle (their registers go to the epilogue warpgroups)
+//   warps 4-15  three epilogue TEAMS of four warps (TMEM lane quarter = warp % 4).  Team t owns every third
+//               intermediate tile (16 output rows = 2 ring groups): it drains the tile's groups from TMEM as they become
+//               final (recombines the digits, writes its own shared-memory tile, zeroes and returns the ring slots) and
+//               then runs the tile's horizontal pass, while the other teams do the same for the next tiles and the MMAs
+//               run up to two tiles ahead: the accumulator ring holds 8 groups (64 output rows), twice a chunk's window.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -41,16 +47,18 @@ constexpr int k8StripBytes = k8Blocks * 128;
 constexpr int k8Chunk = kBand8Chunk;                 // source rows per stage = K of one i8 MMA
 constexpr int k8BlockBytes = 128 * k8Chunk;          // one operand tile: 32 rows x 128 bytes
 constexpr int k8UStageBytes = k8Blocks * k8BlockBytes;
-constexpr int k8UStages = 3, k8BStages = 4;
-constexpr int k8Ring = 4;                            // accumulator groups in TMEM: the ring IS the chunk window
+constexpr int k8UStages = 5, k8BStages = 4;
+constexpr int k8Ring = 8;                            // accumulator groups in TMEM: twice the chunk window
+constexpr int k8WinGroups = kBand8Window / kBand8Group;  // groups one chunk's MMAs touch
+constexpr int k8Teams = 3;                           // epilogue teams (4 warps each)
 constexpr int k8Group = kBand8Group;                 // output rows per group
 constexpr int k8Window = kBand8Window;               // output rows in the ring
 constexpr int k8TileRows = 16;                       // intermediate rows per horizontal phase (two groups)
-constexpr int k8Threads = 256;
+constexpr int k8Threads = 128 + k8Teams * 128;
 constexpr int k8Segs = 8;
 constexpr int k8HeaderBytes = 1024;                  // mbarriers; the operand stages behind it stay 1024-byte aligned (swizzle atoms)
-constexpr size_t k8MaxSmem = 113 * 1024;
-constexpr int k8RegsIo = 40, k8RegsEpi = 216;        // 128 x 40 + 128 x 216 = 256 x 128
+constexpr size_t k8MaxSmem = 226 * 1024;
+constexpr int k8RegsIo = 32, k8RegsEpi = 160;        // 128 x 32 + 384 x 160 = 512 x 128
 constexpr int k8TmpPad = 64;
 
 __host__ __device__ constexpr int tmp8_pitch_floats(int channels) {
@@ -89,20 +97,25 @@ __device__ __forceinline__ void tmem_zero8(uint32_t addr) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
 }
 
+// Barrier over one epilogue team (named barriers 1 .. k8Teams).
+__device__ __forceinline__ void team_barrier(int team) { asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory"); }
+
 constexpr bool k8Conv = IKC_BANDED8_CONV != 0;
 
 }  // namespace
 
-// Shared memory: [mbarriers (1 KB) | operand ring: 3 stages x 4 blocks x (32 rows x 128 B, swizzled) | weight-tile ring
+// Shared memory: [mbarriers (1 KB) | operand ring: 5 stages x 4 blocks x (32 rows x 128 B, swizzled) | weight-tile ring
 //                (4 x L * 1 KB) | horizontal weights of the strip | (left, right) of the strip's outputs |
-//                intermediate tile: 16 rows x pitch floats]
+//                one intermediate tile per team: 16 rows x pitch floats]
 template <int C, int L, bool CONV>
-__global__ void __launch_bounds__(k8Threads, 2)
+__global__ void __launch_bounds__(k8Threads, 1)
 banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, const Band8Geom geom) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int kTmpPitch = tmp8_pitch_floats(C);
-    constexpr int kN = L * k8Window;                // MMA N = TMEM columns per block
-    constexpr int kTmemCols = k8Blocks * kN;        // 256 for L = 2
+    constexpr int kN = L * k8Window;                // MMA N: the columns of one chunk window
+    constexpr int kBlockCols = L * k8Ring * k8Group; // TMEM columns per block: the ring
+    constexpr int kTmemCols = k8Blocks * kBlockCols; // 512 for L = 2
+    constexpr int kTileFloats = k8TileRows * kTmpPitch + k8TmpPad;
     constexpr uint32_t kBTile = uint32_t(kN) * k8Chunk;  // bytes of one chunk's weight tile
 
     uint64_t* const bars = reinterpret_cast<uint64_t*>(smem);
@@ -111,13 +124,13 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
     uint64_t* const b_full = u_empty + k8UStages;    // [k8BStages]
     uint64_t* const b_empty = b_full + k8BStages;    // [k8BStages]
     uint64_t* const t_full = b_empty + k8BStages;    // [k8Ring] every MMA into the group has completed
-    uint64_t* const t_empty = t_full + k8Ring;       // [k8Ring] the 4 epilogue warps have drained and zeroed the group
+    uint64_t* const t_empty = t_full + k8Ring;       // [k8Ring] the 4 warps of a team have drained and zeroed the group
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
     uint8_t* const ustage = smem + k8HeaderBytes;
     uint8_t* const bstage = ustage + k8UStages * k8UStageBytes;
     float2* const hw = reinterpret_cast<float2*>(bstage + k8BStages * kBTile);
     int2* const hlr = reinterpret_cast<int2*>(hw + ((geom.hw_pairs + 1) & ~1));
-    float* const tmp = reinterpret_cast<float*>(hlr + ((geom.max_out + 1) & ~1));
+    float* const tmp_all = reinterpret_cast<float*>(hlr + ((geom.max_out + 1) & ~1));  // k8Teams tiles
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -144,7 +157,7 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
     const int k0 = y_first / k8Chunk, k1 = (y_last - 1) / k8Chunk;
     const int nchunks = k1 - k0 + 1;
     const int g0 = __ldg(gbase + k0);                // first group (of 8 outputs) any MMA of this item touches
-    const int g_end = __ldg(gbase + k1) + k8Ring;    // one past the last
+    const int g_end = __ldg(gbase + k1) + k8WinGroups;  // one past the last
 
     if (tid == 0) {
         if (smem_addr(smem) & 1023u) __trap();  // the swizzled operand tiles need 1024-byte aligned shared memory
@@ -206,13 +219,12 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
             const uint32_t a_lo0 = ((smem_addr(ustage) >> 4) & 0x3fffu) | ((1024u >> 4) << 16);
             const uint32_t b_lo0 = ((smem_addr(bstage) >> 4) & 0x3fffu) | (((uint32_t(kN) * 16u) >> 4) << 16);
             constexpr uint32_t kBDescHi = (128u >> 4) | (1u << 14);
-            const uint32_t idesc = instr_desc_i8(uint32_t(kN));
             int gb_next = g0;
             for (int i = 0; i < nchunks; ++i) {
                 const int k = k0 + i;
                 const int gb = gb_next;
                 gb_next = (i + 1 < nchunks) ? __ldg(gbase + k + 1) : 0;
-                while (acquired < gb + k8Ring) {  // ring slot = absolute group & 3, use count = how often the item reached it
+                while (acquired < gb + k8WinGroups) {  // ring slot = absolute group & 7, use count = how often the item reached it
                     mbar_wait(t_empty + (acquired & (k8Ring - 1)), ((acquired - g0) / k8Ring) & 1);
                     ++acquired;
                 }
@@ -221,11 +233,19 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                 mbar_wait(b_full + sb, (i / k8BStages) & 1);
                 tc_fence_after();
                 const uint32_t a_lo = a_lo0 + uint32_t(su) * (k8UStageBytes >> 4);
-                const uint64_t b_desc = make_u64(b_lo0 + uint32_t(sb) * (kBTile >> 4), kBDescHi);
+                const uint32_t b_lo = b_lo0 + uint32_t(sb) * (kBTile >> 4);
+                const int s0 = gb & (k8Ring - 1);
+                const uint32_t n1 = uint32_t(min(k8WinGroups, k8Ring - s0) * k8Group * L), n2 = uint32_t(kN) - n1;  // n2 > 0: the window wraps
+                const uint32_t id1 = instr_desc_i8(n1), id2 = instr_desc_i8(n2);
+                const uint32_t c1 = tmem + uint32_t(s0 * k8Group * L);
 #pragma unroll
-                for (int b = 0; b < k8Blocks; ++b)
-                    if (b < nblk)
-                        mma_i8_acc(tmem + uint32_t(b * kN), make_u64(a_lo + uint32_t(b) * (k8BlockBytes >> 4), a8_desc_hi()), b_desc, idesc);
+                for (int b = 0; b < k8Blocks; ++b) {
+                    if (b < nblk) {
+                        const uint64_t a_desc = make_u64(a_lo + uint32_t(b) * (k8BlockBytes >> 4), a8_desc_hi());
+                        mma_i8_acc(c1 + uint32_t(b * kBlockCols), a_desc, make_u64(b_lo, kBDescHi), id1);
+                        if (n2) mma_i8_acc(tmem + uint32_t(b * kBlockCols), a_desc, make_u64(b_lo + (n1 >> 3) * (128u >> 4), kBDescHi), id2);
+                    }
+                }
                 tc_commit(u_empty + su);
                 tc_commit(b_empty + sb);
                 const int final_below = (i + 1 < nchunks) ? gb_next : acquired;  // groups below it get no more contributions
@@ -239,13 +259,17 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(k8RegsEpi));
         // ------------------------------------------------------------------------------ epilogue + horizontal pass
         const int q = warp & 3;                                  // TMEM lane quarter this warp may touch
+        const int team = (warp >> 2) - 1;                        // 0 .. k8Teams - 1
         const uint32_t tlane = tmem + (uint32_t(q * 32) << 16);
-        for (int c = 0; c < kTmemCols; c += 8) tmem_zero8(tlane + uint32_t(c));
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0)
-            for (int s = 0; s < k8Ring; ++s) mbar_arrive(t_empty + s);
+        if (team == 0) {  // hand every ring slot to the MMA warp, zeroed
+            for (int c = 0; c < kTmemCols; c += 8) tmem_zero8(tlane + uint32_t(c));
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                for (int s = 0; s < k8Ring; ++s) mbar_arrive(t_empty + s);
+        }
+        float* const tmp = tmp_all + team * kTileFloats;         // this team's intermediate tile
 
         const int hrow = lane & 15;
         const int seg = 2 * q + (lane >> 4);
@@ -257,14 +281,12 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
         const size_t dst_pitch = J->dst_pitch;
         const float* const my_row = tmp + hrow * kTmpPitch - b0;   // indexed by source byte column x * C + c
         const bool uni2 = os < oe && J->h.uni_step == 2 && hstride == 12 && os >= J->h.uni_lo && oe <= J->h.uni_hi;
-        float2 uw[12];
-#pragma unroll
-        for (int t = 0; t < 12; ++t) uw[t] = uni2 ? hw[(os - ox0) * 12 + t] : make_float2(0.0f, 0.0f);
         float* const tcol = tmp + q * 32 + lane;
 
-        // Groups are drained one by one, as soon as they are final: the ring has no spare slot, the next chunk's MMAs wait
-        // for it.  The horizontal phase runs per intermediate tile = an even group and its successor.
-        for (int g = g0; g < g_end; ++g) {
+        // This team's tiles: every k8Teams-th pair (even group, its successor).  Groups are drained one by one, as soon as
+        // they are final, so that their ring slots go back to the MMAs early.
+        for (int gt = (g0 & ~1) + 2 * team; gt < g_end; gt += 2 * k8Teams)
+        for (int g = max(gt, g0); g < min(gt + 2, g_end); ++g) {
             const int slot = g & (k8Ring - 1);
             mbar_wait(t_full + slot, ((g - g0) / k8Ring) & 1);
             tc_fence_after();
@@ -275,7 +297,7 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                 int v[k8Blocks][8 * L];
 #pragma unroll
                 for (int b = 0; b < k8Blocks; ++b)
-                    if (b < nblk) tmem_ld_n<8 * L>(tlane + uint32_t(b * kN) + gcol, v[b]);
+                    if (b < nblk) tmem_ld_n<8 * L>(tlane + uint32_t(b * kBlockCols) + gcol, v[b]);
                 tmem_ld_wait();
                 float* const trow = tcol + (g & 1) * k8Group * kTmpPitch;
 #pragma unroll
@@ -293,13 +315,13 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
             }
 #pragma unroll
             for (int b = 0; b < k8Blocks; ++b)
-                if (b < nblk) tmem_zero_n<8 * L>(tlane + uint32_t(b * kN) + gcol);
+                if (b < nblk) tmem_zero_n<8 * L>(tlane + uint32_t(b * kBlockCols) + gcol);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty + slot);
             if (!live || (!(g & 1) && g + 1 < g_end)) continue;  // the tile's second group is still to come
-            epi_barrier();  // the whole tile is in shared memory
+            team_barrier(team);  // the whole tile is in shared memory
 
             const int orow = tile_row0 + hrow;
             const bool row_live = orow >= oy0 && orow < oy1;
@@ -309,32 +331,45 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                     // Blocks of 8 outputs as straight-line code: the 26 pixels their windows span are loaded at once
                     // (output j of the block reads pixels 2j .. 2j + 11).  Reads past the segment's last window stay
                     // inside the tile's padding and are never stored.
+                    float2 uw[12];  // the stretch's 12 tap weights (duplicated pairs); re-read per tile: they are not worth 24 live registers
+#pragma unroll
+                    for (int t = 0; t < 12; ++t) uw[t] = hw[(os - ox0) * 12 + t];
                     for (int o = os; o < oe; o += 8) {
                         const float* px = my_row + hlr[o - ox0].x * C;
-                        float4 p[26];
-#pragma unroll
-                        for (int t = 0; t < 26; ++t) p[t] = load_px<C>(px + t * C);
                         uint32_t word[8];
+                        // two halves of 4 outputs: 18 pixels live at a time (output j of a half reads its pixels 2j .. 2j + 11)
+                        float4 p[18];
 #pragma unroll
-                        for (int j = 0; j < 8; j += 2) {  // two outputs at a time: eight accumulation chains in flight
-                            float2 a01 = make_float2(kRoundBias, kRoundBias), a23 = a01, c01 = make_float2(0.0f, 0.0f), c23 = c01;
-                            float2 d01 = a01, d23 = a01, e01 = c01, e23 = c01;
+                        for (int t = 0; t < 18; ++t) p[t] = load_px<C>(px + t * C);
 #pragma unroll
-                            for (int t = 0; t < 12; t += 2) {
-                                const float4 x0 = p[2 * j + t], x1 = p[2 * j + t + 1], y0 = p[2 * j + 2 + t], y1 = p[2 * j + 3 + t];
-                                a01 = __ffma2_rn(uw[t], make_float2(x0.x, x0.y), a01);
-                                a23 = __ffma2_rn(uw[t], make_float2(x0.z, x0.w), a23);
-                                d01 = __ffma2_rn(uw[t], make_float2(y0.x, y0.y), d01);
-                                d23 = __ffma2_rn(uw[t], make_float2(y0.z, y0.w), d23);
-                                c01 = __ffma2_rn(uw[t + 1], make_float2(x1.x, x1.y), c01);
-                                c23 = __ffma2_rn(uw[t + 1], make_float2(x1.z, x1.w), c23);
-                                e01 = __ffma2_rn(uw[t + 1], make_float2(y1.x, y1.y), e01);
-                                e23 = __ffma2_rn(uw[t + 1], make_float2(y1.z, y1.w), e23);
+                        for (int half = 0; half < 2; ++half) {
+                            if (half == 1) {
+#pragma unroll
+                                for (int t = 0; t < 10; ++t) p[t] = p[t + 8];          // (register renaming, no moves once unrolled)
+#pragma unroll
+                                for (int t = 10; t < 18; ++t) p[t] = load_px<C>(px + (t + 8) * C);
                             }
-                            a01 = __fadd2_rn(a01, c01); a23 = __fadd2_rn(a23, c23);
-                            d01 = __fadd2_rn(d01, e01); d23 = __fadd2_rn(d23, e23);
-                            word[j] = pack_pixel(make_float4(a01.x, a01.y, a23.x, a23.y));
-                            word[j + 1] = pack_pixel(make_float4(d01.x, d01.y, d23.x, d23.y));
+#pragma unroll
+                            for (int j = 0; j < 4; j += 2) {  // two outputs at a time: eight accumulation chains in flight
+                                float2 a01 = make_float2(kRoundBias, kRoundBias), a23 = a01, c01 = make_float2(0.0f, 0.0f), c23 = c01;
+                                float2 d01 = a01, d23 = a01, e01 = c01, e23 = c01;
+#pragma unroll
+                                for (int t = 0; t < 12; t += 2) {
+                                    const float4 x0 = p[2 * j + t], x1 = p[2 * j + t + 1], y0 = p[2 * j + 2 + t], y1 = p[2 * j + 3 + t];
+                                    a01 = __ffma2_rn(uw[t], make_float2(x0.x, x0.y), a01);
+                                    a23 = __ffma2_rn(uw[t], make_float2(x0.z, x0.w), a23);
+                                    d01 = __ffma2_rn(uw[t], make_float2(y0.x, y0.y), d01);
+                                    d23 = __ffma2_rn(uw[t], make_float2(y0.z, y0.w), d23);
+                                    c01 = __ffma2_rn(uw[t + 1], make_float2(x1.x, x1.y), c01);
+                                    c23 = __ffma2_rn(uw[t + 1], make_float2(x1.z, x1.w), c23);
+                                    e01 = __ffma2_rn(uw[t + 1], make_float2(y1.x, y1.y), e01);
+                                    e23 = __ffma2_rn(uw[t + 1], make_float2(y1.z, y1.w), e23);
+                                }
+                                a01 = __fadd2_rn(a01, c01); a23 = __fadd2_rn(a23, c23);
+                                d01 = __fadd2_rn(d01, e01); d23 = __fadd2_rn(d23, e23);
+                                word[4 * half + j] = pack_pixel(make_float4(a01.x, a01.y, a23.x, a23.y));
+                                word[4 * half + j + 1] = pack_pixel(make_float4(d01.x, d01.y, d23.x, d23.y));
+                            }
                         }
                         if (row_live) {
                             uint8_t* const d = my_dst + size_t(o) * CO;
@@ -376,7 +411,7 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                 }
             }
             __syncwarp();
-            epi_barrier();  // the tile may be overwritten
+            team_barrier(team);  // the tile may be overwritten
         }
     }
 
@@ -396,7 +431,7 @@ size_t banded8_smem_bytes(int channels, const Band8Geom& g) {
     const size_t tmp_pitch = size_t(tmp8_pitch_floats(channels));
     return size_t(k8HeaderBytes) + size_t(k8UStages) * k8UStageBytes + size_t(k8BStages) * size_t(g.limbs) * k8Window * k8Chunk +
            size_t((g.hw_pairs + 1) & ~1) * sizeof(float2) + size_t((g.max_out + 1) & ~1) * sizeof(int2) +
-           (size_t(k8TileRows) * tmp_pitch + k8TmpPad) * sizeof(float);
+           size_t(k8Teams) * (size_t(k8TileRows) * tmp_pitch + k8TmpPad) * sizeof(float);
 }
 size_t banded8_max_smem() { return k8MaxSmem; }
 int banded8_max_src_bytes() { return k8StripBytes; }

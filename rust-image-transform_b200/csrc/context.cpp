@@ -596,8 +596,8 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
     // no chunk so short that the vertical halo (taps - ratio rows per chunk) dominates.
     size_t total_strips = 0;
     for (auto& c : cands) total_strips += c.strips.size();
-    const size_t slots = size_t(dev.sm_count()) * 2;
     for (auto& c : cands) {
+        const size_t slots = size_t(dev.sm_count()) * (c.band8 ? 1 : 2);  // the banded8 kernel runs one CTA per SM
         const DevJob& j = lp.jobs[c.job];
         const int group_rows = c.band8 ? banded8_tile_rows() : c.band_n ? banded_group_rows() : fused_group_rows();
         // Pick the chunk count that minimises (tail-wave waste) x (vertical halo recompute), assuming

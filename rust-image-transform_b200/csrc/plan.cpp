@@ -372,7 +372,7 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
                     const int32_t y = p.left[o] + int32_t(i);
                     const uint32_t c = uint32_t(y) / kBand8Chunk;
                     const int kk = y % kBand8Chunk;
-                    const int pos = int(o % kBand8Window);
+                    const int pos = int(o) - gbase[c] * kBand8Group;  // position in the chunk's window
                     int8_t* t = p.band8.tiles.data() + size_t(c) * tile;
                     int64_t v = W[i];
                     for (int d = limbs - 1; d >= 0; --d) {   // least significant digit first

@@ -25,7 +25,8 @@ int target_dims(uint32_t ow, uint32_t oh, bool has_w, uint32_t w, bool has_h, ui
 // = number of groups).  Every weight is the integer W = round(w * 2^band8_shift) (each output's weights are
 // nudged to sum to exactly 2^band8_shift), split into band8_limbs signed 8-bit digits, base 128, low digits in
 // [-64, 63].  band8_tiles: per chunk one K-major s8 operand tile of (band8_limbs * 32) rows x 32 indices in the
-// shared-memory layout the MMA reads; row = (output mod 32) * band8_limbs + digit, most significant digit first.
+// shared-memory layout the MMA reads; row = (output - 8 * band8_gbase[k]) * band8_limbs + digit, most significant
+// digit first.
 // band8_limbs == 0: not applicable (upscale, a chunk window wider than 32 outputs, or too many taps).
 struct Band8 {
     int limbs = 0, shift = 0;

@@ -74,8 +74,9 @@ def pass_band(filt: int, n_in: int, n_out: int):
 
 
 def pass_band8(filt: int, n_in: int, n_out: int):
-    """(limbs, shift, gbase[n_chunks + 1], digits[n_chunks, limbs, 32 outputs, 32 indices]) of a downscale pass: the s8
-    weight tiles of the integer tensor-core vertical pass, un-laid-out; None if the pass has no such form."""
+    """(limbs, shift, gbase[n_chunks + 1], digits[n_chunks, limbs, 32 window positions, 32 indices]) of a downscale pass:
+    the s8 weight tiles of the integer tensor-core vertical pass, un-laid-out (window position p of chunk k is output
+    8 * gbase[k] + p); None if the pass has no such form."""
     L = _lib.load()
     limbs, shift = C.c_uint32(), C.c_uint32()
     chunks = L.ikc_pass_band8(filt, n_in, n_out, C.byref(limbs), C.byref(shift), None, None, 0)
@@ -88,8 +89,8 @@ def pass_band8(filt: int, n_in: int, n_out: int):
                            raw.ctypes.data_as(C.POINTER(C.c_int8)), raw.size)
     assert got == chunks
     t = raw.reshape(chunks, 2, nl * 4, 8, 16)                      # [chunk][k / 16][n / 8][n % 8][k % 16]
-    t = t.transpose(0, 2, 3, 1, 4).reshape(chunks, 32, nl, 32)     # [chunk][output mod 32][digit][k]
-    t = t.transpose(0, 2, 1, 3)                                    # [chunk][digit][output mod 32][k]
+    t = t.transpose(0, 2, 3, 1, 4).reshape(chunks, 32, nl, 32)     # [chunk][window position][digit][k]
+    t = t.transpose(0, 2, 1, 3)                                    # [chunk][digit][window position][k]
     return nl, shift.value, gbase, t
 
 

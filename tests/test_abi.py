@@ -191,7 +191,7 @@ def test_band8_tiles_are_the_quantised_pass(ik, oracle, filt, n_in, n_out):
     assert np.all(np.diff(gbase[:-1]) >= 0)
     assert dig[:, 1:].min() >= -64 and dig[:, 1:].max() <= 63          # low digits
     left, count, w = oracle.pass_table(filt, n_in, n_out)
-    # integer weights rebuilt from the digits, accumulated where the tiles put them (ring position = output mod 32)
+    # integer weights rebuilt from the digits, accumulated where the tiles put them (window position p = output 8 * gbase + p)
     W = np.zeros((n_out + 64, chunks * 32), np.int64)
     for c in range(chunks):
         val = np.zeros((32, 32), np.int64)
@@ -200,7 +200,7 @@ def test_band8_tiles_are_the_quantised_pass(ik, oracle, filt, n_in, n_out):
         for pos in range(32):
             if not val[pos].any():
                 continue
-            o = 8 * gbase[c] + (pos - 8 * gbase[c]) % 32                # the window's output with this ring position
+            o = 8 * gbase[c] + pos
             W[o, 32 * c:32 * c + 32] += val[pos]
     assert not W[n_out:].any() and not W[:, n_in:].any()
     scale = float(2 ** shift)
