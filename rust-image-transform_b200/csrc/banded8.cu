@@ -20,7 +20,7 @@
 //
 // One CTA per SM (512 threads, all 512 TMEM columns, ~200 KB of shared memory):
 //   warp 0      producer (TMA): 5-stage ring of source boxes + ring of weight tiles
-//   warp 1      MMA issuer (one lane); warps 2-3 idle (their registers go to the epilogue warpgroups)
+//   warps 1-2   MMA issuers (one lane each, two blocks each); warp 3 idle (registers go to the epilogue warpgroups)
 //   warps 4-15  three epilogue TEAMS of four warps (TMEM lane quarter = warp % 4).  Team t owns every third
 //               intermediate tile (16 output rows = 2 ring groups): it drains the tile's groups from TMEM as they become
 //               final (recombines the digits, writes its own shared-memory tile, zeroes and returns the ring slots) and
@@ -51,6 +51,7 @@ constexpr int k8UStages = 5, k8BStages = 4;
 constexpr int k8Ring = 8;                            // accumulator groups in TMEM: twice the chunk window
 constexpr int k8WinGroups = kBand8Window / kBand8Group;  // groups one chunk's MMAs touch
 constexpr int k8Teams = 3;                           // epilogue teams (4 warps each)
+constexpr int k8MmaWarps = 2;                        // MMA-issuing warps (warps 1 ..): each owns k8Blocks / k8MmaWarps blocks
 constexpr int k8Group = kBand8Group;                 // output rows per group
 constexpr int k8Window = kBand8Window;               // output rows in the ring
 constexpr int k8TileRows = 16;                       // intermediate rows per horizontal phase (two groups)
@@ -161,9 +162,9 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
 
     if (tid == 0) {
         if (smem_addr(smem) & 1023u) __trap();  // the swizzled operand tiles need 1024-byte aligned shared memory
-        for (int s = 0; s < k8UStages; ++s) { mbar_init(u_full + s, 1); mbar_init(u_empty + s, 1); }
-        for (int s = 0; s < k8BStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < k8Ring; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 4); }
+        for (int s = 0; s < k8UStages; ++s) { mbar_init(u_full + s, 1); mbar_init(u_empty + s, k8MmaWarps); }
+        for (int s = 0; s < k8BStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, k8MmaWarps); }
+        for (int s = 0; s < k8Ring; ++s) { mbar_init(t_full + s, k8MmaWarps); mbar_init(t_empty + s, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -211,8 +212,12 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------------------ MMA issuer (one lane)
+    } else if (warp <= k8MmaWarps) {
+        // ------------------------------------------------------------------------------ MMA issuers (one lane each)
+        // The issue loop is a single thread's latency-bound instruction stream (uniform-datapath descriptor arithmetic
+        // around every UTCIMMA), so the strip's blocks are split over k8MmaWarps issuing warps; every hand-off barrier
+        // they commit to counts one arrival per issuer.
+        const int b_lo_blk = (warp - 1) * (k8Blocks / k8MmaWarps), b_hi_blk = b_lo_blk + k8Blocks / k8MmaWarps;
         if (lane == 0) {
             int acquired = g0;   // groups [g0, acquired) belong to the MMAs (zeroed by the epilogue warps)
             int completed = g0;  // groups [g0, completed) have been committed to the epilogue
@@ -240,7 +245,7 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                 const uint32_t c1 = tmem + uint32_t(s0 * k8Group * L);
 #pragma unroll
                 for (int b = 0; b < k8Blocks; ++b) {
-                    if (b < nblk) {
+                    if (b >= b_lo_blk && b < b_hi_blk && b < nblk) {
                         const uint64_t a_desc = make_u64(a_lo + uint32_t(b) * (k8BlockBytes >> 4), a8_desc_hi());
                         mma_i8_acc(c1 + uint32_t(b * kBlockCols), a_desc, make_u64(b_lo, kBDescHi), id1);
                         if (n2) mma_i8_acc(tmem + uint32_t(b * kBlockCols), a_desc, make_u64(b_lo + (n1 >> 3) * (128u >> 4), kBDescHi), id2);
