@@ -30,13 +30,13 @@
 namespace ikc {
 namespace {
 
-constexpr int kUpThreads = 256;
+constexpr int kUpThreads = 128;
 constexpr int kUpKY = 16;                // source rows per tile        ->  32 output rows
 constexpr int kUpOutH = 2 * kUpKY;
 
 template <int C, int T>
 struct UpGeom {
-    static constexpr int kSegPx = C == 4 ? 7 : 8;             // source pixels per warp in the horizontal pass
+    static constexpr int kSegPx = C == 4 ? 6 : 8;             // source pixels per warp in the horizontal pass
     static constexpr int kKX = kSegPx * (kUpThreads / 32);    // source pixels per tile row
     static constexpr int kOutW = 2 * kKX;                     // output columns per tile
     static constexpr int kCols = kKX + T - 1;                 // staged source pixels per row
@@ -86,7 +86,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Persistent CTAs: each walks the tile list with a grid stride and prefetches the next tile's source
 // footprint and weight pairs (cp.async, double buffered) while it computes the current one.
 template <int C, int T>
-__global__ void __launch_bounds__(kUpThreads, 2)
+__global__ void __launch_bounds__(kUpThreads, 4)
 up2_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, int n_items) {
     using G = UpGeom<C, T>;
     extern __shared__ __align__(16) uint8_t up_smem[];
