@@ -101,6 +101,45 @@ __device__ __forceinline__ void tmem_zero8(uint32_t addr) {
 // Barrier over one epilogue team (named barriers 1 .. k8Teams).
 __device__ __forceinline__ void team_barrier(int team) { asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory"); }
 
+
+// One accumulator group (8 output rows x the strip's blocks) of this thread's TMEM lane: TMEM -> registers, the ring slot
+// is zeroed and handed back right away (the stores retire while the digits are recombined), digits -> f32 -> the
+// intermediate tile's column of this lane.  FULL: the strip has all k8Blocks blocks (no per-block predicates).
+template <int L, int PITCH, bool FULL>
+__device__ __forceinline__ void drain_group8(uint32_t taddr, float* __restrict__ trow, int nblk, bool live, uint32_t empty_bar, int lane) {
+    constexpr int kBlockCols = L * k8Ring * k8Group;
+    if (live) {
+        int v[k8Blocks][8 * L];
+#pragma unroll
+        for (int b = 0; b < k8Blocks; ++b)
+            if (FULL || b < nblk) tmem_ld_n<8 * L>(taddr + uint32_t(b * kBlockCols), v[b]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int b = 0; b < k8Blocks; ++b)
+            if (FULL || b < nblk) tmem_zero_n<8 * L>(taddr + uint32_t(b * kBlockCols));
+#pragma unroll
+        for (int b = 0; b < k8Blocks; ++b) {
+            if (FULL || b < nblk) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    int t = v[b][r * L];                                        // most significant digit first
+#pragma unroll
+                    for (int d = 1; d < L; ++d) t = t * 128 + v[b][r * L + d];
+                    trow[r * PITCH + b * 128] = __int2float_rn(t);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < k8Blocks; ++b)
+            if (FULL || b < nblk) tmem_zero_n<8 * L>(taddr + uint32_t(b * kBlockCols));
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_at(empty_bar);
+}
+
 constexpr bool k8Conv = IKC_BANDED8_CONV != 0;
 
 }  // namespace
@@ -133,7 +172,8 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
     int2* const hlr = reinterpret_cast<int2*>(hw + ((geom.hw_pairs + 1) & ~1));
     float* const tmp_all = reinterpret_cast<float*>(hlr + ((geom.max_out + 1) & ~1));  // k8Teams tiles
 
-    const int tid = threadIdx.x;
+    int tid;  // read once: the compiler otherwise re-reads %tid.x (a ~20-cycle S2R) inside the epilogue loops
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
@@ -275,57 +315,47 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                 for (int s = 0; s < k8Ring; ++s) mbar_arrive(t_empty + s);
         }
         float* const tmp = tmp_all + team * kTileFloats;         // this team's intermediate tile
+        uint32_t t_full_a = smem_addr(t_full), t_empty_a = smem_addr(t_empty);  // pinned in registers (not re-derived per use)
+        asm volatile("" : "+r"(t_full_a), "+r"(t_empty_a));
 
         const int hrow = lane & 15;
         const int seg = 2 * q + (lane >> 4);
-        const int per = (n_out + k8Segs - 1) / k8Segs;
-        const int os = ox0 + seg * per;
-        const int oe = min(os + per, ox1);
         const int CO = CONV ? J->out_channels : C;
         uint8_t* const dst_base = J->dst;
         const size_t dst_pitch = J->dst_pitch;
+        // Segments of the strip's outputs.  Rgba8 -> Rgba8 with a 16-byte aligned destination: segments start on absolute
+        // multiples of four outputs (the first one may begin up to three outputs before the strip: computed, never stored),
+        // so that every run of four finished pixels is one 16-byte store.
+        const bool vec_store = C == 4 && !CONV && ((reinterpret_cast<uintptr_t>(dst_base) | dst_pitch) & 15) == 0;
+        const int a0 = vec_store ? (ox0 & ~3) : ox0;
+        int per = (ox1 - a0 + k8Segs - 1) / k8Segs;
+        if (vec_store) per = (per + 3) & ~3;
+        const int os_raw = a0 + seg * per;
+        const int os = max(os_raw, ox0);
+        const int oe = min(os_raw + per, ox1);
         const float* const my_row = tmp + hrow * kTmpPitch - b0;   // indexed by source byte column x * C + c
         const bool uni2 = os < oe && J->h.uni_step == 2 && hstride == 12 && os >= J->h.uni_lo && oe <= J->h.uni_hi;
         float* const tcol = tmp + q * 32 + lane;
+        const bool full = nblk == k8Blocks;
+        // uniform 2:1 stretch: first pixel of output os_raw (outputs before the strip included: the stretch is linear)
+        const int px_first = os < oe ? hlr[os - ox0].x - 2 * (os - os_raw) : 0;
 
         // This team's tiles: every k8Teams-th pair (even group, its successor).  Groups are drained one by one, as soon as
         // they are final, so that their ring slots go back to the MMAs early.
-        for (int gt = (g0 & ~1) + 2 * team; gt < g_end; gt += 2 * k8Teams)
-        for (int g = max(gt, g0); g < min(gt + 2, g_end); ++g) {
-            const int slot = g & (k8Ring - 1);
-            mbar_wait(t_full + slot, ((g - g0) / k8Ring) & 1);
-            tc_fence_after();
-            const int tile_row0 = (g >> 1) * k8TileRows;          // output row of the intermediate tile's first row
+        for (int gt = (g0 & ~1) + 2 * team; gt < g_end; gt += 2 * k8Teams) {
+            const int tile_row0 = (gt >> 1) * k8TileRows;          // output row of the intermediate tile's first row
             const bool live = tile_row0 < oy1 && tile_row0 + k8TileRows > oy0;
-            const uint32_t gcol = uint32_t(slot * k8Group * L);   // the group's first column within a block
-            if (live) {  // TMEM -> registers (digits recombined: exact integer, one conversion) -> tile rows (g & 1) * 8 ..
-                int v[k8Blocks][8 * L];
-#pragma unroll
-                for (int b = 0; b < k8Blocks; ++b)
-                    if (b < nblk) tmem_ld_n<8 * L>(tlane + uint32_t(b * kBlockCols) + gcol, v[b]);
-                tmem_ld_wait();
+            const int g_lo = max(gt, g0), g_hi = min(gt + 2, g_end);
+            for (int g = g_lo; g < g_hi; ++g) {
+                const int slot = g & (k8Ring - 1);
+                mbar_wait_at(t_full_a + slot * 8, ((g - g0) / k8Ring) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tlane + uint32_t(slot * k8Group * L);   // the group's first column within block 0
                 float* const trow = tcol + (g & 1) * k8Group * kTmpPitch;
-#pragma unroll
-                for (int b = 0; b < k8Blocks; ++b) {
-                    if (b < nblk) {
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            int t = v[b][r * L];                                        // most significant digit first
-#pragma unroll
-                            for (int d = 1; d < L; ++d) t = t * 128 + v[b][r * L + d];
-                            trow[r * kTmpPitch + b * 128] = __int2float_rn(t);
-                        }
-                    }
-                }
+                if (full) drain_group8<L, kTmpPitch, true>(taddr, trow, nblk, live, t_empty_a + slot * 8, lane);
+                else drain_group8<L, kTmpPitch, false>(taddr, trow, nblk, live, t_empty_a + slot * 8, lane);
             }
-#pragma unroll
-            for (int b = 0; b < k8Blocks; ++b)
-                if (b < nblk) tmem_zero_n<8 * L>(tlane + uint32_t(b * kBlockCols) + gcol);
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty + slot);
-            if (!live || (!(g & 1) && g + 1 < g_end)) continue;  // the tile's second group is still to come
+            if (!live) continue;
             team_barrier(team);  // the whole tile is in shared memory
 
             const int orow = tile_row0 + hrow;
@@ -333,17 +363,16 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
             uint8_t* const my_dst = dst_base + size_t(orow) * dst_pitch;
             if (os < oe) {
                 if (uni2) {
-                    // Blocks of 8 outputs as straight-line code: the 26 pixels their windows span are loaded at once
-                    // (output j of the block reads pixels 2j .. 2j + 11).  Reads past the segment's last window stay
-                    // inside the tile's padding and are never stored.
-                    float2 uw[12];  // the stretch's 12 tap weights (duplicated pairs); re-read per tile: they are not worth 24 live registers
+                    // Blocks of 8 outputs as straight-line code: output j of the block reads pixels 2j .. 2j + 11 of the 26
+                    // the block spans.  Reads past the segment's last window stay inside the tile's padding and are never
+                    // stored.  Taps are accumulated in ascending order (the reference's order), four chains in flight.
+                    float2 uw[12];  // the stretch's 12 tap weights (duplicated pairs)
 #pragma unroll
                     for (int t = 0; t < 12; ++t) uw[t] = hw[(os - ox0) * 12 + t];
-                    for (int o = os; o < oe; o += 8) {
-                        const float* px = my_row + hlr[o - ox0].x * C;
+                    for (int o = os_raw; o < oe; o += 8) {
+                        const float* px = my_row + (px_first + 2 * (o - os_raw)) * C;
                         uint32_t word[8];
-                        // two halves of 4 outputs: 18 pixels live at a time (output j of a half reads its pixels 2j .. 2j + 11)
-                        float4 p[18];
+                        float4 p[18];   // two halves of 4 outputs: 18 pixels live at a time
 #pragma unroll
                         for (int t = 0; t < 18; ++t) p[t] = load_px<C>(px + t * C);
 #pragma unroll
@@ -355,36 +384,32 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                                 for (int t = 10; t < 18; ++t) p[t] = load_px<C>(px + (t + 8) * C);
                             }
 #pragma unroll
-                            for (int j = 0; j < 4; j += 2) {  // two outputs at a time: eight accumulation chains in flight
-                                float2 a01 = make_float2(kRoundBias, kRoundBias), a23 = a01, c01 = make_float2(0.0f, 0.0f), c23 = c01;
-                                float2 d01 = a01, d23 = a01, e01 = c01, e23 = c01;
+                            for (int j = 0; j < 4; j += 2) {
+                                float2 a01 = make_float2(kRoundBias, kRoundBias), a23 = a01, d01 = a01, d23 = a01;
 #pragma unroll
-                                for (int t = 0; t < 12; t += 2) {
-                                    const float4 x0 = p[2 * j + t], x1 = p[2 * j + t + 1], y0 = p[2 * j + 2 + t], y1 = p[2 * j + 3 + t];
-                                    a01 = __ffma2_rn(uw[t], make_float2(x0.x, x0.y), a01);
-                                    a23 = __ffma2_rn(uw[t], make_float2(x0.z, x0.w), a23);
-                                    d01 = __ffma2_rn(uw[t], make_float2(y0.x, y0.y), d01);
-                                    d23 = __ffma2_rn(uw[t], make_float2(y0.z, y0.w), d23);
-                                    c01 = __ffma2_rn(uw[t + 1], make_float2(x1.x, x1.y), c01);
-                                    c23 = __ffma2_rn(uw[t + 1], make_float2(x1.z, x1.w), c23);
-                                    e01 = __ffma2_rn(uw[t + 1], make_float2(y1.x, y1.y), e01);
-                                    e23 = __ffma2_rn(uw[t + 1], make_float2(y1.z, y1.w), e23);
+                                for (int t = 0; t < 12; ++t) {
+                                    const float4 x = p[2 * j + t], y = p[2 * j + 2 + t];
+                                    a01 = __ffma2_rn(uw[t], make_float2(x.x, x.y), a01);
+                                    a23 = __ffma2_rn(uw[t], make_float2(x.z, x.w), a23);
+                                    d01 = __ffma2_rn(uw[t], make_float2(y.x, y.y), d01);
+                                    d23 = __ffma2_rn(uw[t], make_float2(y.z, y.w), d23);
                                 }
-                                a01 = __fadd2_rn(a01, c01); a23 = __fadd2_rn(a23, c23);
-                                d01 = __fadd2_rn(d01, e01); d23 = __fadd2_rn(d23, e23);
                                 word[4 * half + j] = pack_pixel(make_float4(a01.x, a01.y, a23.x, a23.y));
                                 word[4 * half + j + 1] = pack_pixel(make_float4(d01.x, d01.y, d23.x, d23.y));
                             }
                         }
                         if (row_live) {
-                            uint8_t* const d = my_dst + size_t(o) * CO;
-                            if (C == 4 && !CONV && o + 8 <= oe && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
-                                *reinterpret_cast<uint4*>(d) = make_uint4(word[0], word[1], word[2], word[3]);
-                                *reinterpret_cast<uint4*>(d + 16) = make_uint4(word[4], word[5], word[6], word[7]);
-                            } else {
+                            uint8_t* const d = my_dst + ptrdiff_t(o) * CO;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    if (o + j < oe) store_word<C>(d + j * CO, word[j], CO);
+                            for (int half = 0; half < 2; ++half) {
+                                const int oh = o + 4 * half;
+                                if (vec_store && oh >= ox0 && oh + 4 <= oe) {
+                                    *reinterpret_cast<uint4*>(d + 16 * half) = make_uint4(word[4 * half], word[4 * half + 1], word[4 * half + 2], word[4 * half + 3]);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        if (oh + j >= ox0 && oh + j < oe) store_word<C>(d + (4 * half + j) * CO, word[4 * half + j], CO);
+                                }
                             }
                         }
                     }

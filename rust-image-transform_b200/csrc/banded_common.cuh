@@ -27,6 +27,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// The same on a precomputed 32-bit shared address (epilogue loops: keeps the address arithmetic out of the loop).
+__device__ __forceinline__ void mbar_wait_at(uint32_t bar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar_addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_at(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {  // suspend-time hint: no busy polling
     asm volatile(
         "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(
