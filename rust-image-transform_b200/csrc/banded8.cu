@@ -233,59 +233,69 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(k8RegsIo));
     if (warp == 0) {
         // ------------------------------------------------------------------------------ producer
-        if (lane == 0) {
-            const void* const src_map = J->src_map8;
-            asm volatile("prefetch.tensormap [%0];" ::"l"(src_map) : "memory");
-            const uint8_t* const tiles = reinterpret_cast<const uint8_t*>(J->v.band8_tiles);
-            for (int i = 0; i < nchunks; ++i) {
-                const int k = k0 + i;
-                const int su = i % k8UStages, sb = i % k8BStages;
-                mbar_wait_parked(u_empty + su, ((i / k8UStages) & 1) ^ 1);
+        // (the whole warp runs the loop and polls; one elected lane issues the copies)
+        const bool leader = elect_one();
+        const void* const src_map = J->src_map8;
+        if (leader) asm volatile("prefetch.tensormap [%0];" ::"l"(src_map) : "memory");
+        const uint8_t* const tiles = reinterpret_cast<const uint8_t*>(J->v.band8_tiles) + size_t(k0) * kBTile;
+        int su = 0, sb = 0;
+        uint32_t pu = 1, pb = 1;  // phase bits of the empty barriers (first pass: free)
+        for (int i = 0; i < nchunks; ++i) {
+            mbar_wait_parked(u_empty + su, pu);
+            if (leader) {
                 // one box per 128-byte block: 32 rows x 128 bytes, swizzled into the MMA's operand layout; bytes past the
                 // raster's pitch or rows read as zero
                 mbar_expect_tx(u_full + su, uint32_t(nblk) * k8BlockBytes);
                 for (int b = 0; b < nblk; ++b)
-                    tma_load_2d(ustage + su * k8UStageBytes + b * k8BlockBytes, src_map, b0 + b * 128, k * k8Chunk, u_full + su);
-                mbar_wait_parked(b_empty + sb, ((i / k8BStages) & 1) ^ 1);
-                mbar_expect_tx(b_full + sb, kBTile);
-                bulk_load(bstage + sb * kBTile, tiles + size_t(k) * kBTile, kBTile, b_full + sb);
+                    tma_load_2d(ustage + su * k8UStageBytes + b * k8BlockBytes, src_map, b0 + b * 128, (k0 + i) * k8Chunk, u_full + su);
             }
+            mbar_wait_parked(b_empty + sb, pb);
+            if (leader) {
+                mbar_expect_tx(b_full + sb, kBTile);
+                bulk_load(bstage + sb * kBTile, tiles + size_t(i) * kBTile, kBTile, b_full + sb);
+            }
+            if (++su == k8UStages) { su = 0; pu ^= 1; }
+            if (++sb == k8BStages) { sb = 0; pb ^= 1; }
         }
         __syncwarp();
     } else if (warp <= k8MmaWarps) {
-        // ------------------------------------------------------------------------------ MMA issuers (one lane each)
-        // The issue loop is a single thread's latency-bound instruction stream (uniform-datapath descriptor arithmetic
-        // around every UTCIMMA), so the strip's blocks are split over k8MmaWarps issuing warps; every hand-off barrier
-        // they commit to counts one arrival per issuer.
-        const int b_lo_blk = (warp - 1) * (k8Blocks / k8MmaWarps), b_hi_blk = b_lo_blk + k8Blocks / k8MmaWarps;
-        if (lane == 0) {
-            int acquired = g0;   // groups [g0, acquired) belong to the MMAs (zeroed by the epilogue warps)
-            int completed = g0;  // groups [g0, completed) have been committed to the epilogue
-            const uint32_t a_lo0 = ((smem_addr(ustage) >> 4) & 0x3fffu) | ((1024u >> 4) << 16);
-            const uint32_t b_lo0 = ((smem_addr(bstage) >> 4) & 0x3fffu) | (((uint32_t(kN) * 16u) >> 4) << 16);
-            constexpr uint32_t kBDescHi = (128u >> 4) | (1u << 14);
-            int gb_next = g0;
-            for (int i = 0; i < nchunks; ++i) {
-                const int k = k0 + i;
-                const int gb = gb_next;
-                gb_next = (i + 1 < nchunks) ? __ldg(gbase + k + 1) : 0;
-                while (acquired < gb + k8WinGroups) {  // ring slot = absolute group & 7, use count = how often the item reached it
-                    mbar_wait(t_empty + (acquired & (k8Ring - 1)), ((acquired - g0) / k8Ring) & 1);
-                    ++acquired;
-                }
-                const int su = i % k8UStages, sb = i % k8BStages;
-                mbar_wait(u_full + su, (i / k8UStages) & 1);
-                mbar_wait(b_full + sb, (i / k8BStages) & 1);
-                tc_fence_after();
-                const uint32_t a_lo = a_lo0 + uint32_t(su) * (k8UStageBytes >> 4);
-                const uint32_t b_lo = b_lo0 + uint32_t(sb) * (kBTile >> 4);
-                const int s0 = gb & (k8Ring - 1);
-                const uint32_t n1 = uint32_t(min(k8WinGroups, k8Ring - s0) * k8Group * L), n2 = uint32_t(kN) - n1;  // n2 > 0: the window wraps
-                const uint32_t id1 = instr_desc_i8(n1), id2 = instr_desc_i8(n2);
-                const uint32_t c1 = tmem + uint32_t(s0 * k8Group * L);
+        // ------------------------------------------------------------------------------ MMA issuers
+        // The issue loop is one warp's latency-bound instruction stream, so the strip's blocks are split over k8MmaWarps
+        // issuing warps; every hand-off barrier they commit to counts one arrival per issuer.
+        // The whole warp runs the loop (warp-uniform control flow: the descriptor arithmetic stays on the uniform datapath,
+        // every lane polls the barriers) and one elected lane issues the MMAs and commits.
+        const int b_lo_blk = (warp - 1) * (k8Blocks / k8MmaWarps);
+        const bool leader = elect_one();
+        int acquired = g0;   // groups [g0, acquired) belong to the MMAs (zeroed by the epilogue warps)
+        int completed = g0;  // groups [g0, completed) have been committed to the epilogue
+        const uint32_t a_lo0 = ((smem_addr(ustage) >> 4) & 0x3fffu) | ((1024u >> 4) << 16);
+        const uint32_t b_lo0 = ((smem_addr(bstage) >> 4) & 0x3fffu) | (((uint32_t(kN) * 16u) >> 4) << 16);
+        constexpr uint32_t kBDescHi = (128u >> 4) | (1u << 14);
+        const uint32_t bars_a = smem_addr(bars);
+        int gb_next = g0;
+        int su = 0, sb = 0;
+        uint32_t pu = 0, pb = 0;  // phase bits of the two operand rings
+        for (int i = 0; i < nchunks; ++i) {
+            const int gb = gb_next;
+            gb_next = (i + 1 < nchunks) ? __ldg(gbase + k0 + i + 1) : 0;
+            while (acquired < gb + k8WinGroups) {  // ring slot = absolute group & 7, use count = how often the item reached it
+                mbar_wait_at(bars_a + uint32_t(2 * k8UStages + 2 * k8BStages + k8Ring + (acquired & (k8Ring - 1))) * 8, ((acquired - g0) >> 3) & 1);
+                ++acquired;
+            }
+            mbar_wait_at(bars_a + uint32_t(su) * 8, pu);
+            mbar_wait_at(bars_a + uint32_t(2 * k8UStages + sb) * 8, pb);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + uint32_t(su) * (k8UStageBytes >> 4);
+            const uint32_t b_lo = b_lo0 + uint32_t(sb) * (kBTile >> 4);
+            const int s0 = gb & (k8Ring - 1);
+            const uint32_t n1 = uint32_t(min(k8WinGroups, k8Ring - s0) * k8Group * L), n2 = uint32_t(kN) - n1;  // n2 > 0: the window wraps
+            const uint32_t id1 = instr_desc_i8(n1), id2 = instr_desc_i8(n2);
+            const uint32_t c1 = tmem + uint32_t(s0 * k8Group * L);
+            if (leader) {
 #pragma unroll
-                for (int b = 0; b < k8Blocks; ++b) {
-                    if (b >= b_lo_blk && b < b_hi_blk && b < nblk) {
+                for (int bb = 0; bb < k8Blocks / k8MmaWarps; ++bb) {
+                    const int b = b_lo_blk + bb;
+                    if (b < nblk) {
                         const uint64_t a_desc = make_u64(a_lo + uint32_t(b) * (k8BlockBytes >> 4), a8_desc_hi());
                         mma_i8_acc(c1 + uint32_t(b * kBlockCols), a_desc, make_u64(b_lo, kBDescHi), id1);
                         if (n2) mma_i8_acc(tmem + uint32_t(b * kBlockCols), a_desc, make_u64(b_lo + (n1 >> 3) * (128u >> 4), kBDescHi), id2);
@@ -293,9 +303,12 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                 }
                 tc_commit(u_empty + su);
                 tc_commit(b_empty + sb);
-                const int final_below = (i + 1 < nchunks) ? gb_next : acquired;  // groups below it get no more contributions
-                for (; completed < final_below; ++completed) tc_commit(t_full + (completed & (k8Ring - 1)));
             }
+            const int final_below = (i + 1 < nchunks) ? gb_next : acquired;  // groups below it get no more contributions
+            for (; completed < final_below; ++completed)
+                if (leader) tc_commit(t_full + (completed & (k8Ring - 1)));
+            if (++su == k8UStages) { su = 0; pu ^= 1; }
+            if (++sb == k8BStages) { sb = 0; pb ^= 1; }
         }
         __syncwarp();
     }
