@@ -106,7 +106,7 @@ __device__ __forceinline__ void team_barrier(int team) { asm volatile("bar.sync 
 // is zeroed and handed back right away (the stores retire while the digits are recombined), digits -> f32 -> the
 // intermediate tile's column of this lane.  FULL: the strip has all k8Blocks blocks (no per-block predicates).
 template <int L, int PITCH, bool FULL>
-__device__ __forceinline__ void drain_group8(uint32_t taddr, float* __restrict__ trow, int nblk, bool live, uint32_t empty_bar, int lane) {
+__device__ __forceinline__ void drain_group8(uint32_t taddr, uint32_t trow, int nblk, bool live, uint32_t empty_bar, int lane) {
     constexpr int kBlockCols = L * k8Ring * k8Group;
     if (live) {
         int v[k8Blocks][8 * L];
@@ -125,7 +125,7 @@ __device__ __forceinline__ void drain_group8(uint32_t taddr, float* __restrict__
                     int t = v[b][r * L];                                        // most significant digit first
 #pragma unroll
                     for (int d = 1; d < L; ++d) t = t * 128 + v[b][r * L + d];
-                    trow[r * PITCH + b * 128] = __int2float_rn(t);
+                    sts_f32(trow + uint32_t(r * PITCH + b * 128) * 4, __int2float_rn(t));
                 }
             }
         }
@@ -328,8 +328,13 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                 for (int s = 0; s < k8Ring; ++s) mbar_arrive(t_empty + s);
         }
         float* const tmp = tmp_all + team * kTileFloats;         // this team's intermediate tile
-        uint32_t t_full_a = smem_addr(t_full), t_empty_a = smem_addr(t_empty);  // pinned in registers (not re-derived per use)
-        asm volatile("" : "+r"(t_full_a), "+r"(t_empty_a));
+        // Loop invariants pinned in registers: opaque to the compiler, which otherwise re-derives them (S2R %tid.x, shifts,
+        // multiplies) for every group and tile to save registers it has no other use for.
+        const uint32_t t_full_a = pin_u32(smem_addr(t_full), lane), t_empty_a = pin_u32(smem_addr(t_empty), lane);
+        const uint32_t tcol_a = pin_u32(smem_addr(tmp + q * 32 + lane), lane);   // this lane's column of the tile (drain)
+        const uint32_t tlane_p = pin_u32(tlane, lane);
+        const int lane_p = int(pin_u32(uint32_t(lane), lane));
+        const int team_p = int(pin_u32(uint32_t(team), lane));
 
         const int hrow = lane & 15;
         const int seg = 2 * q + (lane >> 4);
@@ -347,8 +352,9 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
         const int os = max(os_raw, ox0);
         const int oe = min(os_raw + per, ox1);
         const float* const my_row = tmp + hrow * kTmpPitch - b0;   // indexed by source byte column x * C + c
+        const uint32_t my_row_a = pin_u32(smem_addr(tmp + hrow * kTmpPitch) - uint32_t(b0) * 4, lane);
+        const uint32_t uw_a = pin_u32(smem_addr(hw) + uint32_t(max(os - ox0, 0) * 12) * 8, lane);   // the segment's first weight row
         const bool uni2 = os < oe && J->h.uni_step == 2 && hstride == 12 && os >= J->h.uni_lo && oe <= J->h.uni_hi;
-        float* const tcol = tmp + q * 32 + lane;
         const bool full = nblk == k8Blocks;
         // uniform 2:1 stretch: first pixel of output os_raw (outputs before the strip included: the stretch is linear)
         const int px_first = os < oe ? hlr[os - ox0].x - 2 * (os - os_raw) : 0;
@@ -363,13 +369,13 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                 const int slot = g & (k8Ring - 1);
                 mbar_wait_at(t_full_a + slot * 8, ((g - g0) / k8Ring) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tlane + uint32_t(slot * k8Group * L);   // the group's first column within block 0
-                float* const trow = tcol + (g & 1) * k8Group * kTmpPitch;
-                if (full) drain_group8<L, kTmpPitch, true>(taddr, trow, nblk, live, t_empty_a + slot * 8, lane);
-                else drain_group8<L, kTmpPitch, false>(taddr, trow, nblk, live, t_empty_a + slot * 8, lane);
+                const uint32_t taddr = tlane_p + uint32_t(slot * k8Group * L);   // the group's first column within block 0
+                const uint32_t trow = tcol_a + uint32_t((g & 1) * k8Group * kTmpPitch) * 4;
+                if (full) drain_group8<L, kTmpPitch, true>(taddr, trow, nblk, live, t_empty_a + slot * 8, lane_p);
+                else drain_group8<L, kTmpPitch, false>(taddr, trow, nblk, live, t_empty_a + slot * 8, lane_p);
             }
             if (!live) continue;
-            team_barrier(team);  // the whole tile is in shared memory
+            team_barrier(team_p);  // the whole tile is in shared memory
 
             const int orow = tile_row0 + hrow;
             const bool row_live = orow >= oy0 && orow < oy1;
@@ -381,20 +387,21 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                     // stored.  Taps are accumulated in ascending order (the reference's order), four chains in flight.
                     float2 uw[12];  // the stretch's 12 tap weights (duplicated pairs)
 #pragma unroll
-                    for (int t = 0; t < 12; ++t) uw[t] = hw[(os - ox0) * 12 + t];
+                    for (int t = 0; t < 12; ++t) uw[t] = lds_f32x2(uw_a + t * 8);
                     for (int o = os_raw; o < oe; o += 8) {
                         const float* px = my_row + (px_first + 2 * (o - os_raw)) * C;
+                        const uint32_t px_a = my_row_a + uint32_t((px_first + 2 * (o - os_raw)) * C) * 4;
                         uint32_t word[8];
                         float4 p[18];   // two halves of 4 outputs: 18 pixels live at a time
 #pragma unroll
-                        for (int t = 0; t < 18; ++t) p[t] = load_px<C>(px + t * C);
+                        for (int t = 0; t < 18; ++t) p[t] = C == 4 ? lds_f32x4(px_a + t * 16) : load_px<C>(px + t * C);
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
                             if (half == 1) {
 #pragma unroll
                                 for (int t = 0; t < 10; ++t) p[t] = p[t + 8];          // (register renaming, no moves once unrolled)
 #pragma unroll
-                                for (int t = 10; t < 18; ++t) p[t] = load_px<C>(px + (t + 8) * C);
+                                for (int t = 10; t < 18; ++t) p[t] = C == 4 ? lds_f32x4(px_a + (t + 8) * 16) : load_px<C>(px + (t + 8) * C);
                             }
 #pragma unroll
                             for (int j = 0; j < 4; j += 2) {
@@ -454,7 +461,7 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
                 }
             }
             __syncwarp();
-            team_barrier(team);  // the tile may be overwritten
+            team_barrier(team_p);  // the tile may be overwritten
         }
     }
 

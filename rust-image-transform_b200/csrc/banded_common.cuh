@@ -143,6 +143,24 @@ __device__ __forceinline__ void store_pixel(uint8_t* dst_px, float4 v_plus_half,
     store_word<C>(dst_px, pack_pixel(v_plus_half), co);
 }
 
+// Pins a loop invariant in a register: the value comes back from a warp shuffle of the lane with itself, which ptxas
+// neither folds nor re-executes, so it cannot re-derive the value (S2R %tid.x + shifts + multiplies) at every use.
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
+
+// Shared-memory accesses on a 32-bit shared address held in one register (the epilogue loops pin their base addresses
+// instead of letting the compiler re-derive 64-bit pointers).
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+
 // One intermediate pixel (C floats at `p`) as a float4; missing channels read as zero.
 template <int C>
 __device__ __forceinline__ float4 load_px(const float* p) {
