@@ -386,7 +386,8 @@ int ikc_batch_describe(const ikc_batch* b, char* out, size_t cap) {
     std::string s;
     for (auto& g : b->impl.lp.groups) {
         if (!s.empty()) s += "; ";
-        if (g.band8_limbs) s += "banded8_kernel<" + std::to_string(g.channels) + (g.convert ? ",conv" : "") + "> (" + std::to_string(g.band8_limbs) + " digits)";
+        if (g.band8t) s += "banded8t_kernel<4> (2 digits, " + std::to_string(g.b8tgeom.chunks) + " chunks per band)";
+        else if (g.band8_limbs) s += "banded8_kernel<" + std::to_string(g.channels) + (g.convert ? ",conv" : "") + "> (" + std::to_string(g.band8_limbs) + " digits)";
         else if (g.band_n) s += "banded_kernel<" + std::to_string(g.channels) + (g.convert ? ",conv" : "") + "> (band_n " + std::to_string(g.band_n) + ")";
         else if (g.up_taps) s += "up2_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.up_taps) + ">";
         else if (g.kv == 0) s += g.bps == 2 ? "tile_kernel<u16>" : "tile_kernel";

@@ -403,20 +403,21 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
 #pragma unroll
                                 for (int t = 10; t < 18; ++t) p[t] = C == 4 ? lds_f32x4(px_a + (t + 8) * 16) : load_px<C>(px + (t + 8) * C);
                             }
+                            float2 acc[4][2];  // four outputs at a time: eight accumulation chains in flight
 #pragma unroll
-                            for (int j = 0; j < 4; j += 2) {
-                                float2 a01 = make_float2(kRoundBias, kRoundBias), a23 = a01, d01 = a01, d23 = a01;
+                            for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = make_float2(kRoundBias, kRoundBias);
 #pragma unroll
-                                for (int t = 0; t < 12; ++t) {
-                                    const float4 x = p[2 * j + t], y = p[2 * j + 2 + t];
-                                    a01 = __ffma2_rn(uw[t], make_float2(x.x, x.y), a01);
-                                    a23 = __ffma2_rn(uw[t], make_float2(x.z, x.w), a23);
-                                    d01 = __ffma2_rn(uw[t], make_float2(y.x, y.y), d01);
-                                    d23 = __ffma2_rn(uw[t], make_float2(y.z, y.w), d23);
+                            for (int t = 0; t < 12; ++t) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 x = p[2 * j + t];
+                                    acc[j][0] = __ffma2_rn(uw[t], make_float2(x.x, x.y), acc[j][0]);
+                                    acc[j][1] = __ffma2_rn(uw[t], make_float2(x.z, x.w), acc[j][1]);
                                 }
-                                word[4 * half + j] = pack_pixel(make_float4(a01.x, a01.y, a23.x, a23.y));
-                                word[4 * half + j + 1] = pack_pixel(make_float4(d01.x, d01.y, d23.x, d23.y));
                             }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                word[4 * half + j] = pack_pixel(make_float4(acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y));
                         }
                         if (row_live) {
                             uint8_t* const d = my_dst + ptrdiff_t(o) * CO;

@@ -259,11 +259,13 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     const size_t b_gbase = up(sizeof(int32_t) * host->band_gbase.size());
     const size_t b_band8 = up(host->band8.tiles.size());
     const size_t b_gbase8 = up(sizeof(int32_t) * host->band8.gbase.size());
+    const size_t b_band8t = up(host->band8t.tiles.size());
+    const size_t b_klo8t = up(sizeof(int32_t) * host->band8t.k_lo.size());
     auto t = std::make_shared<DevTables>();
     t->device = ordinal_;
     t->host = host;
     check_cuda(cudaSetDevice(ordinal_), "cudaSetDevice");
-    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + 2 * b_ring + 2 * b_up2 + b_band + b_gbase + b_band8 + b_gbase8 + 256), "cudaMalloc(weight tables)");
+    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + 2 * b_ring + 2 * b_up2 + b_band + b_gbase + b_band8 + b_gbase8 + b_band8t + b_klo8t + 256), "cudaMalloc(weight tables)");
     uint8_t* p = static_cast<uint8_t*>(t->base);
     auto put = [&](const void* src, size_t bytes, size_t slot) {
         uint8_t* at = p;
@@ -299,6 +301,11 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     t->pass.band8_gbase = host->band8.limbs ? reinterpret_cast<const int32_t*>(gbase8) : nullptr;
     t->pass.band8_limbs = host->band8.limbs;
     t->pass.band8_shift = host->band8.shift;
+    const uint8_t* band8t = put(host->band8t.tiles.data(), host->band8t.tiles.size(), b_band8t);
+    const uint8_t* klo8t = put(host->band8t.k_lo.data(), sizeof(int32_t) * host->band8t.k_lo.size(), b_klo8t);
+    t->pass.band8t_tiles = host->band8t.chunks ? reinterpret_cast<const int8_t*>(band8t) : nullptr;
+    t->pass.band8t_klo = host->band8t.chunks ? reinterpret_cast<const int32_t*>(klo8t) : nullptr;
+    t->pass.band8t_chunks = host->band8t.chunks;
     t->pass.up2_off = host->up2_off;
     t->pass.up2_taps = host->up2_taps;
     t->pass.up2_uni_lo = host->up2_uni_lo;
@@ -473,6 +480,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
     };
     std::vector<Cand> cands;
     std::vector<WorkItem> tile_items[2];  // [bytes per sample - 1]: one tile-kernel launch per sample type
+    std::vector<int> b8t_jobs;            // jobs of the banded8t launch (cut into items once the batch is known)
     TileGeom tile_geom[2]{};
     lp.jobs.reserve(n);
     for (size_t i = 0; i < n; ++i) {
@@ -506,8 +514,25 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
             bool fused = !exact && d.bps == 1 && d.sh >= d.dh && d.sw >= d.dw &&
                          fused_supported(d.channels, tv->pass.ring_k, th->pass.ring_k) && tma_ok;
             Cand c{idx, {}, d.channels, tv->pass.ring_k, th->pass.ring_k, 0, 0, d.oc() != d.channels, 0, 0};
-            // First choice for downscales: the banded8 kernel (vertical pass as an integer product on the tensor cores,
-            // source bytes used as they are).
+            // Rgba8 downscales that are exactly 2:1 horizontally (and at most ~2:1 vertically): the row-band kernel, whose
+            // horizontal pass runs from registers (banded8t.cu).  Work items: bands of 128 output rows x column segments.
+            if (!exact && mode.load() == 0 && d.bps == 1 && d.channels == 4 && d.oc() == 4 && tma_ok &&
+                ((reinterpret_cast<uintptr_t>(d.dst) | d.dst_pitch) & 15) == 0 && tv->pass.band8t_tiles && tv->pass.band8_limbs == 2 &&
+                th->host->h2_12 && encode_src_map8(lp.jobs[size_t(idx)].src_map8, d.src, d.sh, d.src_pitch)) {
+                FusedGroup* g = nullptr;
+                for (auto& gg : lp.groups)
+                    if (gg.band8t) g = &gg;
+                if (!g) {
+                    lp.groups.push_back(FusedGroup{4, 0, 0, {}, {}, {}});
+                    g = &lp.groups.back();
+                    g->band8t = true;
+                }
+                g->b8tgeom.chunks = std::max(g->b8tgeom.chunks, tv->pass.band8t_chunks);
+                b8t_jobs.push_back(idx);
+                continue;
+            }
+            // First choice for the other downscales: the banded8 kernel (vertical pass as an integer product on the tensor
+            // cores, source bytes used as they are).
             bool banded8 = !exact && mode.load() == 0 && d.bps == 1 && d.sh >= d.dh && d.sw >= d.dw && tma_ok &&
                            tv->pass.band8_tiles && banded8_supported(d.channels, tv->pass.band8_limbs);
             if (banded8) {
@@ -589,6 +614,29 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         g.tgeom.n_items = int(g.items.size());
         g.bps = b + 1;
         lp.groups.push_back(std::move(g));
+    }
+    if (!b8t_jobs.empty()) {
+        // Items: band x column segment.  Enough segments to give every SM about two items, none narrower than 128 outputs
+        // (each segment pays one block of pre-roll), boundaries on multiples of eight outputs.
+        FusedGroup* g = nullptr;
+        for (auto& gg : lp.groups)
+            if (gg.band8t) g = &gg;
+        const int rows = banded8t_band_rows();
+        size_t bands = 0;
+        for (int idx : b8t_jobs) bands += (lp.jobs[size_t(idx)].dh + rows - 1) / rows;
+        const int want = int((2 * size_t(dev.sm_count()) + bands - 1) / bands);
+        for (int idx : b8t_jobs) {
+            const DevJob& j = lp.jobs[size_t(idx)];
+            const int dw = int(j.dw), dh = int(j.dh);
+            const int segs = std::max(1, std::min(want, dw / 128));
+            for (int oy = 0; oy < dh; oy += rows)
+                for (int k = 0; k < segs; ++k) {
+                    const int x0 = k == 0 ? 0 : int(int64_t(dw) * k / segs) & ~7;
+                    const int x1 = k == segs - 1 ? dw : int(int64_t(dw) * (k + 1) / segs) & ~7;
+                    if (x1 > x0) g->items.push_back(WorkItem{idx, x0, x1, oy, std::min(dh, oy + rows)});
+                }
+        }
+        g->b8tgeom.n_items = int(g->items.size());
     }
     if (cands.empty()) return lp;
 
@@ -711,7 +759,8 @@ void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, 
     size_t off = (sizeof(DevJob) * lp.jobs.size() + 15) & ~size_t(15);
     for (auto& g : lp.groups) {
         const WorkItem* d_items = reinterpret_cast<const WorkItem*>(d_desc_base + off);
-        if (g.band8_limbs) check_cuda(launch_banded8(g.channels, g.convert, d_jobs, d_items, g.b8geom, stream), "launch banded8_kernel");
+        if (g.band8t) check_cuda(launch_banded8t(d_jobs, d_items, g.b8tgeom, stream), "launch banded8t_kernel");
+        else if (g.band8_limbs) check_cuda(launch_banded8(g.channels, g.convert, d_jobs, d_items, g.b8geom, stream), "launch banded8_kernel");
         else if (g.band_n) check_cuda(launch_banded(g.channels, g.convert, d_jobs, d_items, g.bgeom, stream), "launch banded_kernel");
         else if (g.up_taps) check_cuda(launch_up2(g.channels, g.up_taps, d_jobs, d_items, int(g.items.size()), stream), "launch up2_kernel");
         else if (g.kv == 0) check_cuda(launch_tile(g.bps, d_jobs, d_items, g.tgeom, stream), "launch tile_kernel");

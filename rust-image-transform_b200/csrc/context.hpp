@@ -68,6 +68,8 @@ struct FusedGroup {  // one kernel launch over a list of work items
     BandGeom bgeom{};
     int band8_limbs = 0;   // > 0: a banded8 (integer tensor-core) launch with this many digits per weight
     Band8Geom b8geom{};
+    bool band8t = false;   // a banded8t (row-band integer tensor-core) launch
+    Band8TGeom b8tgeom{};
 };
 
 // Everything needed to enqueue a set of device-resident jobs.

@@ -40,6 +40,11 @@ struct DevPass {
     const int32_t* band8_gbase;      // [n_chunks + 1], groups of 8 outputs
     int32_t band8_limbs;             // base-128 digits per weight (2 or 3); 0 if none
     int32_t band8_shift;             // weights are round(w * 2^shift)
+    // Row-band form of the same digits (plan.hpp: Band8T), used by the kernel whose accumulator lanes are output rows
+    // (banded8t.cu).
+    const int8_t* band8t_tiles;      // [n_bands][band8t_chunks][2][128 x 32] s8, operand layout; nullptr if none
+    const int32_t* band8t_klo;       // [n_bands] first chunk of each band of 128 outputs
+    int32_t band8t_chunks;           // operand tiles per band and digit (<= 10); 0 if none
 };
 
 // One image resize, device pointers.
@@ -89,6 +94,12 @@ struct Band8Geom {
     int32_t limbs;         // digits per weight: all jobs of a launch share it
     int32_t max_out;
     int32_t hw_pairs;
+    int32_t n_items;
+};
+
+// Launch-wide geometry of the banded8t (row-band integer tensor-core) kernel.
+struct Band8TGeom {
+    int32_t chunks;        // weight tiles per band and digit: max over the launch's jobs (sizes shared memory)
     int32_t n_items;
 };
 

@@ -251,6 +251,12 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
             p.uni_hi = int(best_lo + best_len);
         }
     }
+    if (p.uni_step == 2 && p.count[size_t(p.uni_lo)] == 12 && p.left[size_t(p.uni_lo)] == 2 * p.uni_lo - 5) {
+        bool ok = true;
+        for (uint32_t o = 0; o < n_out && ok; ++o)
+            ok = int64_t(p.left[o]) >= 2 * int64_t(o) - 5 && int64_t(p.right[o]) <= 2 * int64_t(o) + 7;
+        p.h2_12 = ok;
+    }
     // Frame form for exact 2x upscales.
     if (n_out == 2 * n_in) {
         int off = 0x7fffffff, end = -0x7fffffff;
@@ -357,6 +363,25 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
             p.band8.tiles.assign(size_t(n_chunks) * tile, 0);
             const double scale = std::ldexp(1.0, shift);
             std::vector<int64_t> W;
+            // row-band form: applicable when no band of 128 outputs spans more than kBand8TMaxChunks chunks
+            const uint32_t n_bands = (n_out + kBand8TRows - 1) / kBand8TRows;
+            int band_chunks = 0;
+            std::vector<int32_t> k_lo(n_bands, 0);
+            if (limbs == 2) {
+                for (uint32_t r = 0; r < n_bands; ++r) {
+                    const uint32_t o0 = r * kBand8TRows, o1 = std::min(n_out, o0 + kBand8TRows);
+                    k_lo[r] = p.left[o0] / kBand8Chunk;
+                    const int k_hi = (p.right[o1 - 1] - 1) / kBand8Chunk;
+                    band_chunks = std::max(band_chunks, k_hi - k_lo[r] + 1);
+                }
+                if (band_chunks > kBand8TMaxChunks) band_chunks = 0;
+            }
+            constexpr size_t kTTile = size_t(kBand8TRows) * kBand8Chunk;
+            if (band_chunks) {
+                p.band8t.chunks = band_chunks;
+                p.band8t.k_lo = k_lo;
+                p.band8t.tiles.assign(size_t(n_bands) * band_chunks * 2 * kTTile, 0);
+            }
             for (uint32_t o = 0; o < n_out; ++o) {
                 const auto& ws = ragged[o];
                 W.resize(ws.size());
@@ -382,6 +407,12 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
                         const int n = pos * limbs + d;         // row of the tile: an output's digits are adjacent, most significant first
                         const size_t at = size_t(kk / 16) * (size_t(limbs) * kBand8Window * 16) + size_t(n / 8) * 128 + size_t(n % 8) * 16 + size_t(kk % 16);
                         t[at] = int8_t(digit);
+                        if (band_chunks) {  // the same digit in the row-band tile (band, chunk, digit): row m, index kk
+                            const uint32_t r = o / kBand8TRows;
+                            const int m = int(o % kBand8TRows);
+                            const size_t tt = ((size_t(r) * band_chunks + size_t(int(c) - k_lo[r])) * 2 + size_t(d)) * kTTile;
+                            p.band8t.tiles[tt + size_t(kk / 16) * (size_t(kBand8TRows) * 16) + size_t(m / 8) * 128 + size_t(m % 8) * 16 + size_t(kk % 16)] = int8_t(digit);
+                        }
                     }
                 }
             }

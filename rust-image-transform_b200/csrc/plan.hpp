@@ -35,6 +35,19 @@ struct Band8 {
 };
 constexpr int kBand8Chunk = 32, kBand8Group = 8, kBand8Window = 32;
 
+// Row-band form of the same integer weights, for the kernel whose accumulator lanes are OUTPUT rows (banded8t.cu): the
+// weights are the A operand.  Band r = outputs [128 r, 128 r + 128); it reads the chunks (of kBand8Chunk source indices)
+// k_lo[r] .. k_lo[r] + chunks - 1.  tiles: per band, chunk and digit (most significant first) one K-major s8 operand
+// tile of 128 rows x 32 indices in the shared-memory layout the MMA reads (8 x 16-byte core matrices: rows 128 bytes
+// apart, the two halves of the 32 indices 2048 bytes apart).  chunks == 0: not applicable (a band needs more than
+// kBand8TMaxChunks chunks, i.e. the ratio is well above 2).
+struct Band8T {
+    int chunks = 0;
+    std::vector<int32_t> k_lo;    // [n_bands]
+    std::vector<int8_t> tiles;    // [n_bands][chunks][2][128 * 32]
+};
+constexpr int kBand8TRows = 128, kBand8TMaxChunks = 10;
+
 
 // One separable pass n_in -> n_out with a given filter.
 struct PassPlan {
@@ -77,6 +90,10 @@ struct PassPlan {
     std::vector<int32_t> band_gbase;    // [n_chunks + 1]
     std::vector<uint16_t> band_tiles;   // [n_chunks][2][band_n * 16] f16 bit patterns
     Band8 band8;                        // the 8-bit band form (see above)
+    Band8T band8t;                      // its row-band form (shares band8.shift; two digits)
+    // Exact 2:1 pass whose every window lies inside the 12 source indices [2 o - 5, 2 o + 7) and whose uniform stretch has
+    // exactly those 12 taps: what banded8t.cu's register-resident horizontal filter is written for.
+    bool h2_12 = false;
 };
 
 constexpr int kBandChunk = 16;          // source indices per chunk (K of tcgen05.mma kind::f16)
