@@ -236,7 +236,7 @@ banded8t_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
                     if (leader) {
                         mbar_expect_tx(u_full + su, uint32_t(nch) * kTStageBytes);
                         for (int c = 0; c < nch; ++c)
-                            tma_load_2d(ustage + su * kTBlockStage + c * kTStageBytes, src_map, blk * kTBlockBytes, (k_lo + c) * kTChunk, u_full + su);
+                            tma_load_2d(ustage + su * kTBlockStage + c * kTStageBytes, src_map, blk * kTBlockBytes, k_lo + c * kTChunk, u_full + su);
                     }
                     if (++su == kTStages) { su = 0; pu ^= 1; }
                 }
@@ -309,7 +309,8 @@ banded8t_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
         for (int k = 0; k < 4; ++k) st.word[k] = 0;
 
         // One block = two super-steps = four quarters of 8 pixels; the next quarter's digits are in flight (tcgen05.ld into
-        // the other register buffer) while the current one is pushed through the filter.
+        // the other register buffer) while the current one is pushed through the filter.  The super-step body exists once
+        // (a two-trip loop): the straight-line code of a whole block would not stay in the instruction cache.
         const int nb = sr.blocks();
         for (int n = 0; n < nb; ++n) {
             const int Q = 2 * (sr.b0 + n);                         // the block's first super-step
@@ -318,29 +319,27 @@ banded8t_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
             int hiA[32], loA[32], hiB[32], loB[32];
             tmem_ld32(taddr, hiA);
             tmem_ld32(taddr + kTUnitCols, loA);
-            tmem_ld_wait();
-            tmem_ld32(taddr + 32, hiB);
-            tmem_ld32(taddr + kTUnitCols + 32, loB);
             // every output the block touches lies in the uniform stretch: tap weights from registers
             const bool interior = 8 * Q - 3 >= uni_lo && 8 * (Q + 1) + 10 < uni_hi;
-            if (interior) push_half<0, false>(st, hiA, loA, uw, Q, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
-            else push_half<0, true>(st, hiA, loA, uw, Q, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
-            tmem_ld_wait();
-            tmem_ld32(taddr + 64, hiA);
-            tmem_ld32(taddr + kTUnitCols + 64, loA);
-            if (interior) push_half<1, false>(st, hiB, loB, uw, Q, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
-            else push_half<1, true>(st, hiB, loB, uw, Q, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
-            tmem_ld_wait();
-            tmem_ld32(taddr + 96, hiB);
-            tmem_ld32(taddr + kTUnitCols + 96, loB);
-            if (interior) push_half<0, false>(st, hiA, loA, uw, Q + 1, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
-            else push_half<0, true>(st, hiA, loA, uw, Q + 1, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_at(t_empty_a);              // the tile may be overwritten
-            if (interior) push_half<1, false>(st, hiB, loB, uw, Q + 1, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
-            else push_half<1, true>(st, hiB, loB, uw, Q + 1, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+#pragma unroll 1
+            for (int ss = 0; ss < 2; ++ss) {
+                tmem_ld_wait();
+                tmem_ld32(taddr + uint32_t(64 * ss + 32), hiB);
+                tmem_ld32(taddr + kTUnitCols + uint32_t(64 * ss + 32), loB);
+                if (interior) push_half<0, false>(st, hiA, loA, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+                else push_half<0, true>(st, hiA, loA, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+                tmem_ld_wait();
+                if (ss == 0) {
+                    tmem_ld32(taddr + 64, hiA);
+                    tmem_ld32(taddr + kTUnitCols + 64, loA);
+                } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_at(t_empty_a);      // the tile may be overwritten
+                }
+                if (interior) push_half<1, false>(st, hiB, loB, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+                else push_half<1, true>(st, hiB, loB, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+            }
         }
     }
 

@@ -370,9 +370,8 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
             if (limbs == 2) {
                 for (uint32_t r = 0; r < n_bands; ++r) {
                     const uint32_t o0 = r * kBand8TRows, o1 = std::min(n_out, o0 + kBand8TRows);
-                    k_lo[r] = p.left[o0] / kBand8Chunk;
-                    const int k_hi = (p.right[o1 - 1] - 1) / kBand8Chunk;
-                    band_chunks = std::max(band_chunks, k_hi - k_lo[r] + 1);
+                    k_lo[r] = p.left[o0];  // the band's chunks start at its first source index (not on a multiple of 32)
+                    band_chunks = std::max(band_chunks, (p.right[o1 - 1] - k_lo[r] + kBand8Chunk - 1) / kBand8Chunk);
                 }
                 if (band_chunks > kBand8TMaxChunks) band_chunks = 0;
             }
@@ -407,11 +406,12 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
                         const int n = pos * limbs + d;         // row of the tile: an output's digits are adjacent, most significant first
                         const size_t at = size_t(kk / 16) * (size_t(limbs) * kBand8Window * 16) + size_t(n / 8) * 128 + size_t(n % 8) * 16 + size_t(kk % 16);
                         t[at] = int8_t(digit);
-                        if (band_chunks) {  // the same digit in the row-band tile (band, chunk, digit): row m, index kk
+                        if (band_chunks) {  // the same digit in the row-band tile (band, chunk, digit): row m, index kt
                             const uint32_t r = o / kBand8TRows;
                             const int m = int(o % kBand8TRows);
-                            const size_t tt = ((size_t(r) * band_chunks + size_t(int(c) - k_lo[r])) * 2 + size_t(d)) * kTTile;
-                            p.band8t.tiles[tt + size_t(kk / 16) * (size_t(kBand8TRows) * 16) + size_t(m / 8) * 128 + size_t(m % 8) * 16 + size_t(kk % 16)] = int8_t(digit);
+                            const int ct = (y - k_lo[r]) / kBand8Chunk, kt = (y - k_lo[r]) % kBand8Chunk;
+                            const size_t tt = ((size_t(r) * band_chunks + size_t(ct)) * 2 + size_t(d)) * kTTile;
+                            p.band8t.tiles[tt + size_t(kt / 16) * (size_t(kBand8TRows) * 16) + size_t(m / 8) * 128 + size_t(m % 8) * 16 + size_t(kt % 16)] = int8_t(digit);
                         }
                     }
                 }
