@@ -308,9 +308,11 @@ banded8t_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
 #pragma unroll
         for (int k = 0; k < 4; ++k) st.word[k] = 0;
 
-        // One block = two super-steps = four quarters of 8 pixels; the next quarter's digits are in flight (tcgen05.ld into
-        // the other register buffer) while the current one is pushed through the filter.  The super-step body exists once
-        // (a two-trip loop): the straight-line code of a whole block would not stay in the instruction cache.
+        // One block = two super-steps = four quarters of 8 pixels in two register buffers.  Quarters 2 and 3 are fetched
+        // (tcgen05.ld) while quarters 0 and 1 are pushed through the filter, and the tile goes back to the MMA warp as soon
+        // as they have landed: the next block's MMAs then have half a block of this quad's arithmetic to hide behind.  The
+        // super-step body exists once (a two-trip loop): the straight-line code of a whole block would not stay in the
+        // instruction cache.
         const int nb = sr.blocks();
         for (int n = 0; n < nb; ++n) {
             const int Q = 2 * (sr.b0 + n);                         // the block's first super-step
@@ -319,26 +321,29 @@ banded8t_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
             int hiA[32], loA[32], hiB[32], loB[32];
             tmem_ld32(taddr, hiA);
             tmem_ld32(taddr + kTUnitCols, loA);
+            tmem_ld32(taddr + 32, hiB);
+            tmem_ld32(taddr + kTUnitCols + 32, loB);
             // every output the block touches lies in the uniform stretch: tap weights from registers
             const bool interior = 8 * Q - 3 >= uni_lo && 8 * (Q + 1) + 10 < uni_hi;
+            tmem_ld_wait();
 #pragma unroll 1
             for (int ss = 0; ss < 2; ++ss) {
-                tmem_ld_wait();
-                tmem_ld32(taddr + uint32_t(64 * ss + 32), hiB);
-                tmem_ld32(taddr + kTUnitCols + uint32_t(64 * ss + 32), loB);
                 if (interior) push_half<0, false>(st, hiA, loA, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
                 else push_half<0, true>(st, hiA, loA, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
-                tmem_ld_wait();
                 if (ss == 0) {
                     tmem_ld32(taddr + 64, hiA);
                     tmem_ld32(taddr + kTUnitCols + 64, loA);
-                } else {
+                }
+                if (interior) push_half<1, false>(st, hiB, loB, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+                else push_half<1, true>(st, hiB, loB, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+                if (ss == 0) {
+                    tmem_ld32(taddr + 96, hiB);
+                    tmem_ld32(taddr + kTUnitCols + 96, loB);
+                    tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_at(t_empty_a);      // the tile may be overwritten
                 }
-                if (interior) push_half<1, false>(st, hiB, loB, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
-                else push_half<1, true>(st, hiB, loB, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
             }
         }
     }
