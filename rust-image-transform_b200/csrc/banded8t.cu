@@ -114,8 +114,9 @@ __device__ __forceinline__ float edge_weight(const DevPass& h, int o, int x, flo
 //   hi / lo : the digits of the 32 intermediate values, as tcgen05.ld delivered them
 //   uw      : the uniform stretch's twelve tap weights (x 2^-shift, duplicated pairs)      (EDGE == false)
 //   EDGE    : weights are looked up per (output, pixel) instead
-// Output 8 Q + j is complete after pixel 2 j + 6 of the super-step; it is stored when its group of four is, if in range.
-template <int HALF, bool EDGE>
+// Output 8 Q + j is complete after pixel 2 j + 6 of the super-step; it is stored when its group of four is, if in range
+// (FULL: the caller knows every group the super-step completes is).
+template <int HALF, bool EDGE, bool FULL>
 __device__ __forceinline__ void push_half(RowState& st, const int (&hi)[32], const int (&lo)[32], const float2 (&uw)[kTTaps], int Q,
                                           const DevPass& h, float unscale, uint8_t* __restrict__ dst_row, int x0, int x1, bool row_live) {
 #pragma unroll
@@ -132,12 +133,13 @@ __device__ __forceinline__ void push_half(RowState& st, const int (&hi)[32], con
             const int t = i - (2 * j - kTLead);         // tap index
             if (t < 0 || t >= kTTaps) continue;
             const int slot = (j + kTSlots) & (kTSlots - 1);
-            float2 w;
-            if (EDGE) {
-                const float we = edge_weight(h, 8 * Q + j, kTPx * Q + i, unscale);
-                w = make_float2(we, we);
-            } else {
-                w = uw[t];
+            float2 w = uw[t];
+            if (EDGE) {                                 // outputs outside the uniform stretch: look the weight up
+                const int o = 8 * Q + j;
+                if (o < h.uni_lo || o >= h.uni_hi) {
+                    const float we = edge_weight(h, o, kTPx * Q + i, unscale);
+                    w = make_float2(we, we);
+                }
             }
             st.acc[slot][0] = __ffma2_rn(w, v01, st.acc[slot][0]);
             st.acc[slot][1] = __ffma2_rn(w, v23, st.acc[slot][1]);
@@ -150,7 +152,9 @@ __device__ __forceinline__ void push_half(RowState& st, const int (&hi)[32], con
             st.acc[slot][0] = st.acc[slot][1] = make_float2(kRoundBias, kRoundBias);
             if (((j + 4) & 3) == 3) {                   // outputs o - 3 .. o: one aligned group of four
                 const int og = o - 3;
-                if (row_live) {
+                if (FULL) {                             // the whole super-step lies inside the stream's columns: no range tests
+                    if (row_live) *reinterpret_cast<uint4*>(dst_row + size_t(og) * 4) = make_uint4(st.word[0], st.word[1], st.word[2], st.word[3]);
+                } else if (row_live) {
                     if (og >= x0 && o < x1) {
                         *reinterpret_cast<uint4*>(dst_row + size_t(og) * 4) = make_uint4(st.word[0], st.word[1], st.word[2], st.word[3]);
                     } else if (o >= x0 && og < x1) {
@@ -323,19 +327,24 @@ banded8t_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
             tmem_ld32(taddr + kTUnitCols, loA);
             tmem_ld32(taddr + 32, hiB);
             tmem_ld32(taddr + kTUnitCols + 32, loB);
-            // every output the block touches lies in the uniform stretch: tap weights from registers
-            const bool interior = 8 * Q - 3 >= uni_lo && 8 * (Q + 1) + 10 < uni_hi;
             tmem_ld_wait();
 #pragma unroll 1
             for (int ss = 0; ss < 2; ++ss) {
-                if (interior) push_half<0, false>(st, hiA, loA, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
-                else push_half<0, true>(st, hiA, loA, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+                // every output the super-step touches lies in the uniform stretch (tap weights from registers) and every
+                // group of four it completes inside the stream's columns (no range tests): the fast path
+                const int qs = Q + ss;
+                const bool interior = 8 * qs - 3 >= uni_lo && 8 * qs + 10 < uni_hi;
+                const bool fast = interior && 8 * qs - 4 >= sr.x0 && 8 * qs + 3 < sr.x1;
+                if (fast) push_half<0, false, true>(st, hiA, loA, uw, qs, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+                else if (interior) push_half<0, false, false>(st, hiA, loA, uw, qs, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+                else push_half<0, true, false>(st, hiA, loA, uw, qs, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
                 if (ss == 0) {
                     tmem_ld32(taddr + 64, hiA);
                     tmem_ld32(taddr + kTUnitCols + 64, loA);
                 }
-                if (interior) push_half<1, false>(st, hiB, loB, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
-                else push_half<1, true>(st, hiB, loB, uw, Q + ss, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+                if (fast) push_half<1, false, true>(st, hiB, loB, uw, qs, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+                else if (interior) push_half<1, false, false>(st, hiB, loB, uw, qs, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
+                else push_half<1, true, false>(st, hiB, loB, uw, qs, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
                 if (ss == 0) {
                     tmem_ld32(taddr + 96, hiB);
                     tmem_ld32(taddr + kTUnitCols + 96, loB);
