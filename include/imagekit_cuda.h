@@ -191,6 +191,15 @@ IKC_API uint32_t ikc_pass_band(int filter, uint32_t n_in, uint32_t n_out, uint32
 IKC_API uint32_t ikc_pass_band8(int filter, uint32_t n_in, uint32_t n_out, uint32_t* limbs, uint32_t* shift, int32_t* gbase,
                                 int8_t* tiles, size_t tiles_cap);
 
+/* Row-band form of the same integer weights (the A operand of the kernel whose accumulator lanes are output rows;
+ * inspection for tests; no GPU needed).  Band r = outputs [128 r, 128 r + 128); its chunks of 32 source indices start at
+ * k_lo[r].  tiles: per band, chunk (*chunks of them) and digit (most significant first) one s8 operand tile of 128 rows
+ * x 32 indices, element (row m, index k) at (k / 16) * 2048 + (m / 8) * 128 + (m % 8) * 16 + (k % 16).  Returns the
+ * number of bands (0: the pass has no such form -- ratio well above 2, or no 8-bit band form at all -- or a buffer is too
+ * small); k_lo == tiles == NULL: only *chunks and the count. */
+IKC_API uint32_t ikc_pass_band8t(int filter, uint32_t n_in, uint32_t n_out, uint32_t* chunks, int32_t* k_lo, int8_t* tiles,
+                                 size_t tiles_cap);
+
 /* ---- host-buffer entry points (the drop-in path; include H2D + D2H) -------------------------- */
 
 /* Replaces imageops::resize(&buf, dw, dh, filter) for 8-bit rasters (image 0.25.8

@@ -162,6 +162,22 @@ uint32_t ikc_pass_band8(int filter, uint32_t n_in, uint32_t n_out, uint32_t* lim
     return chunks;
 }
 
+uint32_t ikc_pass_band8t(int filter, uint32_t n_in, uint32_t n_out, uint32_t* chunks, int32_t* k_lo, int8_t* tiles, size_t tiles_cap) {
+    uint32_t bands = 0;
+    guarded([&] {
+        auto p = build_pass(filter, n_in, n_out);
+        if (!p || p->band8t.chunks == 0) return;
+        if (chunks) *chunks = uint32_t(p->band8t.chunks);
+        if (k_lo || tiles) {
+            if (!k_lo || !tiles || tiles_cap < p->band8t.tiles.size()) return;
+            std::memcpy(k_lo, p->band8t.k_lo.data(), sizeof(int32_t) * p->band8t.k_lo.size());
+            std::memcpy(tiles, p->band8t.tiles.data(), p->band8t.tiles.size());
+        }
+        bands = uint32_t(p->band8t.k_lo.size());
+    });
+    return bands;
+}
+
 int ikc_pass_info(int filter, uint32_t n_in, uint32_t n_out, ikc_pass_info_t* out) {
     if (!out) return IKC_ERR_INVALID_ARG;
     return guarded([&] {

@@ -616,15 +616,21 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         lp.groups.push_back(std::move(g));
     }
     if (!b8t_jobs.empty()) {
-        // Items: band x column segment.  Enough segments to give every SM about two items, none narrower than 128 outputs
-        // (each segment pays one block of pre-roll), boundaries on multiples of eight outputs.
+        // Items: band x column segment (boundaries on multiples of eight outputs, no segment narrower than 128 outputs:
+        // each pays one block of pre-roll).  One CTA per SM: the segment count minimises (waves) x (work per item).
         FusedGroup* g = nullptr;
         for (auto& gg : lp.groups)
             if (gg.band8t) g = &gg;
         const int rows = banded8t_band_rows();
         size_t bands = 0;
         for (int idx : b8t_jobs) bands += (lp.jobs[size_t(idx)].dh + rows - 1) / rows;
-        const int want = int((2 * size_t(dev.sm_count()) + bands - 1) / bands);
+        int want = 1;
+        double best = 1e30;
+        for (int sgs = 1; sgs <= 64; ++sgs) {
+            const double waves = std::ceil(double(bands) * sgs / double(dev.sm_count()));
+            const double cost = waves * (1.0 / sgs + 0.03);
+            if (cost < best - 1e-12) { best = cost; want = sgs; }
+        }
         for (int idx : b8t_jobs) {
             const DevJob& j = lp.jobs[size_t(idx)];
             const int dw = int(j.dw), dh = int(j.dh);

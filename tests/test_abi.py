@@ -214,6 +214,39 @@ def test_band8_tiles_are_the_quantised_pass(ik, oracle, filt, n_in, n_out):
     assert np.abs(W).max() <= 127 * 128 + 63
 
 
+@pytest.mark.parametrize("filt,n_in,n_out", [(4, 2160, 1080), (4, 777, 388), (2, 500, 250), (4, 64, 32), (4, 700, 400), (4, 1300, 600)])
+def test_band8t_tiles_hold_the_same_integers_as_band8(ik, filt, n_in, n_out):
+    """The row-band tiles (A operand of banded8t.cu) and the chunk-window tiles (B operand of banded8.cu) are two layouts of
+    one integer weight matrix."""
+    from imagekit_cuda import engine
+    limbs, shift, gbase, dig = engine.pass_band8(filt, n_in, n_out)
+    band_t = engine.pass_band8t(filt, n_in, n_out)
+    assert band_t is not None
+    nc, k_lo, t = band_t
+    bands = t.shape[0]
+    assert bands == (n_out + 127) // 128 and 1 <= nc <= 10
+    W8 = np.zeros((n_out + 64, dig.shape[0] * 32 + 512), np.int64)
+    for c in range(dig.shape[0]):
+        val = dig[c, 0].astype(np.int64) * 128 + dig[c, 1].astype(np.int64)
+        for pos in np.flatnonzero(val.any(axis=1)):
+            W8[8 * gbase[c] + pos, 32 * c:32 * c + 32] += val[pos]
+    WT = np.zeros_like(W8)
+    for r in range(bands):
+        for c in range(nc):
+            val = t[r, c, 0].astype(np.int64) * 128 + t[r, c, 1].astype(np.int64)
+            y0 = k_lo[r] + 32 * c
+            rows = min(128, WT.shape[0] - 128 * r)
+            assert not val[rows:].any()
+            WT[128 * r:128 * r + rows, y0:y0 + 32] += val[:rows]
+    assert np.array_equal(W8[:n_out], WT[:n_out]) and not WT[n_out:].any()
+
+
+def test_band8t_needs_a_ratio_near_two(ik):
+    from imagekit_cuda import engine
+    assert engine.pass_band8t(4, 3024, 300) is None     # a band of 128 outputs spans far more than 10 chunks
+    assert engine.pass_band8t(4, 100, 200) is None
+
+
 def test_band8_needs_a_narrow_chunk_window(ik):
     from imagekit_cuda import engine
     assert engine.pass_band8(4, 100, 200) is None       # upscale

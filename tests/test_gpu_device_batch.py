@@ -170,3 +170,72 @@ def test_randomised_prepared_batches(ctx, ik, oracle):
                 failures.append((dsc, d, batch.describe()))
         batch.free()
     assert not failures, failures[:4]
+
+
+ROW_BAND_SHAPES = [  # Rgba8, exactly 2:1 horizontally, at most ~2:1 vertically, 16-byte aligned rows: (h, w, dw, dh)
+    (384, 512, 256, 192), (130, 264, 132, 65), (700, 1000, 500, 350), (300, 640, 320, 150), (514, 2056, 1028, 257),
+    (700, 1000, 500, 400), (2160, 3840, 1920, 1080), (1090, 768, 384, 545), (64, 96, 48, 32),
+]
+
+
+@pytest.mark.parametrize("shape", ROW_BAND_SHAPES)
+@pytest.mark.parametrize("content", ["noise", "edges"])
+def test_row_band_kernel(ctx, ik, oracle, shape, content):
+    """banded8t.cu: accumulator lanes are output rows, the horizontal pass runs from registers.  Single images are cut
+    into column segments (one CTA each), so segment seams, the image borders (looked-up weights) and the last, partial
+    band are all on the path."""
+    import torch
+    from conftest import checker
+    h, w, dw, dh = shape
+    if content != "noise" and h * w > 2_000_000:
+        pytest.skip("large shapes run on noise only")
+    ctx.set_mode(ik.MODE_FAST)
+    dev = torch.device("cuda:0")
+    s = splitmix_noise((h, w, 4), image_id=h) if content == "noise" else checker((h, w, 4))
+    ts = torch.from_numpy(s).to(dev)
+    td = torch.zeros((dh, dw, 4), dtype=torch.uint8, device=dev)
+    batch = ctx.prepare_batch(0, [(ts.data_ptr(), w, h, w * 4, td.data_ptr(), dw, dh, dw * 4, 4, ik.FILTER_LANCZOS3)])
+    assert batch.jobs[0].status == 0
+    assert "banded8t_kernel" in batch.describe(), batch.describe()
+    stream = torch.cuda.Stream()
+    batch.launch(stream.cuda_stream)
+    stream.synchronize()
+    hist = delta_histogram(td.cpu().numpy(), oracle.resize_exact(s, dw, dh, oracle.LANCZOS3))
+    assert max(abs(k) for k in hist) <= 1, hist
+    off = sum(v for k, v in hist.items() if k != 0) / td.numel()
+    assert off < (0.02 if content == "noise" else 0.5), hist
+    batch.free()
+
+
+def test_row_band_kernel_batches_and_fallbacks(ctx, ik, oracle):
+    """A batch of 2:1 Rgba8 jobs of different sizes shares one banded8t launch (whole-width items); a destination that is
+    not 16-byte aligned, another channel count or a fused conversion take the other downscale kernel in the same batch."""
+    import torch
+    ctx.set_mode(ik.MODE_FAST)
+    dev = torch.device("cuda:0")
+    cases = [  # (h, w, c, dw, dh, co, dst pitch slack)
+        (384, 512, 4, 256, 192, 4, 0), (1080, 1920, 4, 960, 540, 4, 0), (300, 640, 4, 320, 150, 4, 0), (700, 1000, 4, 500, 350, 4, 0),
+        (300, 640, 4, 320, 150, 4, 4), (300, 640, 3, 320, 150, 3, 0), (300, 640, 4, 320, 150, 3, 0),
+    ]
+    keep, jobs, want = [], [], []
+    for i, (h, w, c, dw, dh, co, slack) in enumerate(cases):
+        s = splitmix_noise((h, w, c), image_id=70 + i)
+        ts = torch.from_numpy(s).to(dev)
+        pitch = dw * co + slack
+        td = torch.zeros((dh, pitch), dtype=torch.uint8, device=dev)
+        keep.append((ts, td))
+        jobs.append((ts.data_ptr(), w, h, w * c, td.data_ptr(), dw, dh, pitch, c | (co << 8) if co != c else c, ik.FILTER_LANCZOS3))
+        r = oracle.resize_exact(s, dw, dh, oracle.LANCZOS3)
+        want.append(r if co == c else oracle.to_rgb8(r))
+    batch = ctx.prepare_batch(0, jobs)
+    assert all(j.status == 0 for j in batch.jobs), [j.status for j in batch.jobs]
+    desc = batch.describe()
+    assert "banded8t_kernel" in desc and "banded8_kernel" in desc, desc
+    stream = torch.cuda.Stream()
+    batch.launch(stream.cuda_stream)
+    stream.synchronize()
+    for (h, w, c, dw, dh, co, slack), (_, td), exp in zip(cases, keep, want):
+        got = td.cpu().numpy()[:, :dw * co].reshape(dh, dw, co)
+        hist = delta_histogram(got, exp)
+        assert max(abs(k) for k in hist) <= 1, ((h, w, c, co, slack), hist)
+    batch.free()
