@@ -88,7 +88,7 @@ void Buffer::release() {
 }
 void Buffer::reserve(size_t bytes) {
     if (bytes <= cap) return;
-    size_t want = std::max<size_t>(bytes, 1 << 16);
+    size_t want = std::max<size_t>(bytes, size_t(4) << 20);  // (growing means cudaFree + cudaMalloc: a device-wide stall; start big enough for thumbnails)
     want = std::max(want, cap + cap / 2);
     want = (want + 255) & ~size_t(255);
     release();
@@ -98,13 +98,22 @@ void Buffer::reserve(size_t bytes) {
 }
 
 DevTables::~DevTables() {
-    if (base) {
-        int cur = 0;
-        cudaGetDevice(&cur);
-        cudaSetDevice(device);
-        cudaFree(base);
-        cudaSetDevice(cur);
+    if (!base && !ready) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    if (base) cudaFreeAsync(base, stream);   // stream-ordered: no device-wide synchronisation on eviction
+    if (ready) cudaEventDestroy(ready);
+    cudaSetDevice(cur);
+}
+
+void DevTables::wait_ready(cudaStream_t s) {
+    if (settled.load(std::memory_order_acquire) || !ready) return;
+    if (cudaEventQuery(ready) == cudaSuccess) {
+        settled.store(true, std::memory_order_release);
+        return;
     }
+    check_cuda(cudaStreamWaitEvent(s, ready, 0), "cudaStreamWaitEvent(weight tables)");
 }
 
 // ---- copy pool ------------------------------------------------------------------------------------
@@ -203,6 +212,14 @@ Device::Device(Context* ctx, int ordinal, int index) : ctx_(ctx), ordinal_(ordin
     if (prop.major < 10)
         fail(kCudaError, std::string("device ") + prop.name + " is not sm_100-class; this library is built for sm_100a only");
     sm_count_ = prop.multiProcessorCount;
+    check_cuda(cudaStreamCreateWithFlags(&table_stream_, cudaStreamNonBlocking), "cudaStreamCreate(table stream)");
+    {   // freed table memory stays in the pool instead of going back to the driver (which would synchronise)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, ordinal) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     for (int i = 0; i < kLanesPerDevice; ++i) {
         auto l = std::make_unique<Lane>();
         check_cuda(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -213,7 +230,16 @@ Device::Device(Context* ctx, int ordinal, int index) : ctx_(ctx), ordinal_(ordin
 
 Device::~Device() {
     cudaSetDevice(ordinal_);
+    for (auto& l : lanes_)
+        if (l->stream) cudaStreamSynchronize(l->stream);
     tabs_.clear();
+    if (table_stream_) cudaStreamSynchronize(table_stream_);
+    for (auto& b : stage_) {
+        if (b.done) cudaEventDestroy(b.done);
+        if (b.p) cudaFreeHost(b.p);
+    }
+    // (the table stream itself is left to the context's teardown: tables still referenced by a caller's prepared batch
+    // free themselves on it)
     for (auto& l : lanes_) {
         if (l->stream) {
             cudaStreamSynchronize(l->stream);
@@ -226,10 +252,15 @@ Device::~Device() {
 }
 
 Lane* Device::acquire_lane() {
+    // First come, first served: with a plain condition variable a thread that has just released a lane wins it back
+    // against the waiters again and again, and the waiters' latency grows a tail of tens of milliseconds.
     std::unique_lock<std::mutex> lk(mu_);
-    cv_.wait(lk, [&] { return !free_.empty(); });
+    const uint64_t ticket = next_ticket_++;
+    cv_.wait(lk, [&] { return ticket == serving_ && !free_.empty(); });
+    ++serving_;
     Lane* l = free_.back();
     free_.pop_back();
+    cv_.notify_all();  // the next ticket may find a free lane too
     return l;
 }
 void Device::release_lane(Lane* l) {
@@ -237,7 +268,7 @@ void Device::release_lane(Lane* l) {
         std::lock_guard<std::mutex> lk(mu_);
         free_.push_back(l);
     }
-    cv_.notify_one();
+    cv_.notify_all();
 }
 
 std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_out) {
@@ -249,62 +280,105 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     }
     auto host = ctx_->pass(filter, n_in, n_out);
     if (!host) fail(kInvalidArg, "cannot plan pass");
-    // one allocation: left | right | w | ring (each 256-byte aligned)
+    // One stream-ordered allocation (left | right | w | ring forms | 2x-upscale pairs | band forms, each 256-byte aligned),
+    // filled from one pinned staging block by one asynchronous copy on the device's table stream.  Nothing here waits
+    // for the device: consumers order their streams behind `ready` (DevTables::wait_ready).
     auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
-    const size_t b_idx = up(sizeof(int32_t) * n_out);
-    const size_t b_w = up(sizeof(float) * host->w.size());
-    const size_t b_ring = up(sizeof(float) * host->ring_v.size());
-    const size_t b_up2 = up(sizeof(float) * host->up2_pairs.size());
-    const size_t b_band = up(sizeof(uint16_t) * host->band_tiles.size());
-    const size_t b_gbase = up(sizeof(int32_t) * host->band_gbase.size());
-    const size_t b_band8 = up(host->band8.tiles.size());
-    const size_t b_gbase8 = up(sizeof(int32_t) * host->band8.gbase.size());
-    const size_t b_band8t = up(host->band8t.tiles.size());
-    const size_t b_klo8t = up(sizeof(int32_t) * host->band8t.k_lo.size());
+    std::vector<float> up2_v(host->up2_pairs.size()), up2_h(host->up2_pairs.size());
+    for (size_t i = 0; i < up2_v.size(); ++i) {
+        up2_v[i] = host->up2_pairs[i] * kRingScaleV;  // exact: powers of two
+        up2_h[i] = host->up2_pairs[i] * kRingScaleH;
+    }
+    struct Part { const void* src; size_t bytes; size_t off; };
+    std::vector<Part> parts;
+    size_t total = 0;
+    auto add = [&](const void* src, size_t bytes) {
+        parts.push_back(Part{src, bytes, total});
+        total += up(bytes);
+        return parts.size() - 1;
+    };
+    const size_t i_left = add(host->left.data(), sizeof(int32_t) * n_out);
+    const size_t i_right = add(host->right.data(), sizeof(int32_t) * n_out);
+    const size_t i_w = add(host->w.data(), sizeof(float) * host->w.size());
+    const size_t i_ring_v = add(host->ring_v.data(), sizeof(float) * host->ring_v.size());
+    const size_t i_ring_h = add(host->ring_h.data(), sizeof(float) * host->ring_h.size());
+    const size_t i_up2_v = add(up2_v.data(), sizeof(float) * up2_v.size());
+    const size_t i_up2_h = add(up2_h.data(), sizeof(float) * up2_h.size());
+    const size_t i_band = add(host->band_tiles.data(), sizeof(uint16_t) * host->band_tiles.size());
+    const size_t i_gbase = add(host->band_gbase.data(), sizeof(int32_t) * host->band_gbase.size());
+    const size_t i_band8 = add(host->band8.tiles.data(), host->band8.tiles.size());
+    const size_t i_gbase8 = add(host->band8.gbase.data(), sizeof(int32_t) * host->band8.gbase.size());
+    const size_t i_band8t = add(host->band8t.tiles.data(), host->band8t.tiles.size());
+    const size_t i_klo8t = add(host->band8t.k_lo.data(), sizeof(int32_t) * host->band8t.k_lo.size());
+    total = std::max<size_t>(total, 256);
+
     auto t = std::make_shared<DevTables>();
     t->device = ordinal_;
     t->host = host;
+    t->stream = table_stream_;
     check_cuda(cudaSetDevice(ordinal_), "cudaSetDevice");
-    check_cuda(cudaMalloc(&t->base, 2 * b_idx + b_w + 2 * b_ring + 2 * b_up2 + b_band + b_gbase + b_band8 + b_gbase8 + b_band8t + b_klo8t + 256), "cudaMalloc(weight tables)");
-    uint8_t* p = static_cast<uint8_t*>(t->base);
-    auto put = [&](const void* src, size_t bytes, size_t slot) {
-        uint8_t* at = p;
-        if (bytes) check_cuda(cudaMemcpy(at, src, bytes, cudaMemcpyHostToDevice), "cudaMemcpy(weight tables)");
-        p += slot;
-        return at;
-    };
-    struct SyncOnExit {  // pageable-source cudaMemcpy may return before the DMA lands, and the lanes'
-        ~SyncOnExit() { cudaDeviceSynchronize(); }  // non-blocking streams do not order against it
-    } sync_on_exit;
-    t->pass.left = reinterpret_cast<const int32_t*>(put(host->left.data(), sizeof(int32_t) * n_out, b_idx));
-    t->pass.right = reinterpret_cast<const int32_t*>(put(host->right.data(), sizeof(int32_t) * n_out, b_idx));
-    t->pass.w = reinterpret_cast<const float*>(put(host->w.data(), sizeof(float) * host->w.size(), b_w));
-    const uint8_t* ring_v = put(host->ring_v.data(), sizeof(float) * host->ring_v.size(), b_ring);
-    const uint8_t* ring_h = put(host->ring_h.data(), sizeof(float) * host->ring_h.size(), b_ring);
-    t->pass.ring_v = host->ring_v.empty() ? nullptr : reinterpret_cast<const float*>(ring_v);
-    t->pass.ring_h = host->ring_h.empty() ? nullptr : reinterpret_cast<const float*>(ring_h);
-    std::vector<float> scaled(host->up2_pairs.size());
-    for (size_t i = 0; i < scaled.size(); ++i) scaled[i] = host->up2_pairs[i] * kRingScaleV;  // exact: a power of two
-    const uint8_t* up2_v = put(scaled.data(), sizeof(float) * scaled.size(), b_up2);
-    for (size_t i = 0; i < scaled.size(); ++i) scaled[i] = host->up2_pairs[i] * kRingScaleH;
-    const uint8_t* up2_h = put(scaled.data(), sizeof(float) * scaled.size(), b_up2);
-    t->pass.up2_pairs_v = scaled.empty() ? nullptr : reinterpret_cast<const float2*>(up2_v);
-    t->pass.up2_pairs_h = scaled.empty() ? nullptr : reinterpret_cast<const float2*>(up2_h);
-    const uint8_t* band = put(host->band_tiles.data(), sizeof(uint16_t) * host->band_tiles.size(), b_band);
-    const uint8_t* gbase = put(host->band_gbase.data(), sizeof(int32_t) * host->band_gbase.size(), b_gbase);
-    t->pass.band_tiles = host->band_n ? reinterpret_cast<const uint16_t*>(band) : nullptr;
-    t->pass.band_gbase = host->band_n ? reinterpret_cast<const int32_t*>(gbase) : nullptr;
+    check_cuda(cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming), "cudaEventCreate(weight tables)");
+    check_cuda(cudaMallocAsync(&t->base, total, table_stream_), "cudaMallocAsync(weight tables)");
+    {
+        // a free staging block (its previous copy has completed, or is waited for by this thread only)
+        size_t k;
+        {
+            std::lock_guard<std::mutex> lk(stage_mu_);
+            for (k = 0; k < stage_.size(); ++k)
+                if (!stage_[k].busy) break;
+            if (k == stage_.size()) stage_.push_back(StageBlock{});
+            stage_[k].busy = true;
+        }
+        StageBlock blk;
+        {
+            std::lock_guard<std::mutex> lk(stage_mu_);
+            blk = stage_[k];
+        }
+        try {
+            if (blk.done) check_cuda(cudaEventSynchronize(blk.done), "cudaEventSynchronize(table staging)");
+            else check_cuda(cudaEventCreateWithFlags(&blk.done, cudaEventDisableTiming), "cudaEventCreate(table staging)");
+            if (blk.cap < total) {
+                if (blk.p) cudaFreeHost(blk.p);
+                blk.p = nullptr;
+                blk.cap = 0;
+                const size_t want = std::max<size_t>(total + total / 2, size_t(1) << 20);
+                check_cuda(cudaMallocHost(&blk.p, want), "cudaMallocHost(table staging)");
+                blk.cap = want;
+            }
+            uint8_t* hp = static_cast<uint8_t*>(blk.p);
+            for (const Part& pt : parts)
+                if (pt.bytes) std::memcpy(hp + pt.off, pt.src, pt.bytes);
+            check_cuda(cudaMemcpyAsync(t->base, hp, total, cudaMemcpyHostToDevice, table_stream_), "cudaMemcpyAsync(weight tables)");
+            check_cuda(cudaEventRecord(blk.done, table_stream_), "cudaEventRecord(table staging)");
+            check_cuda(cudaEventRecord(t->ready, table_stream_), "cudaEventRecord(weight tables)");
+        } catch (...) {
+            std::lock_guard<std::mutex> lk(stage_mu_);
+            blk.busy = false;
+            stage_[k] = blk;
+            throw;
+        }
+        std::lock_guard<std::mutex> lk(stage_mu_);
+        blk.busy = false;
+        stage_[k] = blk;
+    }
+    const uint8_t* base = static_cast<const uint8_t*>(t->base);
+    auto at = [&](size_t i) { return base + parts[i].off; };
+    t->pass.left = reinterpret_cast<const int32_t*>(at(i_left));
+    t->pass.right = reinterpret_cast<const int32_t*>(at(i_right));
+    t->pass.w = reinterpret_cast<const float*>(at(i_w));
+    t->pass.ring_v = host->ring_v.empty() ? nullptr : reinterpret_cast<const float*>(at(i_ring_v));
+    t->pass.ring_h = host->ring_h.empty() ? nullptr : reinterpret_cast<const float*>(at(i_ring_h));
+    t->pass.up2_pairs_v = up2_v.empty() ? nullptr : reinterpret_cast<const float2*>(at(i_up2_v));
+    t->pass.up2_pairs_h = up2_h.empty() ? nullptr : reinterpret_cast<const float2*>(at(i_up2_h));
+    t->pass.band_tiles = host->band_n ? reinterpret_cast<const uint16_t*>(at(i_band)) : nullptr;
+    t->pass.band_gbase = host->band_n ? reinterpret_cast<const int32_t*>(at(i_gbase)) : nullptr;
     t->pass.band_n = host->band_n;
-    const uint8_t* band8 = put(host->band8.tiles.data(), host->band8.tiles.size(), b_band8);
-    const uint8_t* gbase8 = put(host->band8.gbase.data(), sizeof(int32_t) * host->band8.gbase.size(), b_gbase8);
-    t->pass.band8_tiles = host->band8.limbs ? reinterpret_cast<const int8_t*>(band8) : nullptr;
-    t->pass.band8_gbase = host->band8.limbs ? reinterpret_cast<const int32_t*>(gbase8) : nullptr;
+    t->pass.band8_tiles = host->band8.limbs ? reinterpret_cast<const int8_t*>(at(i_band8)) : nullptr;
+    t->pass.band8_gbase = host->band8.limbs ? reinterpret_cast<const int32_t*>(at(i_gbase8)) : nullptr;
     t->pass.band8_limbs = host->band8.limbs;
     t->pass.band8_shift = host->band8.shift;
-    const uint8_t* band8t = put(host->band8t.tiles.data(), host->band8t.tiles.size(), b_band8t);
-    const uint8_t* klo8t = put(host->band8t.k_lo.data(), sizeof(int32_t) * host->band8t.k_lo.size(), b_klo8t);
-    t->pass.band8t_tiles = host->band8t.chunks ? reinterpret_cast<const int8_t*>(band8t) : nullptr;
-    t->pass.band8t_klo = host->band8t.chunks ? reinterpret_cast<const int32_t*>(klo8t) : nullptr;
+    t->pass.band8t_tiles = host->band8t.chunks ? reinterpret_cast<const int8_t*>(at(i_band8t)) : nullptr;
+    t->pass.band8t_klo = host->band8t.chunks ? reinterpret_cast<const int32_t*>(at(i_klo8t)) : nullptr;
     t->pass.band8t_chunks = host->band8t.chunks;
     t->pass.up2_off = host->up2_off;
     t->pass.up2_taps = host->up2_taps;
@@ -761,6 +835,7 @@ void Context::fill_desc(const LaunchPlan& lp, uint8_t* host, float* scratch) con
 }
 
 void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, cudaStream_t stream, bool exact) {
+    for (auto& t : lp.keepalive) t->wait_ready(stream);   // freshly uploaded weight tables: order behind their copy
     const DevJob* d_jobs = reinterpret_cast<const DevJob*>(d_desc_base);
     size_t off = (sizeof(DevJob) * lp.jobs.size() + 15) & ~size_t(15);
     for (auto& g : lp.groups) {
@@ -814,6 +889,7 @@ struct HostJobState {  // one in-flight host job on a lane
     size_t in_pitch = 0, out_pitch = 0;
     bool out_staged = false;
     uint32_t out_chunk_rows = 0;  // staged output: rows per D2H chunk (one event each)
+    LaunchPlan lp;                // kept until the job has finished: it holds the references to the weight tables
 };
 
 constexpr size_t kStageChunkBytes = size_t(4) << 20;   // DMA granule of the pageable staging pipeline
@@ -867,9 +943,9 @@ void start_host_job(Context& ctx, Device& dev, Lane& l, const JobDesc& d, HostJo
     dj.src_pitch = st->in_pitch;
     dj.dst_pitch = st->out_pitch;
     int status = kOk;
-    LaunchPlan lp = ctx.plan(dev, &dj, 1, &status, exact);
+    st->lp = ctx.plan(dev, &dj, 1, &status, exact);
     if (status != kOk) fail(Status(status), last_error());
-    ctx.enqueue(dev, lp, l.h_desc, l.d_desc, l.d_scratch, l.stream, exact);
+    ctx.enqueue(dev, st->lp, l.h_desc, l.d_desc, l.d_scratch, l.stream, exact);
     st->out_staged = !is_pinned(d.dst);
     if (st->out_staged) {
         // Pageable destination: the result comes back in chunks, each followed by an event, so that
@@ -894,12 +970,13 @@ void start_host_job(Context& ctx, Device& dev, Lane& l, const JobDesc& d, HostJo
         check_cuda(cudaMemcpy2DAsync(d.dst, d.dst_pitch, l.d_out.p, st->out_pitch, out_row, d.dh, cudaMemcpyDeviceToHost, l.stream),
                    "D2H copy");
     }
-    // `lp` (and the table references it keeps alive) may go away now: the cache still holds the
-    // tables, and kernels already enqueued only need the device memory, which eviction frees with a
-    // synchronising cudaFree.
 }
 
-void finish_host_job(Context& ctx, Lane& l, const HostJobState& st) {
+void finish_host_job(Context& ctx, Lane& l, HostJobState& st) {
+    struct DropPlan {  // the table references go once the stream has drained (also when a copy below throws)
+        HostJobState& s; cudaStream_t q;
+        ~DropPlan() { cudaStreamSynchronize(q); s.lp = LaunchPlan{}; }
+    } drop{st, l.stream};
     if (st.out_staged) {
         const JobDesc& d = st.d;
         const size_t out_row = size_t(d.dw) * d.oc() * d.bps;
@@ -960,8 +1037,8 @@ void Context::resize_host(const JobDesc& d, int* device_index_out) {
     if (device_index_out) *device_index_out = dev.index();
     check_cuda(cudaSetDevice(dev.ordinal()), "cudaSetDevice");
     Lane* l = dev.acquire_lane();
+    HostJobState st;  // (outlives the handler below: its plan holds the weight tables the enqueued kernels read)
     try {
-        HostJobState st;
         start_host_job(*this, dev, *l, d, &st, mode.load() == 1);
         finish_host_job(*this, *l, st);
     } catch (...) {
@@ -976,6 +1053,7 @@ void Context::resize_batch_host(JobDesc* descs, size_t n, int* status, int* devi
     const int G = device_count();
     const bool exact = mode.load() == 1;
     std::vector<std::string> errors{size_t(G), std::string()};
+    Context& self = *this;
     auto worker = [&](int g) {
         Device& dev = device(g);
         if (cudaSetDevice(dev.ordinal()) != cudaSuccess) {
@@ -986,40 +1064,61 @@ void Context::resize_batch_host(JobDesc* descs, size_t n, int* status, int* devi
         // are staged and enqueued on the other lanes
         std::lock_guard<std::mutex> batch_lock(dev.batch_mu);  // one batch at a time owns all lanes
         const int L = dev.lane_count();
-        std::vector<Lane*> lanes;
-        for (int k = 0; k < L; ++k) lanes.push_back(dev.acquire_lane());
-        std::vector<HostJobState> st(size_t(L), HostJobState{});
-        std::vector<long> inflight(size_t(L), -1);
-        auto drain = [&](int k) {
-            if (inflight[size_t(k)] < 0) return;
-            const size_t i = size_t(inflight[size_t(k)]);
-            try {
-                finish_host_job(*this, *lanes[size_t(k)], st[size_t(k)]);
-            } catch (const Error& e) {
-                status[i] = e.status;
-                errors[size_t(g)] = e.what;
+        std::vector<HostJobState> st{static_cast<size_t>(L)};   // declared before the lanes: destroyed after they are drained
+        std::vector<long> inflight(static_cast<size_t>(L), -1);
+        struct LaneSet {  // every lane of the device, handed back (drained) however the worker ends
+            Device& dev;
+            std::vector<Lane*> lanes;
+            ~LaneSet() {
+                for (Lane* l : lanes) {
+                    cudaStreamSynchronize(l->stream);
+                    dev.release_lane(l);
+                }
             }
-            inflight[size_t(k)] = -1;
-        };
-        int k = 0;
-        for (size_t i = size_t(g); i < n; i += size_t(G)) {
-            status[i] = kOk;
-            device_out[i] = g;
-            try {
-                validate_job(descs[i]);
-                if (trivial_resize(descs[i])) continue;
-                drain(k);
-                start_host_job(*this, dev, *lanes[size_t(k)], descs[i], &st[size_t(k)], exact);
-                inflight[size_t(k)] = long(i);
-                k = (k + 1) % L;
-            } catch (const Error& e) {
-                status[i] = e.status;
-                errors[size_t(g)] = e.what;
-                cudaStreamSynchronize(lanes[size_t(k)]->stream);
+        } held{dev, {}};
+        size_t next = size_t(g);                    // first job this worker has not accounted for yet
+        try {
+            for (int k = 0; k < L; ++k) held.lanes.push_back(dev.acquire_lane());
+            auto& lanes = held.lanes;
+            auto drain = [&](int k) {
+                if (inflight[size_t(k)] < 0) return;
+                const size_t i = size_t(inflight[size_t(k)]);
+                inflight[size_t(k)] = -1;
+                try {
+                    finish_host_job(self, *lanes[size_t(k)], st[size_t(k)]);
+                } catch (const Error& e) {
+                    status[i] = e.status;
+                    errors[size_t(g)] = e.what;
+                }
+            };
+            int k = 0;
+            for (size_t i = size_t(g); i < n; i += size_t(G)) {
+                next = i + size_t(G);
+                status[i] = kOk;
+                device_out[i] = g;
+                try {
+                    validate_job(descs[i]);
+                    if (trivial_resize(descs[i])) continue;
+                    drain(k);
+                    start_host_job(self, dev, *lanes[size_t(k)], descs[i], &st[size_t(k)], exact);
+                    inflight[size_t(k)] = long(i);
+                    k = (k + 1) % L;
+                } catch (const Error& e) {
+                    status[i] = e.status;
+                    errors[size_t(g)] = e.what;
+                    cudaStreamSynchronize(lanes[size_t(k)]->stream);
+                }
             }
+            for (int q = 0; q < L; ++q) drain(q);
+        } catch (...) {
+            // anything that is not an ikc::Error (std::bad_alloc from the planner's vectors, ...): nothing may cross the
+            // C boundary or escape a worker thread.  Jobs in flight and the jobs not reached yet are reported as failed.
+            const bool oom = [] { try { throw; } catch (const std::bad_alloc&) { return true; } catch (...) { return false; } }();
+            for (long i : inflight)
+                if (i >= 0) status[size_t(i)] = oom ? kOom : kCudaError;
+            for (size_t i = next; i < n; i += size_t(G)) status[i] = oom ? kOom : kCudaError;
+            errors[size_t(g)] = oom ? "out of host memory while planning a batch" : "unexpected exception in a batch worker";
         }
-        for (int q = 0; q < L; ++q) drain(q);
-        for (Lane* l : lanes) dev.release_lane(l);
     };
     if (G == 1) worker(0);
     else {

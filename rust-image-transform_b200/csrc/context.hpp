@@ -49,9 +49,15 @@ struct JobDesc {
 // Device copy of one PassPlan; frees its memory when the last holder lets go.
 struct DevTables {
     int device = -1;
-    void* base = nullptr;  // single allocation holding left | right | w | ring
+    void* base = nullptr;  // single stream-ordered allocation holding left | right | w | ring | band forms
+    cudaStream_t stream = nullptr;   // the device's table stream: the upload and, at destruction, the free are ordered on it
+    cudaEvent_t ready = nullptr;     // recorded after the upload; consumers' streams wait on it until it has been seen complete
+    std::atomic<bool> settled{false};
     DevPass pass{};
     std::shared_ptr<const PassPlan> host;
+    // Orders `s` after the upload (no host-side wait).  Holders must keep their reference until the work they enqueued
+    // has completed: the destructor returns the memory with cudaFreeAsync, which does not wait for other streams.
+    void wait_ready(cudaStream_t s);
     ~DevTables();
 };
 
@@ -140,8 +146,14 @@ private:
     std::condition_variable cv_;
     std::vector<std::unique_ptr<Lane>> lanes_;
     std::vector<Lane*> free_;
+    uint64_t next_ticket_ = 0, serving_ = 0;   // lanes are handed out in arrival order
     std::map<std::tuple<int, uint32_t, uint32_t>, std::shared_ptr<DevTables>> tabs_;
     std::vector<std::tuple<int, uint32_t, uint32_t>> tab_order_;
+    // Table uploads: one stream, a few reusable pinned staging blocks (each guarded by the event of its last copy).
+    struct StageBlock { void* p = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool busy = false; };
+    cudaStream_t table_stream_ = nullptr;
+    std::mutex stage_mu_;
+    std::vector<StageBlock> stage_;
 };
 
 class Context {

@@ -387,3 +387,27 @@ def test_u16_rasters_single_launch(ctx, ik, oracle, shape, filt):
     ctx.set_mode(ik.MODE_EXACT)
     assert np.array_equal(ctx.resize(src, dw, dh, filt), want)
     ctx.set_mode(ik.MODE_FAST)
+
+
+def test_table_misses_do_not_stall_the_other_callers(ik, oracle, tmp_path):
+    """A weight-table miss uploads on its own stream from pinned staging and frees stream-ordered (no device-wide
+    synchronisation), and lanes are handed out first come, first served.  8 threads x 300 random target sizes through
+    the C ABI (tools/table_miss_latency.c: every call a miss): p99 < 3 x p50.  (The old path -- cudaMalloc + blocking
+    copies + cudaDeviceSynchronize per miss, a synchronising cudaFree per eviction, unfair lane hand-out -- had a p99 of
+    12 ms against a p50 of 0.4 ms.)"""
+    import json, os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "rust-image-transform_b200")
+    exe = str(tmp_path / "table_miss_latency")
+    subprocess.check_call(["gcc", "-O2", "-std=c99", "-I" + os.path.join(root, "include"), os.path.join(root, "tools", "table_miss_latency.c"),
+                           "-o", exe, "-L" + libdir, "-limagekit_cuda", "-lpthread", "-Wl,-rpath," + libdir])
+    r = json.loads(subprocess.check_output([exe, "300"], timeout=300).decode().strip().splitlines()[-1])
+    print(r)
+    assert r["p99_ms"] < 3.0 * r["p50_ms"], r
+    # and the results are still right when tables are brand new
+    ctx = ik.Context([0])
+    src = splitmix_noise((300, 400, 3))
+    for dw, dh in [(173, 131), (201, 97), (88, 211)]:
+        got = ctx.resize(src, dw, dh, ik.FILTER_LANCZOS3)
+        _check_fast(got, oracle.resize_exact(src, dw, dh, oracle.LANCZOS3), (dw, dh))
+    ctx.close()
