@@ -130,6 +130,22 @@ IKC_API int ikc_set_mode(ikc_ctx* ctx, int mode);          /* enum ikc_mode; def
 IKC_API int ikc_get_mode(const ikc_ctx* ctx);
 /* Number of resampling-kernel launches issued through this context so far. */
 IKC_API uint64_t ikc_kernel_launches(const ikc_ctx* ctx);
+/* Counters a /metrics handler can export for the resize step (the reference counts requests and latencies around its
+ * handlers, src/lib.rs:318-338, :400-427; these are the ones only the library can see).  Monotonic since ikc_create;
+ * ikc_get_stats fills a snapshot (fields are read one by one: a consistent total is not guaranteed while calls run). */
+typedef struct ikc_stats_t {
+    uint64_t calls;               /* images handed to a host-buffer entry point (ikc_resize_*, ikc_resize_batch, ikc_submit_u8) */
+    uint64_t failed;              /* ... that returned an error */
+    uint64_t trivial;             /* ... answered without a kernel (empty or same-size rasters) */
+    uint64_t launches;            /* kernel launches, all entry points (== ikc_kernel_launches) */
+    uint64_t launches_banded8t, launches_banded8, launches_banded_f16, launches_ring, launches_up2, launches_tile,
+        launches_generic;         /* ... per kernel family */
+    uint64_t src_bytes, dst_bytes;   /* raster bytes read / written by host-buffer calls */
+    uint64_t busy_ns;             /* wall time inside host-buffer entry points, summed over calling threads */
+    uint64_t table_hits, table_misses;   /* per-device weight-table cache */
+    uint64_t submit_batches, submit_jobs;   /* ikc_submit_u8: launch groups formed / images they carried */
+} ikc_stats_t;
+IKC_API int ikc_get_stats(const ikc_ctx* ctx, ikc_stats_t* out);
 /* Thread-local text of the last failure on the calling thread ("" if none). */
 IKC_API const char* ikc_last_error(void);
 IKC_API int ikc_version(void);                               /* major*1000 + minor */
@@ -201,6 +217,14 @@ IKC_API uint32_t ikc_pass_band8t(int filter, uint32_t n_in, uint32_t n_out, uint
                                  size_t tiles_cap);
 
 /* ---- host-buffer entry points (the drop-in path; include H2D + D2H) -------------------------- */
+
+/* Same contract and result as ikc_resize_u8 / ikc_resize_convert_u8 (channels may be IKC_CHANNELS(src, dst)), for
+ * handler threads that each resize one image at a time (src/lib.rs:180, :286): calls that arrive while the device is
+ * busy are coalesced -- staged into one pinned block, uploaded with one copy, planned together and run as ONE launch per
+ * kernel variant -- instead of one plan + descriptor upload + launch + two copies each.  Blocks until this caller's image
+ * is done.  A lone caller pays no waiting window: whatever is queued when the dispatcher comes round forms the group. */
+IKC_API int ikc_submit_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch, int channels,
+                          uint8_t* dst, uint32_t dw, uint32_t dh, size_t dst_pitch, int filter);
 
 /* Replaces imageops::resize(&buf, dw, dh, filter) for 8-bit rasters (image 0.25.8
  * imageops/sample.rs; reached from src/transform.rs:85-89 via resize_exact).  `src`/`dst` are

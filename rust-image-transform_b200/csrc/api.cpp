@@ -207,6 +207,34 @@ int ikc_resize_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, si
     });
 }
 
+int ikc_submit_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch, int channels, uint8_t* dst,
+                  uint32_t dw, uint32_t dh, size_t dst_pitch, int filter) {
+    if (!ctx) {
+        set_last_error("ctx is null");
+        return IKC_ERR_INVALID_ARG;
+    }
+    return guarded([&] { ctx->impl.submit_host(make_desc(src, sw, sh, src_pitch, channels, dst, dw, dh, dst_pitch, filter, 1)); });
+}
+
+int ikc_get_stats(const ikc_ctx* ctx, ikc_stats_t* out) {
+    if (!ctx || !out) {
+        set_last_error("ctx or out is null");
+        return IKC_ERR_INVALID_ARG;
+    }
+    const Stats& s = ctx->impl.stats;
+    auto ld = [](const std::atomic<uint64_t>& a) { return a.load(std::memory_order_relaxed); };
+    out->calls = ld(s.calls); out->failed = ld(s.failed); out->trivial = ld(s.trivial);
+    out->launches = ctx->impl.launches.load(std::memory_order_relaxed);
+    out->launches_banded8t = ld(s.launches_by_family[0]); out->launches_banded8 = ld(s.launches_by_family[1]);
+    out->launches_banded_f16 = ld(s.launches_by_family[2]); out->launches_ring = ld(s.launches_by_family[3]);
+    out->launches_up2 = ld(s.launches_by_family[4]); out->launches_tile = ld(s.launches_by_family[5]);
+    out->launches_generic = ld(s.launches_by_family[6]);
+    out->src_bytes = ld(s.src_bytes); out->dst_bytes = ld(s.dst_bytes); out->busy_ns = ld(s.busy_ns);
+    out->table_hits = ld(s.table_hits); out->table_misses = ld(s.table_misses);
+    out->submit_batches = ld(s.submit_batches); out->submit_jobs = ld(s.submit_jobs);
+    return IKC_OK;
+}
+
 int ikc_resize_convert_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch, int src_channels,
                           uint8_t* dst, uint32_t dw, uint32_t dh, size_t dst_pitch, int dst_channels, int filter) {
     if (!ctx) {

@@ -1,6 +1,9 @@
 // context.cpp -- see context.hpp.
 #include "context.hpp"
 
+#include <chrono>
+#include <deque>
+
 #include <algorithm>
 #include <cstring>
 #include <thread>
@@ -276,8 +279,12 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     {
         std::lock_guard<std::mutex> lk(mu_);
         auto it = tabs_.find(key);
-        if (it != tabs_.end()) return it->second;
+        if (it != tabs_.end()) {
+            ctx_->stats.table_hits.fetch_add(1, std::memory_order_relaxed);
+            return it->second;
+        }
     }
+    ctx_->stats.table_misses.fetch_add(1, std::memory_order_relaxed);
     auto host = ctx_->pass(filter, n_in, n_out);
     if (!host) fail(kInvalidArg, "cannot plan pass");
     // One stream-ordered allocation (left | right | w | ring forms | 2x-upscale pairs | band forms, each 256-byte aligned),
@@ -428,7 +435,10 @@ Context::Context(const int* ids, int n) : copy_pool(copy_helpers()) {
     }
 }
 
-Context::~Context() { devs_.clear(); }
+Context::~Context() {
+    submit_.clear();  // joins the dispatcher threads before the devices go
+    devs_.clear();
+}
 
 std::shared_ptr<const PassPlan> Context::pass(int filter, uint32_t n_in, uint32_t n_out) {
     const auto key = std::make_tuple(filter, n_in, n_out);
@@ -848,10 +858,13 @@ void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, 
         else check_cuda(launch_fused(g.channels, g.kv, g.kh, g.sv, g.sh, g.convert, d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");
         off += (sizeof(WorkItem) * g.items.size() + 15) & ~size_t(15);
         launches.fetch_add(1, std::memory_order_relaxed);
+        const int family = g.band8t ? 0 : g.band8_limbs ? 1 : g.band_n ? 2 : g.up_taps ? 4 : g.kv == 0 ? 5 : 3;
+        stats.launches_by_family[family].fetch_add(1, std::memory_order_relaxed);
     }
     for (int idx : lp.generic_jobs) {
         check_cuda(launch_generic(lp.jobs[idx], exact, stream), "launch generic kernels");
         launches.fetch_add(2, std::memory_order_relaxed);
+        stats.launches_by_family[6].fetch_add(2, std::memory_order_relaxed);
     }
 }
 
@@ -1030,9 +1043,33 @@ bool trivial_resize(const JobDesc& d) {
 
 }  // namespace
 
+namespace {
+struct CallTimer {  // one host-buffer call: counted, timed, failures noticed through unwinding
+    Stats& s;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    bool ok = false;
+    explicit CallTimer(Stats& st, uint64_t images = 1) : s(st) { s.calls.fetch_add(images, std::memory_order_relaxed); }
+    ~CallTimer() {
+        s.busy_ns.fetch_add(uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count()),
+                            std::memory_order_relaxed);
+        if (!ok) s.failed.fetch_add(1, std::memory_order_relaxed);
+    }
+};
+void count_bytes(Stats& s, const JobDesc& d) {
+    s.src_bytes.fetch_add(uint64_t(d.sw) * d.sh * d.channels * d.bps, std::memory_order_relaxed);
+    s.dst_bytes.fetch_add(uint64_t(d.dw) * d.dh * d.oc() * d.bps, std::memory_order_relaxed);
+}
+}  // namespace
+
 void Context::resize_host(const JobDesc& d, int* device_index_out) {
+    CallTimer timer(stats);
     validate_job(d);
-    if (trivial_resize(d)) return;
+    if (trivial_resize(d)) {
+        stats.trivial.fetch_add(1, std::memory_order_relaxed);
+        timer.ok = true;
+        return;
+    }
+    count_bytes(stats, d);
     Device& dev = device(next_device());
     if (device_index_out) *device_index_out = dev.index();
     check_cuda(cudaSetDevice(dev.ordinal()), "cudaSetDevice");
@@ -1047,9 +1084,12 @@ void Context::resize_host(const JobDesc& d, int* device_index_out) {
         throw;
     }
     dev.release_lane(l);
+    timer.ok = true;
 }
 
 void Context::resize_batch_host(JobDesc* descs, size_t n, int* status, int* device_out) {
+    CallTimer timer(stats, n);
+    timer.ok = true;  // (per-job failures are counted below)
     const int G = device_count();
     const bool exact = mode.load() == 1;
     std::vector<std::string> errors{size_t(G), std::string()};
@@ -1098,7 +1138,11 @@ void Context::resize_batch_host(JobDesc* descs, size_t n, int* status, int* devi
                 device_out[i] = g;
                 try {
                     validate_job(descs[i]);
-                    if (trivial_resize(descs[i])) continue;
+                    if (trivial_resize(descs[i])) {
+                        stats.trivial.fetch_add(1, std::memory_order_relaxed);
+                        continue;
+                    }
+                    count_bytes(stats, descs[i]);
                     drain(k);
                     start_host_job(self, dev, *lanes[size_t(k)], descs[i], &st[size_t(k)], exact);
                     inflight[size_t(k)] = long(i);
@@ -1127,6 +1171,182 @@ void Context::resize_batch_host(JobDesc* descs, size_t n, int* status, int* devi
         for (auto& t : th) t.join();
     }
     for (auto& e : errors) if (!e.empty()) set_last_error(e);
+    for (size_t i = 0; i < n; ++i)
+        if (status[i] != kOk) stats.failed.fetch_add(1, std::memory_order_relaxed);
+}
+
+// ---- coalescing submit queue ---------------------------------------------------------------------
+
+void Context::resize_group_host(Device& dev, const JobDesc* descs, size_t n, int* status, std::string* errors) {
+    check_cuda(cudaSetDevice(dev.ordinal()), "cudaSetDevice");
+    struct Slot { size_t in_off = 0, out_off = 0, in_pitch = 0, out_pitch = 0; bool live = false; };
+    std::vector<Slot> slot(n);
+    size_t total_in = 0, total_out = 0;
+    for (size_t i = 0; i < n; ++i) {
+        status[i] = kOk;
+        try {
+            const JobDesc& d = descs[i];
+            validate_job(d);
+            if (trivial_resize(d)) {
+                stats.trivial.fetch_add(1, std::memory_order_relaxed);
+                continue;
+            }
+            count_bytes(stats, d);
+            Slot& s = slot[i];
+            s.in_pitch = device_pitch(size_t(d.sw) * d.channels * d.bps);
+            s.out_pitch = device_pitch(size_t(d.dw) * d.oc() * d.bps);
+            s.in_off = total_in;
+            s.out_off = total_out;
+            total_in += s.in_pitch * d.sh;
+            total_out += s.out_pitch * d.dh;
+            s.live = true;
+        } catch (const Error& e) {
+            status[i] = e.status;
+            errors[i] = e.what;
+        }
+    }
+    if (total_in == 0) return;
+    LaunchPlan lp;  // (declared before the lane guard: its table references go only after the guard has drained the stream)
+    Lane* l = dev.acquire_lane();
+    struct Release { Device& d; Lane* l; ~Release() { cudaStreamSynchronize(l->stream); d.release_lane(l); } } release{dev, l};
+    l->h_in.reserve(total_in);
+    l->d_in.reserve(total_in);
+    l->h_out.reserve(total_out);
+    l->d_out.reserve(total_out);
+    uint8_t* hin = static_cast<uint8_t*>(l->h_in.p);
+    // inputs: every image's rows into one pinned block laid out like the device buffer, then ONE copy
+    for (size_t i = 0; i < n; ++i) {
+        if (!slot[i].live) continue;
+        const JobDesc& d = descs[i];
+        pooled_copy_rows(copy_pool, hin + slot[i].in_off, slot[i].in_pitch, static_cast<const uint8_t*>(d.src), d.src_pitch,
+                         size_t(d.sw) * d.channels * d.bps, d.sh);
+    }
+    check_cuda(cudaMemcpyAsync(l->d_in.p, hin, total_in, cudaMemcpyHostToDevice, l->stream), "H2D copy (group)");
+    std::vector<JobDesc> dj;
+    std::vector<size_t> who;
+    for (size_t i = 0; i < n; ++i) {
+        if (!slot[i].live) continue;
+        JobDesc j = descs[i];
+        j.src = static_cast<uint8_t*>(l->d_in.p) + slot[i].in_off;
+        j.dst = static_cast<uint8_t*>(l->d_out.p) + slot[i].out_off;
+        j.src_pitch = slot[i].in_pitch;
+        j.dst_pitch = slot[i].out_pitch;
+        dj.push_back(j);
+        who.push_back(i);
+    }
+    const bool exact = mode.load() == 1;
+    std::vector<int> st(dj.size(), kOk);
+    lp = plan(dev, dj.data(), dj.size(), st.data(), exact);
+    for (size_t k = 0; k < dj.size(); ++k)
+        if (st[k] != kOk) {
+            status[who[k]] = st[k];
+            errors[who[k]] = last_error();
+            slot[who[k]].live = false;
+        }
+    enqueue(dev, lp, l->h_desc, l->d_desc, l->d_scratch, l->stream, exact);
+    check_cuda(cudaMemcpyAsync(l->h_out.p, l->d_out.p, total_out, cudaMemcpyDeviceToHost, l->stream), "D2H copy (group)");
+    check_cuda(cudaStreamSynchronize(l->stream), "resize (group sync)");
+    const uint8_t* hout = static_cast<const uint8_t*>(l->h_out.p);
+    for (size_t i = 0; i < n; ++i) {
+        if (!slot[i].live) continue;
+        const JobDesc& d = descs[i];
+        pooled_copy_rows(copy_pool, static_cast<uint8_t*>(d.dst), d.dst_pitch, hout + slot[i].out_off, slot[i].out_pitch,
+                         size_t(d.dw) * d.oc() * d.bps, d.dh);
+    }
+}
+
+// Per device: callers enqueue a job and sleep; two dispatcher threads (so that one group's staging overlaps the other's
+// GPU work) each take whatever has queued up -- one job when the service is idle, dozens under load -- and run it as one
+// group.
+class SubmitQueue {
+public:
+    SubmitQueue(Context* ctx, Device* dev) : ctx_(ctx), dev_(dev) {
+        for (int i = 0; i < 2; ++i) threads_.emplace_back([this] { run(); });
+    }
+    ~SubmitQueue() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    void submit(const JobDesc& d) {
+        Pending p{d, kOk, {}, false};
+        std::unique_lock<std::mutex> lk(mu_);
+        q_.push_back(&p);
+        cv_.notify_one();
+        done_cv_.wait(lk, [&] { return p.done; });
+        lk.unlock();
+        if (p.status != kOk) fail(Status(p.status), p.err);
+    }
+
+private:
+    struct Pending { JobDesc d; int status; std::string err; bool done; };
+    static constexpr size_t kMaxJobs = 64, kMaxBytes = size_t(256) << 20;
+    void run() {
+        for (;;) {
+            std::vector<Pending*> group;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;  // stopping
+                size_t bytes = 0;
+                while (!q_.empty() && group.size() < kMaxJobs && bytes < kMaxBytes) {
+                    Pending* p = q_.front();
+                    q_.pop_front();
+                    bytes += size_t(p->d.sw) * p->d.sh * size_t(p->d.channels & 0xff) * p->d.bps;
+                    group.push_back(p);
+                }
+            }
+            const size_t n = group.size();
+            std::vector<JobDesc> descs(n);
+            std::vector<int> st(n, kOk);
+            std::vector<std::string> errs(n);
+            for (size_t i = 0; i < n; ++i) descs[i] = group[i]->d;
+            try {
+                ctx_->resize_group_host(*dev_, descs.data(), n, st.data(), errs.data());
+            } catch (const Error& e) {
+                for (size_t i = 0; i < n; ++i) { st[i] = e.status; errs[i] = e.what; }
+            } catch (const std::bad_alloc&) {
+                for (size_t i = 0; i < n; ++i) { st[i] = kOom; errs[i] = "out of host memory in the submit queue"; }
+            } catch (...) {
+                for (size_t i = 0; i < n; ++i) { st[i] = kCudaError; errs[i] = "unexpected exception in the submit queue"; }
+            }
+            ctx_->stats.submit_batches.fetch_add(1, std::memory_order_relaxed);
+            ctx_->stats.submit_jobs.fetch_add(n, std::memory_order_relaxed);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                for (size_t i = 0; i < n; ++i) {
+                    group[i]->status = st[i];
+                    group[i]->err = std::move(errs[i]);
+                    group[i]->done = true;
+                }
+            }
+            done_cv_.notify_all();
+        }
+    }
+    Context* ctx_;
+    Device* dev_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::deque<Pending*> q_;
+    std::vector<std::thread> threads_;
+    bool stop_ = false;
+};
+
+void Context::submit_host(const JobDesc& d) {
+    CallTimer timer(stats);
+    SubmitQueue* q = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(submit_mu_);
+        if (submit_.empty()) submit_.resize(devs_.size());
+        const size_t g = size_t(next_device());
+        if (!submit_[g]) submit_[g] = std::make_unique<SubmitQueue>(this, devs_[g].get());
+        q = submit_[g].get();
+    }
+    q->submit(d);
+    timer.ok = true;
 }
 
 }  // namespace ikc

@@ -156,6 +156,17 @@ private:
     std::vector<StageBlock> stage_;
 };
 
+// Monotonic counters behind ikc_get_stats.
+struct Stats {
+    std::atomic<uint64_t> calls{0}, failed{0}, trivial{0};
+    std::atomic<uint64_t> launches_by_family[7]{};   // banded8t, banded8, banded f16, ring, up2, tile, generic
+    std::atomic<uint64_t> src_bytes{0}, dst_bytes{0}, busy_ns{0};
+    std::atomic<uint64_t> table_hits{0}, table_misses{0};
+    std::atomic<uint64_t> submit_batches{0}, submit_jobs{0};
+};
+
+class SubmitQueue;
+
 class Context {
 public:
     Context(const int* ids, int n);
@@ -168,6 +179,7 @@ public:
 
     std::atomic<int> mode{0};
     std::atomic<uint64_t> launches{0};
+    Stats stats;
     CopyPool copy_pool;
 
     // Plan device-resident jobs for `dev` (device pointers in descs).  Per-job failures are
@@ -184,6 +196,11 @@ public:
     // Host-buffer resize of one image through a lane of some device.
     void resize_host(const JobDesc& d, int* device_index_out);
     void resize_batch_host(JobDesc* descs, size_t n, int* status, int* device_out);
+    // Host-buffer resize through the coalescing submit queue (ikc_submit_u8); throws Error on this job's failure.
+    void submit_host(const JobDesc& d);
+    // One group of host jobs on one lane of `dev`: one staged upload, one plan, one launch per kernel variant, one
+    // download.  Per-job results in status / errors (size n).
+    void resize_group_host(Device& dev, const JobDesc* descs, size_t n, int* status, std::string* errors);
 
 private:
     std::vector<std::unique_ptr<Device>> devs_;
@@ -191,6 +208,8 @@ private:
     std::mutex pass_mu_;
     std::map<std::tuple<int, uint32_t, uint32_t>, std::shared_ptr<const PassPlan>> passes_;
     std::vector<std::tuple<int, uint32_t, uint32_t>> pass_order_;
+    std::mutex submit_mu_;
+    std::vector<std::unique_ptr<SubmitQueue>> submit_;   // one per device, created on first use
 };
 
 // Validation shared by every entry point; throws Error.

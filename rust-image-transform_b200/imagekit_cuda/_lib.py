@@ -22,7 +22,7 @@ MAX_DIM, MAX_PIXELS = 65535, 1 << 28  # IKC_MAX_DIM, IKC_MAX_PIXELS
 # every symbol include/imagekit_cuda.h declares
 EXPORTS = [
     "ikc_create", "ikc_destroy", "ikc_device_count", "ikc_set_mode", "ikc_get_mode", "ikc_kernel_launches",
-    "ikc_last_error", "ikc_version", "ikc_target_dims", "ikc_check_dims", "ikc_pass_table", "ikc_pass_info", "ikc_pass_band", "ikc_pass_band8", "ikc_pass_band8t", "ikc_resize_u8", "ikc_resize_u16",
+    "ikc_last_error", "ikc_version", "ikc_target_dims", "ikc_check_dims", "ikc_pass_table", "ikc_pass_info", "ikc_pass_band", "ikc_pass_band8", "ikc_pass_band8t", "ikc_resize_u8", "ikc_submit_u8", "ikc_get_stats", "ikc_resize_u16",
     "ikc_resize_convert_u8", "ikc_resize_image_u8", "ikc_resize_batch", "ikc_host_alloc", "ikc_host_free", "ikc_host_register", "ikc_host_unregister", "ikc_resize_u8_device",
     "ikc_batch_prepare", "ikc_batch_launch", "ikc_batch_launch_count", "ikc_batch_describe", "ikc_batch_free",
 ]
@@ -36,6 +36,14 @@ class Job(C.Structure):
         ("src_pitch", C.c_size_t), ("dst_pitch", C.c_size_t),
         ("channels", C.c_int32), ("filter", C.c_int32), ("status", C.c_int32), ("device", C.c_int32),
     ]
+
+
+class Stats(C.Structure):
+    """struct ikc_stats_t"""
+    _fields_ = [(n, C.c_uint64) for n in (
+        "calls", "failed", "trivial", "launches", "launches_banded8t", "launches_banded8", "launches_banded_f16", "launches_ring",
+        "launches_up2", "launches_tile", "launches_generic", "src_bytes", "dst_bytes", "busy_ns", "table_hits", "table_misses",
+        "submit_batches", "submit_jobs")]
 
 
 class PassInfo(C.Structure):
@@ -91,6 +99,10 @@ def load() -> C.CDLL:
     L.ikc_pass_info.restype = i32
     L.ikc_resize_u8.argtypes = [vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32]
     L.ikc_resize_u8.restype = i32
+    L.ikc_submit_u8.argtypes = [vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32]
+    L.ikc_submit_u8.restype = i32
+    L.ikc_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.ikc_get_stats.restype = i32
     L.ikc_resize_convert_u8.argtypes = [vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32, i32]
     L.ikc_resize_convert_u8.restype = i32
     L.ikc_resize_u16.argtypes = [vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32]

@@ -216,6 +216,26 @@ class Context:
             return out
         return dst[:, :, 0] if squeeze else dst
 
+    def submit(self, src: np.ndarray, dw: int, dh: int, filt: int = _lib.FILTER_LANCZOS3, out_channels: int | None = None) -> np.ndarray:
+        """resize() for handler threads that each bring one 8-bit image: concurrent calls are coalesced into shared
+        uploads and launches (ikc_submit_u8).  Same result as resize()."""
+        s = np.ascontiguousarray(src[:, :, None] if src.ndim == 2 else src)
+        if s.ndim != 3 or s.dtype != np.uint8:
+            raise ImageKitError(_lib.ERR_UNSUPPORTED, "submit() takes an 8-bit HxW or HxWxC array")
+        sh, sw, ch = s.shape
+        co = ch if out_channels is None else out_channels
+        check_dims(sw, sh, min(dw, 0xFFFFFFFF), min(dh, 0xFFFFFFFF))  # before allocating the result
+        dst = np.empty((dh, dw, co), np.uint8)
+        _check(_lib.load().ikc_submit_u8(self._h, s.ctypes.data, sw, sh, sw * ch, ch | (co << 8) if co != ch else ch, dst.ctypes.data,
+                                         dw, dh, dw * co, filt))
+        return dst[:, :, 0] if src.ndim == 2 and co == 1 else dst
+
+    def stats(self) -> dict:
+        """Counters for a /metrics handler (ikc_get_stats)."""
+        st = _lib.Stats()
+        _check(_lib.load().ikc_get_stats(self._h, C.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in _lib.Stats._fields_}
+
     def _resize_convert(self, src, dw, dh, filt, out, co):
         s = np.ascontiguousarray(src[:, :, None] if src.ndim == 2 else src)
         if s.ndim != 3 or s.dtype != np.uint8:

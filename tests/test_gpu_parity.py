@@ -411,3 +411,48 @@ def test_table_misses_do_not_stall_the_other_callers(ik, oracle, tmp_path):
         got = ctx.resize(src, dw, dh, ik.FILTER_LANCZOS3)
         _check_fast(got, oracle.resize_exact(src, dw, dh, oracle.LANCZOS3), (dw, dh))
     ctx.close()
+
+
+def test_submit_queue_coalesces_concurrent_callers(ik, oracle):
+    """ikc_submit_u8: handler threads that each bring one image share uploads, plans and launches.  Results are those of
+    ikc_resize_u8; the counters (ikc_get_stats) show fewer launch groups than images under concurrency, and one group per
+    image for a lone caller."""
+    import threading
+    ctx = ik.Context([0])
+    shapes = [(480, 640, 3, 200, 150), (300, 400, 4, 200, 150), (240, 320, 3, 100, 75), (600, 800, 3, 160, 120), (96, 128, 1, 61, 47),
+              (240, 320, 3, 640, 480), (64, 64, 3, 64, 64), (200, 300, 2, 150, 100)]
+    srcs = [splitmix_noise((h, w, c), image_id=90 + i) for i, (h, w, c, _, _) in enumerate(shapes)]
+    want = [oracle.resize_exact(s, dw, dh, oracle.LANCZOS3) for s, (_, _, _, dw, dh) in zip(srcs, shapes)]
+    # a lone caller: every image its own group
+    for s, (h, w, c, dw, dh), exp in zip(srcs, shapes, want):
+        got = ctx.submit(s, dw, dh, ik.FILTER_LANCZOS3)
+        hist = delta_histogram(got, exp)
+        assert max(abs(k) for k in hist) <= TOL, ((h, w, c, dw, dh), hist)
+    st0 = ctx.stats()
+    assert st0["submit_jobs"] == len(shapes) == st0["submit_batches"] and st0["calls"] == len(shapes) and st0["failed"] == 0
+    assert st0["trivial"] == 1 and st0["launches"] >= len(shapes) - 1 and st0["src_bytes"] > 0 and st0["busy_ns"] > 0
+    # 16 threads x 12 images at once
+    errors, rounds = [], 12
+    def worker(t):
+        try:
+            for r in range(rounds):
+                i = (t + r) % len(shapes)
+                h, w, c, dw, dh = shapes[i]
+                got = ctx.submit(srcs[i], dw, dh, ik.FILTER_LANCZOS3)
+                hist = delta_histogram(got, want[i])
+                assert max(abs(k) for k in hist) <= TOL, (shapes[i], hist)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(16)]
+    for x in th: x.start()
+    for x in th: x.join()
+    assert not errors, errors[:3]
+    st1 = ctx.stats()
+    jobs = st1["submit_jobs"] - st0["submit_jobs"]
+    groups = st1["submit_batches"] - st0["submit_batches"]
+    assert jobs == 16 * rounds and groups < jobs, (jobs, groups)
+    # a bad request fails alone
+    with pytest.raises(ik.ImageKitError):
+        ctx.submit(srcs[0], 100, 10, 9)      # unknown filter: rejected inside the library
+    assert ctx.stats()["failed"] >= 1
+    ctx.close()
