@@ -49,11 +49,21 @@ fn row_bytes(width: u32, ch: u32, bytes_per_sample: usize) -> usize {
 fn resize_u8(raw: &[u8], sw: u32, sh: u32, ch: u32, dw: u32, dh: u32) -> Result<Vec<u8>, String> {
     check_dims(sw, sh, dw, dh)?;
     let mut out = vec![0u8; row_bytes(dw, ch, 1) * dh as usize];
+    // ikc_submit_u8, not ikc_resize_u8: the handlers (src/lib.rs:180, :286) call this once per request from many tokio
+    // workers; the library coalesces the calls that arrive while the GPU is busy into shared uploads and launches.
     let rc = unsafe {
-        ffi::ikc_resize_u8(ctx()?, raw.as_ptr(), sw, sh, row_bytes(sw, ch, 1), ch as i32, out.as_mut_ptr(), dw, dh,
+        ffi::ikc_submit_u8(ctx()?, raw.as_ptr(), sw, sh, row_bytes(sw, ch, 1), ch as i32, out.as_mut_ptr(), dw, dh,
                            row_bytes(dw, ch, 1), ffi::IKC_FILTER_LANCZOS3)
     };
     if rc == ffi::IKC_OK { Ok(out) } else { Err(last_error()) }
+}
+
+/// Counters of the resize step for imagekit's `/metrics` handler (src/lib.rs:318-338 renders the Prometheus text):
+/// images, failures, kernel launches per family, raster bytes, busy time, weight-table hits / misses, coalescing.
+pub fn stats() -> Result<ffi::ikc_stats_t, String> {
+    let mut s = ffi::ikc_stats_t::default();
+    let rc = unsafe { ffi::ikc_get_stats(ctx()?, &mut s) };
+    if rc == ffi::IKC_OK { Ok(s) } else { Err(last_error()) }
 }
 
 fn resize_u16(raw: &[u16], sw: u32, sh: u32, ch: u32, dw: u32, dh: u32) -> Result<Vec<u16>, String> {
