@@ -456,3 +456,20 @@ def test_submit_queue_coalesces_concurrent_callers(ik, oracle):
         ctx.submit(srcs[0], 100, 10, 9)      # unknown filter: rejected inside the library
     assert ctx.stats()["failed"] >= 1
     ctx.close()
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "reference_image_0_25_8.npz")),
+                    reason="reference_image_0_25_8.npz not generated yet: needs cargo (oracle/ref_harness)")
+def test_reference_pinned_vectors_on_the_gpu(ctx, ik):
+    """The GPU twin of tests/test_oracle_props.py::test_reference_pinned_vectors: EXACT mode reproduces the real
+    `image` 0.25.8 bit for bit, FAST mode within +-1."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_image_0_25_8.npz"))
+    for nme in sorted({k.split("/")[0] for k in g.files}):
+        src, ref = g[nme + "/src"], g[nme + "/ref"]
+        filt = int(g[nme + "/meta"][2])
+        dh, dw = ref.shape[:2]
+        ctx.set_mode(ik.MODE_EXACT)
+        assert np.array_equal(ctx.resize(src, dw, dh, filt), ref), nme
+        ctx.set_mode(ik.MODE_FAST)
+        assert np.abs(ctx.resize(src, dw, dh, filt).astype(int) - ref.astype(int)).max() <= TOL, nme
