@@ -235,6 +235,104 @@ def run_cfg3_shard(ik, ctx, torch, dev, dist, rank, world, barrier, args):
                     "api": "one ikc_resize_batch call per rank over its shard, pinned host buffers"}}
 
 
+def run_cfg5_upload(ik, ctx, dist, dev, rank, world, barrier, args):
+    """BASELINE config 5, the /upload shape (reference src/lib.rs:246-309): CPU decode -> GPU resize -> CPU webp q=80 encode
+    over 256 synthetic 8 MP JPEGs, split over the ranks (one GPU each) and, inside a rank, over its share of the host
+    cores.  Every worker thread runs the library's split call: decode(i + 1) and encode(i - 1) happen between
+    ikc_resize_begin_u8(i) and ikc_resize_end(i), so the upload, kernel and download of image i hide behind the codecs;
+    the resize stores rgb8 directly (to_rgb8() fused).  Pillow stands in for the reference's image / webp crates."""
+    import io
+    from concurrent.futures import ThreadPoolExecutor
+    from PIL import Image
+    from imagekit_cuda.sharding import aggregate_throughput, shard_indices
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import photo_like
+    total, width, w8, h8 = args.upload_images, 800, 3264, 2448
+    base = photo_like((h8, w8, 3), seed=3)
+    jpegs = []
+    for i in range(4):
+        buf = io.BytesIO()
+        Image.fromarray(np.roll(base, 211 * i, axis=1)).save(buf, "JPEG", quality=90)
+        jpegs.append(buf.getvalue())
+    mine = shard_indices(total, world, rank)
+    threads = max(2, (os.cpu_count() or 8) // world)
+    tw, th, _ = ik.target_dims(w8, h8, width, None)
+    stage = {"decode": 0.0, "resize_queue": 0.0, "resize_wait": 0.0, "encode": 0.0}
+    lock = __import__("threading").Lock()
+
+    def decode(b):
+        im = Image.open(io.BytesIO(b))
+        im.draft("RGB", (w8, h8))
+        return np.asarray(im.convert("RGB"))
+
+    def encode(a):
+        buf = io.BytesIO()
+        Image.fromarray(a).save(buf, "WEBP", quality=80, method=4)
+        return buf.tell()
+
+    def worker(idx):
+        # one ticket per thread at a time (a ticket holds a lane): decode(i + 1) runs while image i is on the GPU, then
+        # end(i), begin(i + 1), and encode(i) runs while image i + 1 is on the GPU
+        acc = dict.fromkeys(stage, 0.0)
+        prev, nbytes = None, 0
+        for i in idx:
+            t0 = time.perf_counter()
+            d = decode(jpegs[i % len(jpegs)])
+            t1 = time.perf_counter()
+            out = prev.end() if prev is not None else None
+            t2 = time.perf_counter()
+            prev = ctx.resize_begin(d, tw, th, ik.FILTER_LANCZOS3, out_channels=3)
+            t3 = time.perf_counter()
+            if out is not None:
+                nbytes += encode(out)
+            t4 = time.perf_counter()
+            acc["decode"] += t1 - t0
+            acc["resize_wait"] += t2 - t1
+            acc["resize_queue"] += t3 - t2
+            acc["encode"] += t4 - t3
+        if prev is not None:
+            t2 = time.perf_counter()
+            out = prev.end()
+            t3 = time.perf_counter()
+            nbytes += encode(out)
+            acc["resize_wait"] += t3 - t2
+            acc["encode"] += time.perf_counter() - t3
+        with lock:
+            for k in stage:
+                stage[k] += acc[k]
+        return nbytes
+
+    pool = ThreadPoolExecutor(threads)
+    parts = [mine[k::threads] for k in range(threads)]
+    list(pool.map(worker, [p[:1] for p in parts if len(p)]))   # warm-up: lane buffers, tables, codec imports
+    for k in stage:
+        stage[k] = 0.0
+    barrier()
+    t0 = time.perf_counter()
+    out_bytes = sum(pool.map(worker, parts))
+    dt = time.perf_counter() - t0
+    barrier()
+    _, ms_max, per_s = aggregate_throughput(float(len(mine)), dt * 1e3, dist, dev)
+    busy = sum(stage.values()) or 1.0
+    res = {"workload": f"cfg5: {total} x 8 MP JPEG (3264x2448) -> w={width} Lanczos3 -> webp q=80, {world} GPU(s)",
+           "uploads_per_s": per_s, "seconds": ms_max / 1e3, "uploads_this_rank": len(mine), "worker_threads_this_rank": threads,
+           "stage_seconds_per_upload_this_rank": {k: v / max(1, len(mine)) for k, v in stage.items()},
+           "stage_share_of_worker_time_this_rank": {k: v / busy for k, v in stage.items()},
+           "out_bytes_mean": out_bytes / max(1, len(mine)),
+           "api": "ikc_resize_begin_u8 / ikc_resize_end (split call, pageable decoder output, rgb8 store fused), one upload in flight per worker"}
+    if rank == 0:   # the same pipeline with the reference's CPU resize (oracle port), bounded sample
+        from oracle import oracle
+        sample = min(len(mine), 2 * threads)
+
+        def cpu_one(i):
+            return encode(oracle.resize_image(decode(jpegs[i % len(jpegs)]), width, None))
+        t0 = time.perf_counter()
+        list(pool.map(cpu_one, range(sample)))
+        res["cpu_resize_uploads_per_s"] = {"value": sample / (time.perf_counter() - t0), "threads": threads, "sample": f"{sample} uploads",
+                                           "kind": "port"}
+    return res
+
+
 def run_inprocess(ik, n_dev, sw, sh, ch, dw, dh, filt, args):
     """Rank 0 only, the other ranks idle at a barrier: ONE context over all the box's GPUs, one ikc_resize_batch over
     8 images per device.  Checks the round-robin placement (job i -> device i mod N) and that every device returns
@@ -283,6 +381,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-shard", action="store_true", help="skip the cfg3_shard leg (1024 thumbnails, strong scaling)")
     ap.add_argument("--shard-images", type=int, default=1024)
+    ap.add_argument("--no-upload", action="store_true", help="skip the cfg5_upload leg (decode -> resize -> webp encode of 8 MP JPEGs)")
+    ap.add_argument("--upload-images", type=int, default=256)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -440,6 +540,15 @@ def main():
     if not args.no_shard:
         cfg3_shard = run_cfg3_shard(ik, ctx, torch, dev, dist, rank, world, barrier, args)
 
+    # ---- BASELINE config 5 as it is stated: 256 x 8 MP JPEG uploads, CPU decode -> GPU resize -> CPU webp encode,
+    # split over the ranks; the library's begin / end call lets every worker hide the GPU leg behind the codecs
+    cfg5_upload = None
+    if not args.no_upload:
+        try:
+            cfg5_upload = run_cfg5_upload(ik, ctx, dist, dev, rank, world, barrier, args)
+        except ImportError as e:   # no Pillow on this box: the codecs are the stand-ins, not the product
+            cfg5_upload = {"unavailable": f"{e}"}
+
     # ---- the product's own multi-GPU entry point: ONE context over all N devices in ONE process (rank 0),
     # ikc_resize_batch shards job i -> device i mod N with one worker thread per device
     e2e_inprocess = None
@@ -473,7 +582,9 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        # the arithmetic the path computes in: the tensor-core kernels run the vertical pass as u8 x s8 -> s32 integer
+        # products (exact) and the horizontal pass in f32; the CUDA-core kernels are f32 throughout
+        "dtype": "s32+f32" if "banded8" in prepared.describe() else "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "filter": FILTER_NAMES[filt]},
         "run": {"images_per_step_per_gpu": batch, "layout": "u8 interleaved, tight pitch, device-resident",
                 "l2": f"working set {(algo_bytes) / 1e6:.0f} MB per step per GPU >> 126 MB L2 (inputs larger than L2)",
@@ -483,8 +594,9 @@ def main():
                      "kernel": prepared.describe(),
                      "algorithmic_bytes_per_launch": algo_bytes // max(1, launches_per_step),
                      "kernel_ms": kernel_ms},
-        "roofline_fp32": {"note": "secondary: Lanczos3 downscales sit above the FP32 ridge, so the FMA pipe, not HBM, "
-                                  "is their ceiling (DESIGN.md 4.1); peak = 128 FMA/clk/SM x SMs x max SM clock",
+        "roofline_fp32": {"note": "secondary: all of the resize's FMAs against the CUDA cores' FP32 pipe (round 1's ceiling). "
+                                  "Since round 2 the vertical pass of downscales runs on the tensor cores instead, so this "
+                                  "fraction overstates what the FP32 pipe does; peak = 128 FMA/clk/SM x SMs x max SM clock",
                           "achieved": algo_fma / max(1, launches_per_step) / (kernel_ms * 1e-3) / 1e12,
                           "peak": 128 * torch.cuda.get_device_properties(dev).multi_processor_count *
                                   (clocks.max_mhz or 1965) * 1e6 / 1e12,
@@ -504,6 +616,7 @@ def main():
                          "effective_h2d_gbs_per_gpu": e2e_pageable / world * 1e6 / (dw * dh) * sw * sh * ch / 1e9},
         "e2e_inprocess": e2e_inprocess,
         "cfg3_shard": cfg3_shard,
+        "cfg5_upload": cfg5_upload,
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "parity": parity,

@@ -218,6 +218,19 @@ IKC_API uint32_t ikc_pass_band8t(int filter, uint32_t n_in, uint32_t n_out, uint
 
 /* ---- host-buffer entry points (the drop-in path; include H2D + D2H) -------------------------- */
 
+/* Split form of ikc_resize_u8 for the upload-shaped pipeline (reference src/lib.rs:246-309: decode -> resize -> encode per
+ * upload, duplicate decode in src/fetch.rs:104-121): ikc_resize_begin_u8 returns as soon as the copies and kernels of
+ * this image are queued on a lane (pageable sources are staged before it returns, pinned ones -- ikc_host_alloc /
+ * ikc_host_register -- must stay untouched until the end call); the worker decodes its next upload meanwhile, then
+ * ikc_resize_end blocks until `dst` is complete and frees the ticket (also on failure).  A ticket holds one of the
+ * device's lanes (4, growing to 16 under demand); when all are held, begin waits for an end -- so a thread must end the
+ * ticket it holds before it begins another one, or many such threads can wait on each other for ever.  channels may be
+ * IKC_CHANNELS(src, dst). */
+typedef struct ikc_ticket ikc_ticket;
+IKC_API int ikc_resize_begin_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch, int channels,
+                                uint8_t* dst, uint32_t dw, uint32_t dh, size_t dst_pitch, int filter, ikc_ticket** out);
+IKC_API int ikc_resize_end(ikc_ticket* ticket);
+
 /* Same contract and result as ikc_resize_u8 / ikc_resize_convert_u8 (channels may be IKC_CHANNELS(src, dst)), for
  * handler threads that each resize one image at a time (src/lib.rs:180, :286): calls that arrive while the device is
  * busy are coalesced -- staged into one pinned block, uploaded with one copy, planned together and run as ONE launch per

@@ -216,6 +216,35 @@ int ikc_submit_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, si
     return guarded([&] { ctx->impl.submit_host(make_desc(src, sw, sh, src_pitch, channels, dst, dw, dh, dst_pitch, filter, 1)); });
 }
 
+struct ikc_ticket {
+    ikc_ctx* ctx;
+    void* impl;   // Context's ticket; nullptr: answered at begin (empty or same-size raster)
+};
+
+int ikc_resize_begin_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch, int channels, uint8_t* dst,
+                        uint32_t dw, uint32_t dh, size_t dst_pitch, int filter, ikc_ticket** out) {
+    if (out) *out = nullptr;
+    if (!ctx || !out) {
+        set_last_error("ctx or out is null");
+        return IKC_ERR_INVALID_ARG;
+    }
+    return guarded([&] {
+        auto t = std::make_unique<ikc_ticket>();
+        t->ctx = ctx;
+        t->impl = ctx->impl.begin_host(make_desc(src, sw, sh, src_pitch, channels, dst, dw, dh, dst_pitch, filter, 1));
+        *out = t.release();
+    });
+}
+
+int ikc_resize_end(ikc_ticket* ticket) {
+    if (!ticket) {
+        set_last_error("ticket is null");
+        return IKC_ERR_INVALID_ARG;
+    }
+    std::unique_ptr<ikc_ticket> t(ticket);
+    return guarded([&] { t->ctx->impl.end_host(t->impl); });
+}
+
 int ikc_get_stats(const ikc_ctx* ctx, ikc_stats_t* out) {
     if (!ctx || !out) {
         set_last_error("ctx or out is null");

@@ -205,7 +205,8 @@ void validate_job(const JobDesc& d) {
 
 // ---- device ---------------------------------------------------------------------------------------
 
-static constexpr int kLanesPerDevice = 4;
+static constexpr int kLanesPerDevice = 4;       // what a batch worker pipelines over
+static constexpr int kMaxLanesPerDevice = 16;   // tickets (begin / end) may grow the pool up to this
 static constexpr size_t kMaxCachedTables = 512;
 
 Device::Device(Context* ctx, int ordinal, int index) : ctx_(ctx), ordinal_(ordinal), index_(index) {
@@ -254,10 +255,19 @@ Device::~Device() {
     }
 }
 
-Lane* Device::acquire_lane() {
+Lane* Device::acquire_lane(bool may_grow) {
     // First come, first served: with a plain condition variable a thread that has just released a lane wins it back
     // against the waiters again and again, and the waiters' latency grows a tail of tens of milliseconds.
     std::unique_lock<std::mutex> lk(mu_);
+    if (may_grow && free_.empty() && lanes_.size() < size_t(kMaxLanesPerDevice)) {
+        // every lane is held by a ticket (ikc_resize_begin_u8): one more lane instead of a wait that could be a deadlock
+        auto l = std::make_unique<Lane>();
+        if (cudaSetDevice(ordinal_) == cudaSuccess && cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) == cudaSuccess) {
+            Lane* p = l.get();
+            lanes_.push_back(std::move(l));
+            return p;
+        }
+    }
     const uint64_t ticket = next_ticket_++;
     cv_.wait(lk, [&] { return ticket == serving_ && !free_.empty(); });
     ++serving_;
@@ -1173,6 +1183,62 @@ void Context::resize_batch_host(JobDesc* descs, size_t n, int* status, int* devi
     for (auto& e : errors) if (!e.empty()) set_last_error(e);
     for (size_t i = 0; i < n; ++i)
         if (status[i] != kOk) stats.failed.fetch_add(1, std::memory_order_relaxed);
+}
+
+// ---- split host call: begin / end ----------------------------------------------------------------
+
+namespace {
+struct Ticket {
+    Context* ctx;
+    Device* dev;
+    Lane* lane;
+    HostJobState st;
+};
+}  // namespace
+
+void* Context::begin_host(const JobDesc& d) {
+    CallTimer timer(stats);
+    validate_job(d);
+    if (trivial_resize(d)) {
+        stats.trivial.fetch_add(1, std::memory_order_relaxed);
+        timer.ok = true;
+        return nullptr;
+    }
+    count_bytes(stats, d);
+    Device& dev = device(next_device());
+    check_cuda(cudaSetDevice(dev.ordinal()), "cudaSetDevice");
+    auto t = std::make_unique<Ticket>();
+    t->ctx = this;
+    t->dev = &dev;
+    t->lane = dev.acquire_lane(true);
+    try {
+        start_host_job(*this, dev, *t->lane, d, &t->st, mode.load() == 1);
+    } catch (...) {
+        cudaStreamSynchronize(t->lane->stream);
+        dev.release_lane(t->lane);
+        throw;
+    }
+    timer.ok = true;
+    return t.release();
+}
+
+void Context::end_host(void* ticket) {
+    if (!ticket) return;
+    std::unique_ptr<Ticket> t(static_cast<Ticket*>(ticket));
+    const auto t0 = std::chrono::steady_clock::now();
+    struct Release {
+        Ticket& t;
+        ~Release() { cudaStreamSynchronize(t.lane->stream); t.st.lp = LaunchPlan{}; t.dev->release_lane(t.lane); }
+    } release{*t};
+    cudaSetDevice(t->dev->ordinal());
+    try {
+        finish_host_job(*this, *t->lane, t->st);
+    } catch (...) {
+        stats.failed.fetch_add(1, std::memory_order_relaxed);
+        throw;
+    }
+    stats.busy_ns.fetch_add(uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count()),
+                            std::memory_order_relaxed);
 }
 
 // ---- coalescing submit queue ---------------------------------------------------------------------

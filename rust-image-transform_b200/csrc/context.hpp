@@ -134,9 +134,10 @@ public:
     int sm_count() const { return sm_count_; }
 
     std::shared_ptr<DevTables> tables(int filter, uint32_t n_in, uint32_t n_out);
-    Lane* acquire_lane();
+    Lane* acquire_lane(bool may_grow = false);
     void release_lane(Lane* l);
-    int lane_count() const { return int(lanes_.size()); }
+    int lane_count() const { return kBatchLanes; }   // lanes a batch worker takes (tickets may have grown the pool beyond it)
+    static constexpr int kBatchLanes = 4;
     std::mutex batch_mu;  // serialises batch workers, which take every lane of the device
 
 private:
@@ -196,6 +197,10 @@ public:
     // Host-buffer resize of one image through a lane of some device.
     void resize_host(const JobDesc& d, int* device_index_out);
     void resize_batch_host(JobDesc* descs, size_t n, int* status, int* device_out);
+    // Split host-buffer resize (ikc_resize_begin_u8 / ikc_resize_end): begin returns an opaque ticket (nullptr for a
+    // raster answered without a kernel), end completes and frees it.  Both throw Error.
+    void* begin_host(const JobDesc& d);
+    void end_host(void* ticket);
     // Host-buffer resize through the coalescing submit queue (ikc_submit_u8); throws Error on this job's failure.
     void submit_host(const JobDesc& d);
     // One group of host jobs on one lane of `dev`: one staged upload, one plan, one launch per kernel variant, one

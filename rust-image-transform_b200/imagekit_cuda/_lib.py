@@ -22,7 +22,7 @@ MAX_DIM, MAX_PIXELS = 65535, 1 << 28  # IKC_MAX_DIM, IKC_MAX_PIXELS
 # every symbol include/imagekit_cuda.h declares
 EXPORTS = [
     "ikc_create", "ikc_destroy", "ikc_device_count", "ikc_set_mode", "ikc_get_mode", "ikc_kernel_launches",
-    "ikc_last_error", "ikc_version", "ikc_target_dims", "ikc_check_dims", "ikc_pass_table", "ikc_pass_info", "ikc_pass_band", "ikc_pass_band8", "ikc_pass_band8t", "ikc_resize_u8", "ikc_submit_u8", "ikc_get_stats", "ikc_resize_u16",
+    "ikc_last_error", "ikc_version", "ikc_target_dims", "ikc_check_dims", "ikc_pass_table", "ikc_pass_info", "ikc_pass_band", "ikc_pass_band8", "ikc_pass_band8t", "ikc_resize_u8", "ikc_submit_u8", "ikc_get_stats", "ikc_resize_begin_u8", "ikc_resize_end", "ikc_resize_u16",
     "ikc_resize_convert_u8", "ikc_resize_image_u8", "ikc_resize_batch", "ikc_host_alloc", "ikc_host_free", "ikc_host_register", "ikc_host_unregister", "ikc_resize_u8_device",
     "ikc_batch_prepare", "ikc_batch_launch", "ikc_batch_launch_count", "ikc_batch_describe", "ikc_batch_free",
 ]
@@ -101,6 +101,10 @@ def load() -> C.CDLL:
     L.ikc_resize_u8.restype = i32
     L.ikc_submit_u8.argtypes = [vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32]
     L.ikc_submit_u8.restype = i32
+    L.ikc_resize_begin_u8.argtypes = [vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32, C.POINTER(vp)]
+    L.ikc_resize_begin_u8.restype = i32
+    L.ikc_resize_end.argtypes = [vp]
+    L.ikc_resize_end.restype = i32
     L.ikc_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.ikc_get_stats.restype = i32
     L.ikc_resize_convert_u8.argtypes = [vp, vp, u32, u32, sz, i32, vp, u32, u32, sz, i32, i32]

@@ -147,6 +147,27 @@ class PinnedArray:
             pass
 
 
+class Ticket:
+    """A resize in flight (Context.resize_begin).  end() blocks until the result is complete and returns it."""
+
+    def __init__(self, handle, src, dst):
+        self._h, self._src, self._dst = handle, src, dst
+
+    def end(self) -> np.ndarray:
+        if self._h is not None:
+            h, self._h = self._h, None
+            _check(_lib.load().ikc_resize_end(h))
+        self._src = None
+        return self._dst
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None:
+            try:
+                _lib.load().ikc_resize_end(self._h)
+            except Exception:  # noqa: BLE001
+                pass
+
+
 class Context:
     """ikc_ctx: one per process (the Rust side keeps it in a OnceLock)."""
 
@@ -229,6 +250,24 @@ class Context:
         _check(_lib.load().ikc_submit_u8(self._h, s.ctypes.data, sw, sh, sw * ch, ch | (co << 8) if co != ch else ch, dst.ctypes.data,
                                          dw, dh, dw * co, filt))
         return dst[:, :, 0] if src.ndim == 2 and co == 1 else dst
+
+    def resize_begin(self, src: np.ndarray, dw: int, dh: int, filt: int = _lib.FILTER_LANCZOS3, out_channels: int | None = None,
+                     out: np.ndarray | None = None):
+        """First half of resize() for an 8-bit HxWxC array (ikc_resize_begin_u8): queues the copies and kernels and returns
+        a ticket; the caller decodes its next upload, then ticket.end() returns the resized array.  `src` (if pinned) and
+        the result buffer are kept alive by the ticket."""
+        s = np.ascontiguousarray(src[:, :, None] if src.ndim == 2 else src)
+        if s.ndim != 3 or s.dtype != np.uint8:
+            raise ImageKitError(_lib.ERR_UNSUPPORTED, "resize_begin() takes an 8-bit HxW or HxWxC array")
+        sh, sw, ch = s.shape
+        co = ch if out_channels is None else out_channels
+        check_dims(sw, sh, min(dw, 0xFFFFFFFF), min(dh, 0xFFFFFFFF))
+        dst = out if out is not None else np.empty((dh, dw, co), np.uint8)
+        assert dst.shape == (dh, dw, co) and dst.dtype == np.uint8 and dst.flags.c_contiguous
+        h = C.c_void_p()
+        _check(_lib.load().ikc_resize_begin_u8(self._h, s.ctypes.data, sw, sh, sw * ch, ch | (co << 8) if co != ch else ch, dst.ctypes.data,
+                                               dw, dh, dw * co, filt, C.byref(h)))
+        return Ticket(h, s, dst)
 
     def stats(self) -> dict:
         """Counters for a /metrics handler (ikc_get_stats)."""

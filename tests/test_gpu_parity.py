@@ -473,3 +473,42 @@ def test_reference_pinned_vectors_on_the_gpu(ctx, ik):
         assert np.array_equal(ctx.resize(src, dw, dh, filt), ref), nme
         ctx.set_mode(ik.MODE_FAST)
         assert np.abs(ctx.resize(src, dw, dh, filt).astype(int) - ref.astype(int)).max() <= TOL, nme
+
+
+def test_split_call_begin_end(ik, oracle):
+    """ikc_resize_begin_u8 / ikc_resize_end: the call split in two so that a worker can decode its next upload while this
+    one is on the GPU.  Same pixels as ikc_resize_u8; one thread may hold several tickets (the lane pool grows); many
+    threads, one ticket each, run concurrently."""
+    import threading
+    ctx = ik.Context([0])
+    src = splitmix_noise((480, 640, 3), image_id=5)
+    want = oracle.resize_exact(src, 200, 150, oracle.LANCZOS3)
+    want_rgba = oracle.to_rgba8(want)
+    tickets = [ctx.resize_begin(src, 200, 150, ik.FILTER_LANCZOS3, out_channels=4 if i % 2 else None) for i in range(6)]
+    for i, t in enumerate(tickets):
+        got = t.end()
+        assert np.abs(got.astype(int) - (want_rgba if i % 2 else want).astype(int)).max() <= TOL
+    assert ctx.resize_begin(src, 640, 480).end().tobytes() == src.tobytes()       # same size: answered at begin
+    errors = []
+    def worker(t):
+        try:
+            prev = None
+            for r in range(10):
+                s = np.roll(src, t + r, axis=1)
+                if prev is not None:
+                    got, exp = prev[0].end(), prev[1]
+                    assert np.abs(got.astype(int) - exp.astype(int)).max() <= TOL
+                prev = (ctx.resize_begin(s, 200, 150), np.roll(want, 0, axis=1) if (t + r) == 0 else None)
+                if prev[1] is None:
+                    prev = (prev[0], oracle.resize_exact(s, 200, 150, oracle.LANCZOS3))
+            prev[0].end()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(12)]
+    for x in th: x.start()
+    for x in th: x.join(120)
+    assert not any(x.is_alive() for x in th), "a worker is stuck"
+    assert not errors, errors[:3]
+    with pytest.raises(ik.ImageKitError):
+        ctx.resize_begin(src, 100, 10, 9)
+    ctx.close()
