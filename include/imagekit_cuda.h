@@ -200,7 +200,7 @@ IKC_API uint32_t ikc_pass_band(int filter, uint32_t n_in, uint32_t n_out, uint32
 /* 8-bit band form of a downscale pass, as the integer tensor-core vertical pass consumes it (inspection for tests; no
  * GPU needed).  Chunks of 32 source indices; chunk k only touches the 32 outputs starting at output 8 * gbase[k]
  * (gbase[n_chunks] = number of 8-output groups).  Every weight is the integer round(w * 2^*shift), each output's
- * weights nudged to sum to exactly 2^*shift, split into *limbs signed base-128 digits.  tiles: per chunk one s8 operand
+ * weights nudged to sum to exactly 2^*shift, split into *limbs signed base-256 digits (low digits in [-128, 127]).  tiles: per chunk one s8 operand
  * tile of (*limbs * 32) rows x 32 indices, row = (output - 8 * gbase[k]) * *limbs + digit with the most significant digit first,
  * element (row n, index k) at (k / 16) * (*limbs * 512) + (n / 8) * 128 + (n % 8) * 16 + (k % 16).  Returns the number of chunks
  * (0: the pass has no such form, or a buffer is too small); gbase == tiles == NULL: only *limbs, *shift and the count. */

@@ -8,11 +8,11 @@
 //
 //   A (M x K) = u8 source bytes, M = 128 byte columns, K = 32 source rows, straight from TMA.
 //   B (N x K) = the weights of the <= 32 output rows those source rows can touch, as integers
-//               W = round(w * 2^S) split into L signed base-128 digits (host-built tiles, plan.hpp: Band8);
+//               W = round(w * 2^S) split into L signed base-256 digits (host-built tiles, plan.hpp: Band8);
 //               N = L * 32: one MMA per block and chunk computes every digit's partial sums.
 //   D (M x N) = s32 accumulators in TMEM: lane = byte column, column = (output row mod 32) * L + digit.  The 32 rows are
 //               a ring of 4 groups of 8; a finished group is read with tcgen05.ld, its digits recombined in f32
-//               ((d1 * 128 + d0) -- exact products, one rounding), written to the shared-memory intermediate tile,
+//               ((d1 * 256 + d0) -- exact products, one rounding), written to the shared-memory intermediate tile,
 //               zeroed and handed back.  The integer sums are exact, so the vertical pass is deterministic
 //               fixed-point arithmetic with 2^-S weight resolution (each output's weights sum to exactly one).
 //
@@ -124,7 +124,7 @@ __device__ __forceinline__ void drain_group8(uint32_t taddr, uint32_t trow, int 
                 for (int r = 0; r < 8; ++r) {
                     int t = v[b][r * L];                                        // most significant digit first
 #pragma unroll
-                    for (int d = 1; d < L; ++d) t = t * 128 + v[b][r * L + d];
+                    for (int d = 1; d < L; ++d) t = t * kBand8Base + v[b][r * L + d];
                     sts_f32(trow + uint32_t(r * PITCH + b * 128) * 4, __int2float_rn(t));
                 }
             }

@@ -5,7 +5,7 @@
 // has to go through shared memory (every intermediate value is converted, stored, re-loaded ~6 times, two team barriers
 // per 16 rows).  Here the operands swap roles:
 //
-//   A (M x K) = the vertical weights of one BAND of 128 output rows: round(w * 2^S) in two signed base-128 digits, one
+//   A (M x K) = the vertical weights of one BAND of 128 output rows: round(w * 2^S) in two signed base-256 digits, one
 //               host-built K-major s8 tile per chunk of 32 source rows and digit (plan.hpp: Band8T), resident in
 //               shared memory for the CTA's whole life;
 //   B (N x K) = u8 source bytes, N = 128 byte columns (32 Rgba pixels), K = 32 source rows, exactly as a 2-D TMA box
@@ -125,7 +125,7 @@ __device__ __forceinline__ void push_half(RowState& st, const int (&hi)[32], con
         const int i = kBase + ii;                       // pixel of the super-step
         float v[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = __int2float_rn(hi[4 * ii + c] * 128 + lo[4 * ii + c]);
+        for (int c = 0; c < 4; ++c) v[c] = __int2float_rn(hi[4 * ii + c] * kBand8Base + lo[4 * ii + c]);
         const float2 v01 = make_float2(v[0], v[1]), v23 = make_float2(v[2], v[3]);
         // outputs j (relative to 8 Q) whose windows [2 j - 5, 2 j + 6] contain pixel i
 #pragma unroll

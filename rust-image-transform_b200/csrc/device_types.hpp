@@ -38,7 +38,7 @@ struct DevPass {
     // 8-bit band form (plan.hpp: Band8), used when the pass runs vertically as an integer product (banded8.cu).
     const int8_t* band8_tiles;       // [n_chunks][limbs * 32 x 32] s8, shared-memory operand layout; nullptr if none
     const int32_t* band8_gbase;      // [n_chunks + 1], groups of 8 outputs
-    int32_t band8_limbs;             // base-128 digits per weight (2 or 3); 0 if none
+    int32_t band8_limbs;             // base-256 digits per weight (2); 0 if none
     int32_t band8_shift;             // weights are round(w * 2^shift)
     // Row-band form of the same digits (plan.hpp: Band8T), used by the kernel whose accumulator lanes are output rows
     // (banded8t.cu).

@@ -331,7 +331,7 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
             }
         }
     }
-    // 8-bit band form: integer weights in base-128 digits.
+    // 8-bit band form: integer weights in base-256 digits.
     if (n_in >= n_out && n_in >= uint32_t(kBand8Chunk) && p.max_count <= 240) {
         const int limbs = kBand8DefaultLimbs;
         const uint32_t n_chunks = (n_in + kBand8Chunk - 1) / kBand8Chunk;
@@ -352,10 +352,10 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
         for (auto& ws : ragged)
             for (float wi : ws) wmax = std::max(wmax, std::fabs(wi));
         if (fits && wmax > 0.0f) {
-            // digits: the top one in [-127, 127], the others in [-64, 63]  =>  |W| <= 127 * 128^(limbs-1) + 63 * (...)
-            const double top = 120.0 * std::pow(128.0, limbs - 1);  // (headroom for the sum correction)
+            // digits: the top one in [-127, 127], the others in [-128, 127]  =>  |W| <= 127 * 256^(limbs-1) + 127 * (...)
+            const double top = 120.0 * std::pow(double(kBand8Base), limbs - 1);  // (headroom for the sum correction)
             int shift = int(std::floor(std::log2(top / double(wmax))));
-            shift = std::min(shift, 7 * limbs + 6);
+            shift = std::min(shift, 21);  // 255 * 2^21 * sum|w| stays inside the s32 accumulators
             p.band8.limbs = limbs;
             p.band8.shift = shift;
             p.band8.gbase = gbase;
@@ -401,7 +401,7 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
                     int64_t v = W[i];
                     for (int d = limbs - 1; d >= 0; --d) {   // least significant digit first
                         int64_t digit;
-                        if (d > 0) { digit = ((v + 64) & 127) - 64; v = (v - digit) / 128; }
+                        if (d > 0) { digit = ((v + kBand8Base / 2) & (kBand8Base - 1)) - kBand8Base / 2; v = (v - digit) / kBand8Base; }
                         else digit = v;                       // the top digit takes what is left (|digit| <= 127 by the choice of shift)
                         const int n = pos * limbs + d;         // row of the tile: an output's digits are adjacent, most significant first
                         const size_t at = size_t(kk / 16) * (size_t(limbs) * kBand8Window * 16) + size_t(n / 8) * 128 + size_t(n % 8) * 16 + size_t(kk % 16);

@@ -23,8 +23,8 @@ int target_dims(uint32_t ow, uint32_t oh, bool has_w, uint32_t w, bool has_h, ui
 // source bytes used as they are).  Chunks of kBand8Chunk source indices (the K of one i8 MMA); chunk k touches at
 // most kBand8Window consecutive outputs starting at output 8 * band8_gbase[k] (groups of 8; band8_gbase[n_chunks]
 // = number of groups).  Every weight is the integer W = round(w * 2^band8_shift) (each output's weights are
-// nudged to sum to exactly 2^band8_shift), split into band8_limbs signed 8-bit digits, base 128, low digits in
-// [-64, 63].  band8_tiles: per chunk one K-major s8 operand tile of (band8_limbs * 32) rows x 32 indices in the
+// nudged to sum to exactly 2^band8_shift), split into band8_limbs signed 8-bit digits, base 256, low digits in
+// [-128, 127].  band8_tiles: per chunk one K-major s8 operand tile of (band8_limbs * 32) rows x 32 indices in the
 // shared-memory layout the MMA reads; row = (output - 8 * band8_gbase[k]) * band8_limbs + digit, most significant
 // digit first.
 // band8_limbs == 0: not applicable (upscale, a chunk window wider than 32 outputs, or too many taps).
@@ -34,6 +34,7 @@ struct Band8 {
     std::vector<int8_t> tiles;    // [n_chunks][limbs * 32 * 32]
 };
 constexpr int kBand8Chunk = 32, kBand8Group = 8, kBand8Window = 32;
+constexpr int kBand8Base = 256;   // digit base: W = hi * 256 + lo, lo in [-128, 127], |hi| <= 127
 
 // Row-band form of the same integer weights, for the kernel whose accumulator lanes are OUTPUT rows (banded8t.cu): the
 // weights are the A operand.  Band r = outputs [128 r, 128 r + 128); its chunks (of kBand8Chunk source indices) start at

@@ -189,14 +189,14 @@ def test_band8_tiles_are_the_quantised_pass(ik, oracle, filt, n_in, n_out):
     chunks = dig.shape[0]
     assert limbs == 2 and chunks == (n_in + 31) // 32 and gbase[-1] == (n_out + 7) // 8
     assert np.all(np.diff(gbase[:-1]) >= 0)
-    assert dig[:, 1:].min() >= -64 and dig[:, 1:].max() <= 63          # low digits
+    assert dig[:, 1:].min() >= -128 and dig[:, 1:].max() <= 127        # low digits (base 256)
     left, count, w = oracle.pass_table(filt, n_in, n_out)
     # integer weights rebuilt from the digits, accumulated where the tiles put them (window position p = output 8 * gbase + p)
     W = np.zeros((n_out + 64, chunks * 32), np.int64)
     for c in range(chunks):
         val = np.zeros((32, 32), np.int64)
         for d in range(limbs):
-            val = val * 128 + dig[c, d].astype(np.int64)
+            val = val * 256 + dig[c, d].astype(np.int64)
         for pos in range(32):
             if not val[pos].any():
                 continue
@@ -211,7 +211,7 @@ def test_band8_tiles_are_the_quantised_pass(ik, oracle, filt, n_in, n_out):
         assert row.sum() == 2 ** shift                                  # a flat area stays exactly flat
         err = np.abs(row[left[o]:left[o] + count[o]] / scale - w[o, :count[o]].astype(np.float64))
         assert err.max() <= (count[o] / 2 + 1) / scale                  # half an LSB, plus the sum correction on one tap
-    assert np.abs(W).max() <= 127 * 128 + 63
+    assert np.abs(W).max() <= 127 * 256 + 127
 
 
 @pytest.mark.parametrize("filt,n_in,n_out", [(4, 2160, 1080), (4, 777, 388), (2, 500, 250), (4, 64, 32), (4, 700, 400), (4, 1300, 600)])
@@ -227,13 +227,13 @@ def test_band8t_tiles_hold_the_same_integers_as_band8(ik, filt, n_in, n_out):
     assert bands == (n_out + 127) // 128 and 1 <= nc <= 10
     W8 = np.zeros((n_out + 64, dig.shape[0] * 32 + 512), np.int64)
     for c in range(dig.shape[0]):
-        val = dig[c, 0].astype(np.int64) * 128 + dig[c, 1].astype(np.int64)
+        val = dig[c, 0].astype(np.int64) * 256 + dig[c, 1].astype(np.int64)
         for pos in np.flatnonzero(val.any(axis=1)):
             W8[8 * gbase[c] + pos, 32 * c:32 * c + 32] += val[pos]
     WT = np.zeros_like(W8)
     for r in range(bands):
         for c in range(nc):
-            val = t[r, c, 0].astype(np.int64) * 128 + t[r, c, 1].astype(np.int64)
+            val = t[r, c, 0].astype(np.int64) * 256 + t[r, c, 1].astype(np.int64)
             y0 = k_lo[r] + 32 * c
             rows = min(128, WT.shape[0] - 128 * r)
             assert not val[rows:].any()
