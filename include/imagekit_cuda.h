@@ -290,8 +290,9 @@ IKC_API int ikc_host_unregister(void* p);
 
 /* One resize between device buffers on `device_index` (index into the ctx's device list),
  * executed on `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream).
- * Returns once the stream has finished the resize (its descriptor staging is per call); use
- * ikc_batch_prepare / ikc_batch_launch for fully asynchronous, replayable launches.
+ * Returns once the stream has finished the resize (its descriptor staging is per call; the empty-source memset and
+ * the same-size copy are synchronised the same way); use ikc_batch_prepare / ikc_batch_launch for fully asynchronous,
+ * replayable launches.
  * Device buffers must span rows*pitch bytes; the fused kernel additionally wants a 16-byte
  * aligned base and pitch (otherwise the slower generic kernels are used). */
 IKC_API int ikc_resize_u8_device(ikc_ctx* ctx, int device_index, void* stream, const uint8_t* d_src,
@@ -300,7 +301,10 @@ IKC_API int ikc_resize_u8_device(ikc_ctx* ctx, int device_index, void* stream, c
 
 /* Prepare `n` device-resident jobs (8-bit) as one replayable batch: plans every job, uploads the
  * weight tables and work-item list once.  ikc_batch_launch enqueues the whole batch on `stream`
- * (one launch per kernel family present, normally one).  jobs[i].status is set at prepare time. */
+ * (one launch per kernel family present, normally one).  jobs[i].status is set at prepare time.  If some jobs are
+ * rejected the call returns the first failing status and *out is STILL a valid batch over the accepted jobs (it must be
+ * freed); *out is NULL only when nothing could be prepared (bad arguments, CUDA failure).  The batch references the
+ * weight tables it uses: synchronise the streams it was launched on before ikc_batch_free. */
 IKC_API int ikc_batch_prepare(ikc_ctx* ctx, int device_index, ikc_job* jobs, size_t n, ikc_batch** out);
 IKC_API int ikc_batch_launch(ikc_batch* b, void* stream);
 /* Kernel launches one ikc_batch_launch issues. */

@@ -376,11 +376,13 @@ int ikc_resize_u8_device(ikc_ctx* ctx, int device_index, void* stream, const uin
             fail(kUnsupported, "device entry point: empty or same-size rasters cannot be combined with a channel conversion");
         if (sw == 0 || sh == 0) {
             check_cuda(cudaMemset2DAsync(d_dst, dst_pitch, 0, row, dh, s), "memset");
+            check_cuda(cudaStreamSynchronize(s), "resize (stream sync)");
             return;
         }
         if (sw == dw && sh == dh) {
             check_cuda(cudaMemcpy2DAsync(d_dst, dst_pitch, d_src, src_pitch, row, dh, cudaMemcpyDeviceToDevice, s),
                        "copy");
+            check_cuda(cudaStreamSynchronize(s), "resize (stream sync)");
             return;
         }
         const bool exact = c.mode.load() == 1;

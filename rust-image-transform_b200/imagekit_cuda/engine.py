@@ -335,7 +335,10 @@ class Context:
         for i, (d_src, sw, sh, sp, d_dst, dw, dh, dp, ch, filt) in enumerate(jobs):
             arr[i] = Job(d_src, d_dst, sw, sh, dw, dh, sp, dp, ch, filt, 0, 0)
         h = C.c_void_p()
-        _check(_lib.load().ikc_batch_prepare(self._h, device_index, arr, n, C.byref(h)))
+        rc = _lib.load().ikc_batch_prepare(self._h, device_index, arr, n, C.byref(h))
+        if rc != _lib.OK and h:   # some jobs were rejected: the library still returns a batch over the others; do not leak it
+            _lib.load().ikc_batch_free(h)
+        _check(rc)
         return PreparedBatch(self, h, arr)
 
 
