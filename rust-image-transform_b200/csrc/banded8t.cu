@@ -92,7 +92,9 @@ __device__ __forceinline__ StreamRange stream_range(int ox0, int ox1, int s) {
     r.x0 = s == 0 ? ox0 : mid;
     r.x1 = s == 0 ? mid : ox1;
     r.b0 = max(2 * r.x0 - kTLead, 0) / (2 * kTPx);
-    r.b1 = (2 * (r.x1 - 1) + kTTaps - kTLead - 1) / (2 * kTPx);
+    // (outputs leave in aligned groups of four, when the group's last one completes: run until that one has, even if it
+    // lies beyond the stream's -- or the image's -- last output)
+    r.b1 = (2 * ((r.x1 - 1) | 3) + kTTaps - kTLead - 1) / (2 * kTPx);
     return r;
 }
 

@@ -178,6 +178,20 @@ ROW_BAND_SHAPES = [  # Rgba8, exactly 2:1 horizontally, at most ~2:1 vertically,
 ]
 
 
+@pytest.mark.parametrize("shape", [(1236, 730, 365, 549), (300, 202, 101, 150), (200, 1034, 517, 100), (90, 94, 47, 45)])
+def test_row_band_kernel_widths_not_a_multiple_of_four(ctx, ik, oracle, shape):
+    """Host buffers are staged with a 256-byte pitch, so any width reaches banded8t: the last, partial group of four outputs
+    of a row must still be written (a randomised sweep found the last column missing for dw = 365)."""
+    h, w, dw, dh = shape
+    ctx.set_mode(ik.MODE_FAST)
+    s = splitmix_noise((h, w, 4), image_id=w)
+    before = ctx.stats()["launches_banded8t"]
+    got = ctx.resize(s, dw, dh, ik.FILTER_LANCZOS3)
+    assert ctx.stats()["launches_banded8t"] == before + 1
+    hist = delta_histogram(got, oracle.resize_exact(s, dw, dh, oracle.LANCZOS3))
+    assert max(abs(k) for k in hist) <= 1, hist
+
+
 @pytest.mark.parametrize("shape", ROW_BAND_SHAPES)
 @pytest.mark.parametrize("content", ["noise", "edges"])
 def test_row_band_kernel(ctx, ik, oracle, shape, content):

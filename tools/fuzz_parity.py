@@ -16,7 +16,7 @@ ctx = ik.Context([0])
 bad = 0
 t0 = time.time()
 for case in range(n_cases):
-    kind = rng.choice(["down_int", "down_any", "up2", "up_any", "mixed"], p=[0.3, 0.3, 0.15, 0.1, 0.15])
+    kind = rng.choice(["down_int", "down_any", "up2", "up_any", "mixed", "down2_rgba"], p=[0.22, 0.25, 0.13, 0.1, 0.1, 0.2])
     c = int(rng.choice([1, 2, 3, 4], p=[0.1, 0.1, 0.4, 0.4]))
     filt = int(rng.choice([0, 1, 2, 3, 4], p=[0.05, 0.1, 0.2, 0.1, 0.55]))
     if kind == "down_int":
@@ -24,6 +24,13 @@ for case in range(n_cases):
         dw, dh = int(rng.integers(8, 700)), int(rng.integers(8, 500))
         w, h = dw * r, dh * r
         if rng.random() < 0.3: h = dh * int(rng.choice([2, 3, 4]))       # different integer ratios per axis
+    elif kind == "down2_rgba":   # the row-band tensor-core kernel: Rgba8, exactly 2:1 horizontally, ~1.5 .. 2.3 : 1 vertically
+        c = 4
+        filt = int(rng.choice([4, 4, 4, 3]))
+        dw = int(rng.integers(6, 800)) * (4 if rng.random() < 0.8 else 1)
+        dh = int(rng.integers(8, 700))
+        w = 2 * dw
+        h = 2 * dh if rng.random() < 0.6 else int(dh * rng.uniform(1.5, 2.3))
     elif kind == "down_any":
         w, h = int(rng.integers(16, 2200)), int(rng.integers(16, 1600))
         dw, dh = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1))
@@ -44,7 +51,13 @@ for case in range(n_cases):
     if co is None and rng.random() < 0.15:  # 16-bit rasters (tile / generic kernels)
         src = (src.astype(np.uint16) * 257) ^ rng.integers(0, 256, src.shape, dtype=np.uint16)
     ctx.set_mode(ik.MODE_EXACT if exact else ik.MODE_FAST)
-    got = ctx.resize(src, dw, dh, filt, out_channels=co)
+    how = rng.random()
+    if src.dtype == np.uint8 and how < 0.15:
+        got = ctx.submit(src, dw, dh, filt, out_channels=co)                       # coalescing queue
+    elif src.dtype == np.uint8 and how < 0.3:
+        got = ctx.resize_begin(src, dw, dh, filt, out_channels=co).end()           # split call
+    else:
+        got = ctx.resize(src, dw, dh, filt, out_channels=co)
     want = oracle.resize_exact(src, dw, dh, filt)
     if co == 3: want = oracle.to_rgb8(want)
     if co == 4: want = oracle.to_rgba8(want)
@@ -52,5 +65,5 @@ for case in range(n_cases):
     if d > (0 if exact else 1):
         bad += 1
         print("FAIL", dict(kind=kind, h=h, w=w, c=c, dw=dw, dh=dh, filt=filt, co=co, exact=exact, max_delta=d), flush=True)
-print(f"{n_cases} cases, {bad} failures, {time.time() - t0:.1f} s")
+print(f"{n_cases} cases, {bad} failures, {time.time() - t0:.1f} s; launches per family: { {k: v for k, v in ctx.stats().items() if k.startswith('launches_')} }")
 sys.exit(1 if bad else 0)

@@ -1,5 +1,5 @@
-"""Dev tool: a handful of small resizes that reach every kernel (ring general / uniform / converting, tile,
-up2 vector + ragged paths, generic), checked against the oracle.  Meant to be run under compute-sanitizer:
+"""Dev tool: a handful of small resizes that reach every kernel (tensor-core downscale kernels general / uniform /
+converting / row-band, tile, up2 vector + ragged paths, generic), checked against the oracle.  Meant to be run under compute-sanitizer:
     compute-sanitizer --tool memcheck python tools/sanitize_cases.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -15,6 +15,8 @@ cases = [  # (h, w, c, dw, dh, filter, out_channels)
     (300, 400, 3, 200, 150, 4, 4), (512, 1024, 4, 256, 128, 4, None), (777, 1031, 3, 515, 388, 4, None),
     (240, 320, 3, 640, 480, 2, None), (120, 161, 4, 322, 240, 4, None), (64, 64, 3, 128, 128, 1, None),
     (100, 90, 2, 45, 50, 2, 4), (90, 100, 1, 300, 270, 3, None), (33, 17, 3, 34, 66, 0, None),
+    # the row-band tensor-core kernel (2:1 Rgba8): partial last band, image borders, one block, odd vertical ratio
+    (384, 512, 4, 256, 192, 4, None), (130, 264, 4, 132, 65, 4, None), (64, 96, 4, 48, 32, 4, None), (700, 1000, 4, 500, 400, 4, None),
 ]
 worst = 0
 for h, w, c, dw, dh, filt, co in cases:
