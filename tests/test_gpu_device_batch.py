@@ -229,6 +229,7 @@ def test_row_band_kernel_batches_and_fallbacks(ctx, ik, oracle):
     dev = torch.device("cuda:0")
     cases = [  # (h, w, c, dw, dh, co, dst pitch slack)
         (384, 512, 4, 256, 192, 4, 0), (1080, 1920, 4, 960, 540, 4, 0), (300, 640, 4, 320, 150, 4, 0), (700, 1000, 4, 500, 350, 4, 0),
+        (1236, 736, 4, 368, 549, 4, 0),   # 2.25:1 vertically: ten weight tiles per band, the others nine, in one launch
         (300, 640, 4, 320, 150, 4, 4), (300, 640, 3, 320, 150, 3, 0), (300, 640, 4, 320, 150, 3, 0),
     ]
     keep, jobs, want = [], [], []
