@@ -54,6 +54,7 @@ pub struct ikc_stats_t {
     pub table_misses: u64,
     pub submit_batches: u64,
     pub submit_jobs: u64,
+    pub launches_banded8u: u64,
 }
 
 extern "C" {

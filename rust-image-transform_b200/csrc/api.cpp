@@ -261,6 +261,7 @@ int ikc_get_stats(const ikc_ctx* ctx, ikc_stats_t* out) {
     out->src_bytes = ld(s.src_bytes); out->dst_bytes = ld(s.dst_bytes); out->busy_ns = ld(s.busy_ns);
     out->table_hits = ld(s.table_hits); out->table_misses = ld(s.table_misses);
     out->submit_batches = ld(s.submit_batches); out->submit_jobs = ld(s.submit_jobs);
+    out->launches_banded8u = ld(s.launches_by_family[7]);
     return IKC_OK;
 }
 
@@ -461,7 +462,8 @@ int ikc_batch_describe(const ikc_batch* b, char* out, size_t cap) {
     std::string s;
     for (auto& g : b->impl.lp.groups) {
         if (!s.empty()) s += "; ";
-        if (g.band8t) s += "banded8t_kernel<4> (2 digits, " + std::to_string(g.b8tgeom.chunks) + " chunks per band)";
+        if (g.band8u_taps) s += "banded8u_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.band8u_taps) + ">";
+        else if (g.band8t) s += "banded8t_kernel<4> (2 digits, " + std::to_string(g.b8tgeom.chunks) + " chunks per band)";
         else if (g.band8_limbs) s += "banded8_kernel<" + std::to_string(g.channels) + (g.convert ? ",conv" : "") + "> (" + std::to_string(g.band8_limbs) + " digits)";
         else if (g.band_n) s += "banded_kernel<" + std::to_string(g.channels) + (g.convert ? ",conv" : "") + "> (band_n " + std::to_string(g.band_n) + ")";
         else if (g.up_taps) s += "up2_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.up_taps) + ">";

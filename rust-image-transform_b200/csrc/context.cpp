@@ -575,6 +575,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
     std::vector<Cand> cands;
     std::vector<WorkItem> tile_items[2];  // [bytes per sample - 1]: one tile-kernel launch per sample type
     std::vector<int> b8t_jobs;            // jobs of the banded8t launch (cut into items once the batch is known)
+    std::vector<int> b8u_jobs;            // jobs of the banded8u launches
     TileGeom tile_geom[2]{};
     lp.jobs.reserve(n);
     for (size_t i = 0; i < n; ++i) {
@@ -677,8 +678,24 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
             const bool up2 = !fused && !exact && d.bps == 1 && d.oc() == d.channels && d.dw == 2 * d.sw && d.dh == 2 * d.sh &&
                              tv->pass.up2_pairs_v && th->pass.up2_pairs_h &&
                              up2_supported(d.channels, tv->pass.up2_taps, th->pass.up2_taps);
+            // exact 2x upscales of Rgb8 / Rgba8: the tensor-core kernel first (vertical pass as an integer product, lane =
+            // output row; horizontal pass from registers), the CUDA-core tile kernel of up2.cu otherwise
+            const bool up2_tc = up2 && mode.load() == 0 && tma_ok && ((reinterpret_cast<uintptr_t>(d.dst) | d.dst_pitch) & 15) == 0 &&
+                                tv->pass.band8t_tiles && tv->pass.band8_limbs == 0 && tv->pass.up2_taps == th->pass.up2_taps &&
+                                banded8u_supported(d.channels, th->pass.up2_taps, th->pass.up2_off, tv->pass.band8t_chunks) &&
+                                encode_src_map8(lp.jobs[size_t(idx)].src_map8, d.src, d.sh, d.src_pitch);
             if (fused) cands.push_back(std::move(c));
-            else if (up2) {
+            else if (up2_tc) {
+                FusedGroup* g = nullptr;
+                for (auto& gg : lp.groups)
+                    if (gg.band8u_taps == th->pass.up2_taps && gg.channels == d.channels) g = &gg;
+                if (!g) {
+                    lp.groups.push_back(FusedGroup{d.channels, 0, 0, {}, {}, {}});
+                    g = &lp.groups.back();
+                    g->band8u_taps = th->pass.up2_taps;
+                }
+                b8u_jobs.push_back(idx);
+            } else if (up2) {
                 FusedGroup* g = nullptr;
                 for (auto& gg : lp.groups)
                     if (gg.up_taps == tv->pass.up2_taps && gg.channels == d.channels) g = &gg;
@@ -737,6 +754,35 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
                 }
         }
         g->b8tgeom.n_items = int(g->items.size());
+    }
+    if (!b8u_jobs.empty()) {
+        // Items: band of 128 output rows x column segment in whole blocks of 64 output pixels; the segment count minimises
+        // (waves) x (work per item), each segment paying one block of pre-roll per stream.
+        const int rows = banded8u_band_rows();
+        size_t bands = 0;
+        for (int idx : b8u_jobs) bands += (lp.jobs[size_t(idx)].dh + rows - 1) / rows;
+        int want = 1;
+        double best = 1e30;
+        for (int sgs = 1; sgs <= 64; ++sgs) {
+            const double waves = std::ceil(double(bands) * sgs / double(dev.sm_count()));
+            const double cost = waves * (1.0 / sgs + 0.04);
+            if (cost < best - 1e-12) { best = cost; want = sgs; }
+        }
+        for (int idx : b8u_jobs) {
+            const DevJob& j = lp.jobs[size_t(idx)];
+            FusedGroup* g = nullptr;
+            for (auto& gg : lp.groups)
+                if (gg.band8u_taps == j.h.up2_taps && gg.channels == j.channels) g = &gg;
+            const int dw = int(j.dw), dh = int(j.dh);
+            const int blocks = (dw + 63) / 64;
+            const int segs = std::max(1, std::min(want, blocks / 4));
+            for (int oy = 0; oy < dh; oy += rows)
+                for (int k = 0; k < segs; ++k) {
+                    const int x0 = int(int64_t(blocks) * k / segs) * 64;
+                    const int x1 = k == segs - 1 ? dw : int(int64_t(blocks) * (k + 1) / segs) * 64;
+                    if (x1 > x0) g->items.push_back(WorkItem{idx, x0, x1, oy, std::min(dh, oy + rows)});
+                }
+        }
     }
     if (cands.empty()) return lp;
 
@@ -860,7 +906,8 @@ void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, 
     size_t off = (sizeof(DevJob) * lp.jobs.size() + 15) & ~size_t(15);
     for (auto& g : lp.groups) {
         const WorkItem* d_items = reinterpret_cast<const WorkItem*>(d_desc_base + off);
-        if (g.band8t) check_cuda(launch_banded8t(d_jobs, d_items, g.b8tgeom, stream), "launch banded8t_kernel");
+        if (g.band8u_taps) check_cuda(launch_banded8u(g.channels, g.band8u_taps, d_jobs, d_items, int(g.items.size()), stream), "launch banded8u_kernel");
+        else if (g.band8t) check_cuda(launch_banded8t(d_jobs, d_items, g.b8tgeom, stream), "launch banded8t_kernel");
         else if (g.band8_limbs) check_cuda(launch_banded8(g.channels, g.convert, d_jobs, d_items, g.b8geom, stream), "launch banded8_kernel");
         else if (g.band_n) check_cuda(launch_banded(g.channels, g.convert, d_jobs, d_items, g.bgeom, stream), "launch banded_kernel");
         else if (g.up_taps) check_cuda(launch_up2(g.channels, g.up_taps, d_jobs, d_items, int(g.items.size()), stream), "launch up2_kernel");
@@ -868,7 +915,7 @@ void Context::launch_resident(const LaunchPlan& lp, const uint8_t* d_desc_base, 
         else check_cuda(launch_fused(g.channels, g.kv, g.kh, g.sv, g.sh, g.convert, d_jobs, d_items, g.geom, stream), "launch fused_ring_kernel");
         off += (sizeof(WorkItem) * g.items.size() + 15) & ~size_t(15);
         launches.fetch_add(1, std::memory_order_relaxed);
-        const int family = g.band8t ? 0 : g.band8_limbs ? 1 : g.band_n ? 2 : g.up_taps ? 4 : g.kv == 0 ? 5 : 3;
+        const int family = g.band8u_taps ? 7 : g.band8t ? 0 : g.band8_limbs ? 1 : g.band_n ? 2 : g.up_taps ? 4 : g.kv == 0 ? 5 : 3;
         stats.launches_by_family[family].fetch_add(1, std::memory_order_relaxed);
     }
     for (int idx : lp.generic_jobs) {

@@ -75,6 +75,7 @@ struct FusedGroup {  // one kernel launch over a list of work items
     int band8_limbs = 0;   // > 0: a banded8 (integer tensor-core) launch with this many digits per weight
     Band8Geom b8geom{};
     bool band8t = false;   // a banded8t (row-band integer tensor-core) launch
+    int band8u_taps = 0;   // > 0: a banded8u (tensor-core 2x upscale) launch with this horizontal tap frame
     Band8TGeom b8tgeom{};
 };
 
@@ -160,7 +161,7 @@ private:
 // Monotonic counters behind ikc_get_stats.
 struct Stats {
     std::atomic<uint64_t> calls{0}, failed{0}, trivial{0};
-    std::atomic<uint64_t> launches_by_family[7]{};   // banded8t, banded8, banded f16, ring, up2, tile, generic
+    std::atomic<uint64_t> launches_by_family[8]{};   // banded8t, banded8, banded f16, ring, up2, tile, generic, banded8u
     std::atomic<uint64_t> src_bytes{0}, dst_bytes{0}, busy_ns{0};
     std::atomic<uint64_t> table_hits{0}, table_misses{0};
     std::atomic<uint64_t> submit_batches{0}, submit_jobs{0};

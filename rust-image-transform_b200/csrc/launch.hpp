@@ -48,6 +48,13 @@ int banded8t_band_rows();
 size_t banded8t_smem_bytes(const Band8TGeom& geom);
 cudaError_t launch_banded8t(const DevJob* jobs, const WorkItem* items, const Band8TGeom& geom, cudaStream_t stream);
 
+// Banded8u kernel (banded8u.cu): exact 2x upscales of Rgb8 / Rgba8 with the vertical pass on the tensor cores (accumulator
+// lanes are output rows) and the horizontal pass from registers.  Work items: (band of 128 output rows) x (column range
+// in whole blocks of 64 output pixels).
+bool banded8u_supported(int channels, int taps_h, int off_h, int chunks_v);
+int banded8u_band_rows();
+cudaError_t launch_banded8u(int channels, int taps, const DevJob* jobs, const WorkItem* items, int n_items, cudaStream_t stream);
+
 // Tile kernel (tile.cu): output-stationary fused passes over shared-memory tiles.
 size_t tile_smem_bytes(const TileGeom& geom);
 cudaError_t launch_tile(int bytes_per_sample, const DevJob* jobs, const WorkItem* items, const TileGeom& geom,

@@ -285,6 +285,53 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
             }
             p.up2_uni_lo = int(best_lo);
             p.up2_uni_hi = int(best_lo + best_len);
+            // Row-band integer form of the pass used vertically (banded8u.cu: the tensor-core 2x upscale kernel): the same
+            // digits and tile layout as a downscale's Band8T; a band of 128 outputs spans 64 + taps - 1 source indices.
+            float wmax = 0.0f;
+            for (auto& ws : ragged)
+                for (float wi : ws) wmax = std::max(wmax, std::fabs(wi));
+            const uint32_t n_bands = (n_out + kBand8TRows - 1) / kBand8TRows;
+            std::vector<int32_t> k_lo(n_bands, 0);
+            int band_chunks = 0;
+            for (uint32_t r = 0; r < n_bands; ++r) {
+                const uint32_t o0 = r * kBand8TRows, o1 = std::min(n_out, o0 + kBand8TRows);
+                k_lo[r] = p.left[o0];
+                band_chunks = std::max(band_chunks, (p.right[o1 - 1] - k_lo[r] + kBand8Chunk - 1) / kBand8Chunk);
+            }
+            if (wmax > 0.0f && band_chunks >= 1 && band_chunks <= kBand8TMaxChunks) {
+                int shift = int(std::floor(std::log2(120.0 * kBand8Base / double(wmax))));
+                shift = std::min(shift, 21);
+                const double scale = std::ldexp(1.0, shift);
+                constexpr size_t kTTile = size_t(kBand8TRows) * kBand8Chunk;
+                p.band8.shift = shift;   // (band8.limbs stays 0: there is no chunk-window form of an upscale)
+                p.band8t.chunks = band_chunks;
+                p.band8t.k_lo = k_lo;
+                p.band8t.tiles.assign(size_t(n_bands) * band_chunks * 2 * kTTile, 0);
+                std::vector<int64_t> W;
+                for (uint32_t o = 0; o < n_out; ++o) {
+                    const auto& ws = ragged[o];
+                    W.resize(ws.size());
+                    int64_t sum = 0;
+                    size_t big = 0;
+                    for (size_t i = 0; i < ws.size(); ++i) {
+                        W[i] = int64_t(std::llround(double(ws[i]) * scale));
+                        sum += W[i];
+                        if (std::fabs(ws[i]) > std::fabs(ws[big])) big = i;
+                    }
+                    W[big] += (int64_t(1) << shift) - sum;
+                    const uint32_t r = o / kBand8TRows;
+                    const int m = int(o % kBand8TRows);
+                    for (size_t i = 0; i < ws.size(); ++i) {
+                        const int32_t y = p.left[o] + int32_t(i);
+                        const int ct = (y - k_lo[r]) / kBand8Chunk, kt = (y - k_lo[r]) % kBand8Chunk;
+                        const int64_t lo = ((W[i] + kBand8Base / 2) & (kBand8Base - 1)) - kBand8Base / 2, hi = (W[i] - lo) / kBand8Base;
+                        const size_t at = size_t(kt / 16) * (size_t(kBand8TRows) * 16) + size_t(m / 8) * 128 + size_t(m % 8) * 16 + size_t(kt % 16);
+                        const size_t tt = (size_t(r) * band_chunks + size_t(ct)) * 2 * kTTile;
+                        p.band8t.tiles[tt + at] = int8_t(hi);
+                        p.band8t.tiles[tt + kTTile + at] = int8_t(lo);
+                    }
+                }
+            }
         }
     }
     // Band form for the tensor-core vertical pass (downscales and 1:1 only).
