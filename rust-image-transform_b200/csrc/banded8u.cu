@@ -106,16 +106,26 @@ __device__ __forceinline__ URange u_range(int ox0, int ox1, int s, int off, int 
     return r;
 }
 
+// One 32-byte store (a whole L2 sector) per lane: STG.E.ENL2.256.
+__device__ __forceinline__ void st_global_256(uint8_t* p, const uint32_t* w) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]),
+                 "r"(w[7])
+                 : "memory");
+}
+// Words by which the row's output stream lags a 32-byte boundary at a unit starting with new pixel x0 = 8 * (2 m + parity).
+template <int C, int ADV>
+__host__ __device__ constexpr int carry_words(int parity) { return (((2 * C * (8 * parity - ADV)) % 32 + 32) % 32) / 4; }
+
 __device__ __forceinline__ uint32_t pack4(float a, float b, float c, float d) {  // four (value + 0.5) -> four saturated bytes
     return pack_pixel(make_float4(a, b, c, d));
 }
 
 // Eight NEW source pixels x0 .. x0 + 7 through the filter: they complete the pairs x0 - ADV .. x0 - ADV + 7, i.e. 16 output
-// pixels of this thread's row = 4 C words, which leave as 16-byte groups.  The row's output stream lags 16-byte
-// alignment by CW words (2 C ADV bytes behind a multiple of 16): `carry` holds the CW words of the group in flight.
-// win: the last T pixels seen.
+// pixels of this thread's row = 4 C words, which leave as 32-byte groups (one whole sector per lane and store: with lane =
+// row a warp's store touches 32 different rows, so anything smaller than a sector is a partial write).  The row's output
+// stream lags 32-byte alignment by CW words here: `carry` holds the words of the group in flight.  win: the last T pixels.
 template <int C, int T, int ADV, int CW, bool EDGE>
-__device__ __forceinline__ void push_unit(float (&win)[T][C], uint32_t (&carry)[3], const int (&hi)[8 * C], const int (&lo)[8 * C],
+__device__ __forceinline__ void push_unit(float (&win)[T][C], uint32_t (&carry)[7], const int (&hi)[8 * C], const int (&lo)[8 * C],
                                           const float2 (&up)[T], int x0, const float2* __restrict__ pairs, int n_in, float unscale,
                                           uint8_t* __restrict__ dst_row, int lo_b, int hi_b, bool row_live) {
     uint32_t word[CW + 4 * C];
@@ -159,22 +169,23 @@ __device__ __forceinline__ void push_unit(float (&win)[T][C], uint32_t (&carry)[
             }
         }
     }
+    constexpr int kGroups = (CW + 4 * C) / 8, kLeft = (CW + 4 * C) % 8;
 #pragma unroll
-    for (int j = 0; j < CW; ++j) carry[j] = word[4 * C + j];
+    for (int j = 0; j < kLeft; ++j) carry[j] = word[8 * kGroups + j];
     if (!row_live) return;
-    const int gbyte0 = 2 * (x0 - ADV) * C - 4 * CW;                             // first byte of the first whole group (a multiple of 16)
+    const int gbyte0 = 2 * (x0 - ADV) * C - 4 * CW;                             // first byte of the first whole group (a multiple of 32)
 #pragma unroll
-    for (int g = 0; g < C; ++g) {
-        const int gb = gbyte0 + 16 * g;
-        if (gb >= lo_b && gb + 16 <= hi_b) {
-            *reinterpret_cast<uint4*>(dst_row + gb) = make_uint4(word[4 * g], word[4 * g + 1], word[4 * g + 2], word[4 * g + 3]);
-        } else if (gb + 16 > lo_b && gb < hi_b) {   // the ragged end of the row: byte by byte
+    for (int g = 0; g < kGroups; ++g) {
+        const int gb = gbyte0 + 32 * g;
+        if (gb >= lo_b && gb + 32 <= hi_b) {
+            st_global_256(dst_row + gb, word + 8 * g);
+        } else if (gb + 32 > lo_b && gb < hi_b) {   // the ragged end of the row: byte by byte
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 8; ++j)
 #pragma unroll
                 for (int bb = 0; bb < 4; ++bb) {
                     const int at = gb + 4 * j + bb;
-                    if (at >= lo_b && at < hi_b) dst_row[at] = uint8_t(word[4 * g + j] >> (8 * bb));
+                    if (at >= lo_b && at < hi_b) dst_row[at] = uint8_t(word[8 * g + j] >> (8 * bb));
                 }
         }
     }
@@ -209,7 +220,7 @@ banded8u_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
     const int nch = J->v.band8t_chunks;
     const int k_lo = __ldg(J->v.band8t_klo + band);
     constexpr int kAdv = (T - 1) / 2;                              // pair k is complete once source pixel k + kAdv has arrived (frame offset -(T-1)/2)
-    constexpr int kCW = ((16 - (2 * C * kAdv) % 16) % 16) / 4;     // words the output stream lags a 16-byte boundary
+    constexpr int kCW0 = carry_words<C, kAdv>(0), kCW1 = carry_words<C, kAdv>(1);   // words the output stream lags a 32-byte boundary
     static_assert((2 * C * kAdv) % 4 == 0, "the output stream must stay word aligned");
 
     if (tid == 0) {
@@ -324,7 +335,7 @@ banded8u_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
         for (int t = 0; t < T; ++t)
 #pragma unroll
             for (int c = 0; c < C; ++c) win[t][c] = 0.0f;
-        uint32_t carry[3] = {0u, 0u, 0u};
+        uint32_t carry[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
         const int lo_b = 2 * C * sr.k0, hi_b = min(2 * C * sr.k1, row_bytes);   // this stream's bytes of the row
 
         const int nb = sr.blocks();
@@ -342,14 +353,14 @@ banded8u_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
             for (int h = 0; h < 2; ++h) {
                 const int x0 = xb + 16 * h;
                 const bool in0 = x0 - kAdv >= uni_lo && x0 - kAdv + 8 <= uni_hi, in1 = x0 - kAdv + 8 >= uni_lo && x0 - kAdv + 16 <= uni_hi;
-                if (in0) push_unit<C, T, kAdv, kCW, false>(win, carry, hiA, loA, up, x0, pairs, n_in, unscale, dst_row, lo_b, hi_b, row_live);
-                else push_unit<C, T, kAdv, kCW, true>(win, carry, hiA, loA, up, x0, pairs, n_in, unscale, dst_row, lo_b, hi_b, row_live);
+                if (in0) push_unit<C, T, kAdv, kCW0, false>(win, carry, hiA, loA, up, x0, pairs, n_in, unscale, dst_row, lo_b, hi_b, row_live);
+                else push_unit<C, T, kAdv, kCW0, true>(win, carry, hiA, loA, up, x0, pairs, n_in, unscale, dst_row, lo_b, hi_b, row_live);
                 if (h == 0) {
                     tmem_ld_unit<C>(taddr + 16 * C, hiA);
                     tmem_ld_unit<C>(taddr + 128 + 16 * C, loA);
                 }
-                if (in1) push_unit<C, T, kAdv, kCW, false>(win, carry, hiB, loB, up, x0 + 8, pairs, n_in, unscale, dst_row, lo_b, hi_b, row_live);
-                else push_unit<C, T, kAdv, kCW, true>(win, carry, hiB, loB, up, x0 + 8, pairs, n_in, unscale, dst_row, lo_b, hi_b, row_live);
+                if (in1) push_unit<C, T, kAdv, kCW1, false>(win, carry, hiB, loB, up, x0 + 8, pairs, n_in, unscale, dst_row, lo_b, hi_b, row_live);
+                else push_unit<C, T, kAdv, kCW1, true>(win, carry, hiB, loB, up, x0 + 8, pairs, n_in, unscale, dst_row, lo_b, hi_b, row_live);
                 if (h == 0) {
                     tmem_ld_unit<C>(taddr + 24 * C, hiB);
                     tmem_ld_unit<C>(taddr + 128 + 24 * C, loB);

@@ -680,7 +680,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
                              up2_supported(d.channels, tv->pass.up2_taps, th->pass.up2_taps);
             // exact 2x upscales of Rgb8 / Rgba8: the tensor-core kernel first (vertical pass as an integer product, lane =
             // output row; horizontal pass from registers), the CUDA-core tile kernel of up2.cu otherwise
-            const bool up2_tc = up2 && mode.load() == 0 && tma_ok && ((reinterpret_cast<uintptr_t>(d.dst) | d.dst_pitch) & 15) == 0 &&
+            const bool up2_tc = up2 && mode.load() == 0 && tma_ok && ((reinterpret_cast<uintptr_t>(d.dst) | d.dst_pitch) & 31) == 0 &&
                                 tv->pass.band8t_tiles && tv->pass.band8_limbs == 0 && tv->pass.up2_taps == th->pass.up2_taps &&
                                 banded8u_supported(d.channels, th->pass.up2_taps, th->pass.up2_off, tv->pass.band8t_chunks) &&
                                 encode_src_map8(lp.jobs[size_t(idx)].src_map8, d.src, d.sh, d.src_pitch);
