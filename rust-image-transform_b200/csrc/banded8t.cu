@@ -70,6 +70,13 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One 32-byte store (a whole L2 sector) per lane: with lane = row a warp's store touches 32 different rows, so anything
+// smaller than a sector is a partial write.
+__device__ __forceinline__ void st_global_256(uint8_t* p, const uint32_t (&w)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]),
+                 "r"(w[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, int (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -92,9 +99,9 @@ __device__ __forceinline__ StreamRange stream_range(int ox0, int ox1, int s) {
     r.x0 = s == 0 ? ox0 : mid;
     r.x1 = s == 0 ? mid : ox1;
     r.b0 = max(2 * r.x0 - kTLead, 0) / (2 * kTPx);
-    // (outputs leave in aligned groups of four, when the group's last one completes: run until that one has, even if it
+    // (outputs leave in aligned groups of eight, when the group's last one completes: run until that one has, even if it
     // lies beyond the stream's -- or the image's -- last output)
-    r.b1 = (2 * ((r.x1 - 1) | 3) + kTTaps - kTLead - 1) / (2 * kTPx);
+    r.b1 = (2 * ((r.x1 - 1) | 7) + kTTaps - kTLead - 1) / (2 * kTPx);
     return r;
 }
 
@@ -102,7 +109,7 @@ __device__ __forceinline__ StreamRange stream_range(int ox0, int ox1, int s) {
 // (channels 0-1, 2-3), the packed pixels of the 16-byte group in flight.
 struct RowState {
     float2 acc[kTSlots][2];
-    uint32_t word[4];
+    uint32_t word[8];   // the packed pixels of the 32-byte group in flight (outputs 8 m .. 8 m + 7)
 };
 
 // Weight of source pixel x in output o, times `unscale` (border super-steps; the table is the pass's [n_out][stride]).
@@ -150,18 +157,18 @@ __device__ __forceinline__ void push_half(RowState& st, const int (&hi)[32], con
             const int j = (i - 6) / 2;                  // -3 .. 4
             const int slot = (j + kTSlots) & (kTSlots - 1);
             const int o = 8 * Q + j;
-            st.word[(j + 4) & 3] = pack_pixel(make_float4(st.acc[slot][0].x, st.acc[slot][0].y, st.acc[slot][1].x, st.acc[slot][1].y));
+            st.word[(j + 8) & 7] = pack_pixel(make_float4(st.acc[slot][0].x, st.acc[slot][0].y, st.acc[slot][1].x, st.acc[slot][1].y));
             st.acc[slot][0] = st.acc[slot][1] = make_float2(kRoundBias, kRoundBias);
-            if (((j + 4) & 3) == 3) {                   // outputs o - 3 .. o: one aligned group of four
-                const int og = o - 3;
+            if (((j + 8) & 7) == 7) {                   // outputs o - 7 .. o: one aligned group of eight = one 32-byte sector
+                const int og = o - 7;
                 if (FULL) {                             // the whole super-step lies inside the stream's columns: no range tests
-                    if (row_live) *reinterpret_cast<uint4*>(dst_row + size_t(og) * 4) = make_uint4(st.word[0], st.word[1], st.word[2], st.word[3]);
+                    if (row_live) st_global_256(dst_row + size_t(og) * 4, st.word);
                 } else if (row_live) {
                     if (og >= x0 && o < x1) {
-                        *reinterpret_cast<uint4*>(dst_row + size_t(og) * 4) = make_uint4(st.word[0], st.word[1], st.word[2], st.word[3]);
+                        st_global_256(dst_row + size_t(og) * 4, st.word);
                     } else if (o >= x0 && og < x1) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
+                        for (int k = 0; k < 8; ++k)
                             if (og + k >= x0 && og + k < x1) *reinterpret_cast<uint32_t*>(dst_row + size_t(og + k) * 4) = st.word[k];
                     }
                 }
@@ -312,7 +319,7 @@ banded8t_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
 #pragma unroll
         for (int k = 0; k < kTSlots; ++k) st.acc[k][0] = st.acc[k][1] = make_float2(kRoundBias, kRoundBias);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) st.word[k] = 0;
+        for (int k = 0; k < 8; ++k) st.word[k] = 0;
 
         // One block = two super-steps = four quarters of 8 pixels in two register buffers.  Quarters 2 and 3 are fetched
         // (tcgen05.ld) while quarters 0 and 1 are pushed through the filter, and the tile goes back to the MMA warp as soon
@@ -336,7 +343,7 @@ banded8t_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
                 // group of four it completes inside the stream's columns (no range tests): the fast path
                 const int qs = Q + ss;
                 const bool interior = 8 * qs - 3 >= uni_lo && 8 * qs + 10 < uni_hi;
-                const bool fast = interior && 8 * qs - 4 >= sr.x0 && 8 * qs + 3 < sr.x1;
+                const bool fast = interior && 8 * qs - 8 >= sr.x0 && 8 * qs - 1 < sr.x1;   // the group this super-step completes
                 if (fast) push_half<0, false, true>(st, hiA, loA, uw, qs, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
                 else if (interior) push_half<0, false, false>(st, hiA, loA, uw, qs, hp, unscale, dst_row, sr.x0, sr.x1, row_live);
                 else push_half<0, true, false>(st, hiA, loA, uw, qs, hp, unscale, dst_row, sr.x0, sr.x1, row_live);

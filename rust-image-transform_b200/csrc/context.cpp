@@ -612,7 +612,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
             // Rgba8 downscales that are exactly 2:1 horizontally (and at most ~2:1 vertically): the row-band kernel, whose
             // horizontal pass runs from registers (banded8t.cu).  Work items: bands of 128 output rows x column segments.
             if (!exact && mode.load() == 0 && d.bps == 1 && d.channels == 4 && d.oc() == 4 && tma_ok &&
-                ((reinterpret_cast<uintptr_t>(d.dst) | d.dst_pitch) & 15) == 0 && tv->pass.band8t_tiles && tv->pass.band8_limbs == 2 &&
+                ((reinterpret_cast<uintptr_t>(d.dst) | d.dst_pitch) & 31) == 0 && tv->pass.band8t_tiles && tv->pass.band8_limbs == 2 &&
                 th->host->h2_12 && encode_src_map8(lp.jobs[size_t(idx)].src_map8, d.src, d.sh, d.src_pitch)) {
                 FusedGroup* g = nullptr;
                 for (auto& gg : lp.groups)

@@ -60,7 +60,9 @@ def test_prepared_batch_mixes_every_kernel(ctx, ik, oracle, mode):
     assert all(j.status == 0 for j in batch.jobs), [j.status for j in batch.jobs]
     desc = batch.describe()
     ctx.set_mode(ik.MODE_FAST)
-    for name in ({"tc": "banded8_kernel", "f16": "banded_kernel", "fp32": "fused_ring_kernel"}[mode], "up2_kernel", "tile_kernel"):
+    # (default mode: the 2x upscales take the tensor-core kernel too; the other modes keep the CUDA-core upscale kernel)
+    for name in ({"tc": "banded8_kernel", "f16": "banded_kernel", "fp32": "fused_ring_kernel"}[mode],
+                 "banded8u_kernel" if mode == "tc" else "up2_kernel", "tile_kernel"):
         assert name in desc, desc
     assert ("banded8_kernel" in desc) == (mode == "tc") and ("fused_ring_kernel" in desc) == (mode == "fp32")
     stream = torch.cuda.Stream()
@@ -172,9 +174,9 @@ def test_randomised_prepared_batches(ctx, ik, oracle):
     assert not failures, failures[:4]
 
 
-ROW_BAND_SHAPES = [  # Rgba8, exactly 2:1 horizontally, at most ~2:1 vertically, 16-byte aligned rows: (h, w, dw, dh)
-    (384, 512, 256, 192), (130, 264, 132, 65), (700, 1000, 500, 350), (300, 640, 320, 150), (514, 2056, 1028, 257),
-    (700, 1000, 500, 400), (2160, 3840, 1920, 1080), (1090, 768, 384, 545), (64, 96, 48, 32),
+ROW_BAND_SHAPES = [  # Rgba8, exactly 2:1 horizontally, at most ~2:1 vertically, 32-byte aligned destination rows: (h, w, dw, dh)
+    (384, 512, 256, 192), (130, 272, 136, 65), (700, 1008, 504, 350), (300, 640, 320, 150), (514, 2064, 1032, 257),
+    (700, 1008, 504, 400), (2160, 3840, 1920, 1080), (1090, 768, 384, 545), (64, 96, 48, 32),
 ]
 
 
@@ -228,7 +230,7 @@ def test_row_band_kernel_batches_and_fallbacks(ctx, ik, oracle):
     ctx.set_mode(ik.MODE_FAST)
     dev = torch.device("cuda:0")
     cases = [  # (h, w, c, dw, dh, co, dst pitch slack)
-        (384, 512, 4, 256, 192, 4, 0), (1080, 1920, 4, 960, 540, 4, 0), (300, 640, 4, 320, 150, 4, 0), (700, 1000, 4, 500, 350, 4, 0),
+        (384, 512, 4, 256, 192, 4, 0), (1080, 1920, 4, 960, 540, 4, 0), (300, 640, 4, 320, 150, 4, 0), (700, 1008, 4, 504, 350, 4, 0),
         (1236, 736, 4, 368, 549, 4, 0),   # 2.25:1 vertically: ten weight tiles per band, the others nine, in one launch
         (300, 640, 4, 320, 150, 4, 4), (300, 640, 3, 320, 150, 3, 0), (300, 640, 4, 320, 150, 3, 0),
     ]

@@ -269,15 +269,20 @@ UP2_CASES = [  # (h, w, c, filter): output is (2w, 2h)
 
 @pytest.mark.parametrize("case", UP2_CASES)
 @pytest.mark.parametrize("content", ["noise", "edges"])
-def test_exact_2x_upscale_kernel(ctx, ik, oracle, case, content):
+@pytest.mark.parametrize("mode", ["tc", "fp32"])
+def test_exact_2x_upscale_kernel(ctx, ik, oracle, case, content, mode):
+    """Default mode: banded8u.cu (vertical pass as an integer tensor-core product, 16-bit weights) where its layout applies
+    (Rgb8 CatmullRom, Rgba8), else up2.cu; FAST_FP32: always up2.cu (CUDA cores, f32 weights)."""
     h, w, c, filt = case
     src = {"noise": splitmix_noise, "edges": checker}[content]((h, w, c))
-    _fast(ctx, ik)
+    _fast(ctx, ik, mode)
     before = ctx.kernel_launches
     got = ctx.resize(src, 2 * w, 2 * h, filt)
+    _fast(ctx, ik)
     assert ctx.kernel_launches - before == 1, "expected a single fused launch"
     want = oracle.resize_exact(src, 2 * w, 2 * h, filt)
-    _check_fast(got, want, (case, content), max_off=0.002 if content == "noise" else 0.06)
+    scale = 8 if mode == "tc" else 1
+    _check_fast(got, want, (case, content), max_off=scale * (0.002 if content == "noise" else 0.06))
 
 
 # ---- Luma8 / LumaA8 downscales on the ring kernel (SURVEY 8f N3) -------------------------------------------------
