@@ -284,8 +284,8 @@ void Device::release_lane(Lane* l) {
     cv_.notify_all();
 }
 
-std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_out) {
-    const auto key = std::make_tuple(filter, n_in, n_out);
+std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_out, bool vertical) {
+    const auto key = std::make_tuple(filter, n_in, n_out, vertical);
     {
         std::lock_guard<std::mutex> lk(mu_);
         auto it = tabs_.find(key);
@@ -295,7 +295,7 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
         }
     }
     ctx_->stats.table_misses.fetch_add(1, std::memory_order_relaxed);
-    auto host = ctx_->pass(filter, n_in, n_out);
+    auto host = ctx_->pass(filter, n_in, n_out, vertical);
     if (!host) fail(kInvalidArg, "cannot plan pass");
     // One stream-ordered allocation (left | right | w | ring forms | 2x-upscale pairs | band forms, each 256-byte aligned),
     // filled from one pinned staging block by one asynchronous copy on the device's table stream.  Nothing here waits
@@ -450,14 +450,14 @@ Context::~Context() {
     devs_.clear();
 }
 
-std::shared_ptr<const PassPlan> Context::pass(int filter, uint32_t n_in, uint32_t n_out) {
-    const auto key = std::make_tuple(filter, n_in, n_out);
+std::shared_ptr<const PassPlan> Context::pass(int filter, uint32_t n_in, uint32_t n_out, bool vertical) {
+    const auto key = std::make_tuple(filter, n_in, n_out, vertical);
     {
         std::lock_guard<std::mutex> lk(pass_mu_);
         auto it = passes_.find(key);
         if (it != passes_.end()) return it->second;
     }
-    auto p = build_pass(filter, n_in, n_out);
+    auto p = build_pass(filter, n_in, n_out, vertical);
     std::lock_guard<std::mutex> lk(pass_mu_);
     if (passes_.size() >= kMaxCachedTables) {
         passes_.erase(pass_order_.front());
@@ -585,8 +585,8 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
             validate_job(d);
             if (d.sw == 0 || d.sh == 0 || d.dw == 0 || d.dh == 0 || (d.sw == d.dw && d.sh == d.dh))
                 fail(kInvalidArg, "degenerate resize (empty or same-size) must be handled by the caller");
-            auto tv = dev.tables(d.filter, d.sh, d.dh);
-            auto th = dev.tables(d.filter, d.sw, d.dw);
+            auto tv = dev.tables(d.filter, d.sh, d.dh, true);
+            auto th = dev.tables(d.filter, d.sw, d.dw, false);
             DevJob j{};
             j.src = static_cast<const uint8_t*>(d.src);
             j.dst = static_cast<uint8_t*>(d.dst);

@@ -134,7 +134,8 @@ public:
     int index() const { return index_; }
     int sm_count() const { return sm_count_; }
 
-    std::shared_ptr<DevTables> tables(int filter, uint32_t n_in, uint32_t n_out);
+    // vertical: the pass is used vertically (its tensor-core operand tiles are built and uploaded too)
+    std::shared_ptr<DevTables> tables(int filter, uint32_t n_in, uint32_t n_out, bool vertical);
     Lane* acquire_lane(bool may_grow = false);
     void release_lane(Lane* l);
     int lane_count() const { return kBatchLanes; }   // lanes a batch worker takes (tickets may have grown the pool beyond it)
@@ -149,8 +150,8 @@ private:
     std::vector<std::unique_ptr<Lane>> lanes_;
     std::vector<Lane*> free_;
     uint64_t next_ticket_ = 0, serving_ = 0;   // lanes are handed out in arrival order
-    std::map<std::tuple<int, uint32_t, uint32_t>, std::shared_ptr<DevTables>> tabs_;
-    std::vector<std::tuple<int, uint32_t, uint32_t>> tab_order_;
+    std::map<std::tuple<int, uint32_t, uint32_t, bool>, std::shared_ptr<DevTables>> tabs_;
+    std::vector<std::tuple<int, uint32_t, uint32_t, bool>> tab_order_;
     // Table uploads: one stream, a few reusable pinned staging blocks (each guarded by the event of its last copy).
     struct StageBlock { void* p = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool busy = false; };
     cudaStream_t table_stream_ = nullptr;
@@ -177,7 +178,7 @@ public:
     Device& device(int i) { return *devs_[i]; }
     int next_device() { return int(rr_.fetch_add(1, std::memory_order_relaxed) % devs_.size()); }
 
-    std::shared_ptr<const PassPlan> pass(int filter, uint32_t n_in, uint32_t n_out);
+    std::shared_ptr<const PassPlan> pass(int filter, uint32_t n_in, uint32_t n_out, bool vertical);
 
     std::atomic<int> mode{0};
     std::atomic<uint64_t> launches{0};
@@ -212,8 +213,8 @@ private:
     std::vector<std::unique_ptr<Device>> devs_;
     std::atomic<uint64_t> rr_{0};
     std::mutex pass_mu_;
-    std::map<std::tuple<int, uint32_t, uint32_t>, std::shared_ptr<const PassPlan>> passes_;
-    std::vector<std::tuple<int, uint32_t, uint32_t>> pass_order_;
+    std::map<std::tuple<int, uint32_t, uint32_t, bool>, std::shared_ptr<const PassPlan>> passes_;
+    std::vector<std::tuple<int, uint32_t, uint32_t, bool>> pass_order_;
     std::mutex submit_mu_;
     std::vector<std::unique_ptr<SubmitQueue>> submit_;   // one per device, created on first use
 };

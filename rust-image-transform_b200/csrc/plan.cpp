@@ -168,7 +168,7 @@ int target_dims(uint32_t ow, uint32_t oh, bool has_w, uint32_t w, bool has_h, ui
     return 0;
 }
 
-std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n_out) {
+std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n_out, bool vertical_forms) {
     FilterDef f;
     if (!lookup_filter(filter, &f) || n_in == 0 || n_out == 0) return nullptr;
     auto plan = std::make_shared<PassPlan>();
@@ -298,7 +298,7 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
                 k_lo[r] = p.left[o0];
                 band_chunks = std::max(band_chunks, (p.right[o1 - 1] - k_lo[r] + kBand8Chunk - 1) / kBand8Chunk);
             }
-            if (wmax > 0.0f && band_chunks >= 1 && band_chunks <= kBand8TMaxChunks) {
+            if (vertical_forms && wmax > 0.0f && band_chunks >= 1 && band_chunks <= kBand8TMaxChunks) {
                 int shift = int(std::floor(std::log2(120.0 * kBand8Base / double(wmax))));
                 shift = std::min(shift, 21);
                 const double scale = std::ldexp(1.0, shift);
@@ -335,7 +335,7 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
         }
     }
     // Band form for the tensor-core vertical pass (downscales and 1:1 only).
-    if (n_in >= n_out && n_in >= uint32_t(kBandChunk)) {
+    if (vertical_forms && n_in >= n_out && n_in >= uint32_t(kBandChunk)) {
         const uint32_t n_chunks = (n_in + kBandChunk - 1) / kBandChunk;
         const uint32_t n_groups = (n_out + kBandGroup - 1) / kBandGroup;
         std::vector<int32_t> gbase(n_chunks + 1, 0), ghi(n_chunks, 0);
@@ -379,7 +379,7 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
         }
     }
     // 8-bit band form: integer weights in base-256 digits.
-    if (n_in >= n_out && n_in >= uint32_t(kBand8Chunk) && p.max_count <= 240) {
+    if (vertical_forms && n_in >= n_out && n_in >= uint32_t(kBand8Chunk) && p.max_count <= 240) {
         const int limbs = kBand8DefaultLimbs;
         const uint32_t n_chunks = (n_in + kBand8Chunk - 1) / kBand8Chunk;
         const uint32_t n_groups = (n_out + kBand8Group - 1) / kBand8Group;

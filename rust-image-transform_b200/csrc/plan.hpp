@@ -108,7 +108,9 @@ constexpr float kBandScaleH = 1024.0f;
 uint16_t f32_to_f16_rn(float f);        // IEEE binary16, round to nearest even (host)
 float f16_to_f32(uint16_t h);
 
-std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n_out);
+// vertical_forms: also build the tensor-core operand tiles (band_*, band8, band8t), which only the vertical use of a pass
+// needs (they are most of a pass's bytes).
+std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n_out, bool vertical_forms = true);
 constexpr int kBand8DefaultLimbs = 2;
 
 float filter_support(int filter);

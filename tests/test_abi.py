@@ -244,7 +244,34 @@ def test_band8t_tiles_hold_the_same_integers_as_band8(ik, filt, n_in, n_out):
 def test_band8t_needs_a_ratio_near_two(ik):
     from imagekit_cuda import engine
     assert engine.pass_band8t(4, 3024, 300) is None     # a band of 128 outputs spans far more than 10 chunks
-    assert engine.pass_band8t(4, 100, 200) is None
+    assert engine.pass_band8t(4, 100, 150) is None      # an upscale that is not 2x
+
+
+@pytest.mark.parametrize("filt,n_in", [(2, 1080), (4, 100), (1, 77), (3, 640)])
+def test_band8t_of_a_2x_upscale_is_the_quantised_pass(ik, oracle, filt, n_in):
+    """Exact 2x upscales get the row-band tiles too (banded8u.cu): three chunks per band, rows sum to a power of two, every
+    integer weight within half a unit (plus the sum correction) of w * 2^shift."""
+    from imagekit_cuda import engine
+    n_out = 2 * n_in
+    nc, k_lo, t = engine.pass_band8t(filt, n_in, n_out)
+    assert 1 <= nc <= 4 and t.shape[0] == (n_out + 127) // 128
+    left, count, w = oracle.pass_table(filt, n_in, n_out)
+    W = np.zeros((t.shape[0] * 128, n_in + 256), np.int64)
+    for r in range(t.shape[0]):
+        for c in range(nc):
+            val = t[r, c, 0].astype(np.int64) * 256 + t[r, c, 1].astype(np.int64)
+            W[128 * r:128 * r + 128, k_lo[r] + 32 * c:k_lo[r] + 32 * c + 32] += val
+    assert not W[n_out:].any() and not W[:, n_in:].any()
+    total = int(W[0].sum())
+    shift = total.bit_length() - 1
+    assert total == 1 << shift and 10 <= shift <= 21
+    for o in range(n_out):
+        row = W[o]
+        assert row.sum() == total
+        nz = np.flatnonzero(row)
+        assert nz[0] >= left[o] and nz[-1] < left[o] + count[o]
+        err = np.abs(row[left[o]:left[o] + count[o]] / float(total) - w[o, :count[o]].astype(np.float64))
+        assert err.max() <= (count[o] / 2 + 1) / float(total)
 
 
 def test_band8_needs_a_narrow_chunk_window(ik):
