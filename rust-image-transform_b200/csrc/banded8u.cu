@@ -124,36 +124,8 @@ __device__ __forceinline__ uint32_t pack4(float a, float b, float c, float d) { 
 // pixels of this thread's row = 4 C words, which leave as 32-byte groups (one whole sector per lane and store: with lane =
 // row a warp's store touches 32 different rows, so anything smaller than a sector is a partial write).  The row's output
 // stream lags 32-byte alignment by CW words here: `carry` holds the words of the group in flight.  win: the last T pixels.
-// One new pixel: the window moves on, the pair it completes is accumulated.  TRIM: the pass's first frame tap feeds only the
-// even output and its last one only the odd output (every symmetric kernel at exactly 2x), so those two taps are scalar
-// FMAs instead of packed ones (a fifth of the FMA pipe's cycles for T = 5).
-template <int C, int T, int ADV, bool EDGE, bool TRIM>
-__device__ __forceinline__ void push_pixel(float (&win)[T][C], float2 (&acc)[C], const int* hi, const int* lo, const float2 (&up)[T], int k,
-                                           const float2* __restrict__ pairs, int n_in, float unscale) {
-#pragma unroll
-    for (int t = 0; t + 1 < T; ++t)
-#pragma unroll
-        for (int c = 0; c < C; ++c) win[t][c] = win[t + 1][c];                 // (register renaming once unrolled)
-#pragma unroll
-    for (int c = 0; c < C; ++c) win[T - 1][c] = __int2float_rn(hi[c] * kBand8Base + lo[c]);
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = make_float2(kRoundBias, kRoundBias);
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-        float2 wt = up[t];
-        if (EDGE) {
-            const float2 g = __ldg(pairs + size_t(min(max(k, 0), n_in - 1)) * T + t);
-            wt = make_float2(g.x * unscale, g.y * unscale);
-        }
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            if (TRIM && t == 0) acc[c].x = fmaf(wt.x, win[t][c], acc[c].x);
-            else if (TRIM && t == T - 1) acc[c].y = fmaf(wt.y, win[t][c], acc[c].y);
-            else acc[c] = __ffma2_rn(wt, make_float2(win[t][c], win[t][c]), acc[c]);
-        }
-    }
-}
-
+// TRIM: the pass's first frame tap feeds only the even output and its last one only the odd output (every symmetric kernel
+// at exactly 2x), so those two taps are scalar FMAs instead of packed ones.
 template <int C, int T, int ADV, int CW, bool EDGE, bool TRIM>
 __device__ __forceinline__ void push_unit(float (&win)[T][C], uint32_t (&carry)[7], const int (&hi)[8 * C], const int (&lo)[8 * C],
                                           const float2 (&up)[T], int x0, const float2* __restrict__ pairs, int n_in, float unscale,
@@ -163,21 +135,60 @@ __device__ __forceinline__ void push_unit(float (&win)[T][C], uint32_t (&carry)[
 #pragma unroll
     for (int j = 0; j < CW; ++j) word[j] = carry[j];
     uint32_t* const w = word + CW;   // the unit's own words
+    // the T - 1 pixels kept from before and the eight new ones, as one run: pair i of the unit reads s[i .. i + T - 1]
+    float smp[T - 1 + kUUnitPx][C];
 #pragma unroll
-    for (int i = 0; i < kUUnitPx; i += 2) {   // two pixels = two pairs of outputs = 4 C bytes = C words
-        float2 a[C], b[C];
-        push_pixel<C, T, ADV, EDGE, TRIM>(win, a, hi + i * C, lo + i * C, up, x0 - ADV + i, pairs, n_in, unscale);
-        push_pixel<C, T, ADV, EDGE, TRIM>(win, b, hi + (i + 1) * C, lo + (i + 1) * C, up, x0 - ADV + i + 1, pairs, n_in, unscale);
-        // bytes: even output of the first pair (C channels), its odd output, then the second pair's
-        if (C == 4) {
-            w[2 * i] = pack4(a[0].x, a[1].x, a[2].x, a[3].x);
-            w[2 * i + 1] = pack4(a[0].y, a[1].y, a[2].y, a[3].y);
-            w[2 * i + 2] = pack4(b[0].x, b[1].x, b[2].x, b[3].x);
-            w[2 * i + 3] = pack4(b[0].y, b[1].y, b[2].y, b[3].y);
-        } else {
-            w[3 * (i >> 1)] = pack4(a[0].x, a[1].x, a[2].x, a[0].y);
-            w[3 * (i >> 1) + 1] = pack4(a[1].y, a[2].y, b[0].x, b[1].x);
-            w[3 * (i >> 1) + 2] = pack4(b[2].x, b[0].y, b[1].y, b[2].y);
+    for (int t = 0; t + 1 < T; ++t)
+#pragma unroll
+        for (int c = 0; c < C; ++c) smp[t][c] = win[t + 1][c];
+#pragma unroll
+    for (int i = 0; i < kUUnitPx; ++i)
+#pragma unroll
+        for (int c = 0; c < C; ++c) smp[T - 1 + i][c] = __int2float_rn(hi[i * C + c] * kBand8Base + lo[i * C + c]);
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int c = 0; c < C; ++c) win[t][c] = smp[kUUnitPx - 1 + t][c];   // (win[0] is only a placeholder: T - 1 pixels carry over)
+#pragma unroll
+    for (int h = 0; h < kUUnitPx; h += 4) {   // four pairs at a time: 4 C independent accumulation chains, taps outermost
+        float2 acc[4][C];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[i][c] = make_float2(kRoundBias, kRoundBias);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float2 wt = up[t];
+                if (EDGE) {
+                    const float2 g = __ldg(pairs + size_t(min(max(x0 - ADV + h + i, 0), n_in - 1)) * T + t);
+                    wt = make_float2(g.x * unscale, g.y * unscale);
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float v = smp[h + i + t][c];
+                    if (TRIM && t == 0) acc[i][c].x = fmaf(wt.x, v, acc[i][c].x);
+                    else if (TRIM && t == T - 1) acc[i][c].y = fmaf(wt.y, v, acc[i][c].y);
+                    else acc[i][c] = __ffma2_rn(wt, make_float2(v, v), acc[i][c]);
+                }
+            }
+        }
+        // bytes: per pair the even output (C channels), then the odd one
+#pragma unroll
+        for (int i = 0; i < 4; i += 2) {
+            const float2(&a)[C] = acc[i];
+            const float2(&b)[C] = acc[i + 1];
+            if (C == 4) {
+                w[2 * (h + i)] = pack4(a[0].x, a[1].x, a[2].x, a[3].x);
+                w[2 * (h + i) + 1] = pack4(a[0].y, a[1].y, a[2].y, a[3].y);
+                w[2 * (h + i) + 2] = pack4(b[0].x, b[1].x, b[2].x, b[3].x);
+                w[2 * (h + i) + 3] = pack4(b[0].y, b[1].y, b[2].y, b[3].y);
+            } else {
+                w[3 * ((h + i) >> 1)] = pack4(a[0].x, a[1].x, a[2].x, a[0].y);
+                w[3 * ((h + i) >> 1) + 1] = pack4(a[1].y, a[2].y, b[0].x, b[1].x);
+                w[3 * ((h + i) >> 1) + 2] = pack4(b[2].x, b[0].y, b[1].y, b[2].y);
+            }
         }
     }
     constexpr int kGroups = (CW + 4 * C) / 8, kLeft = (CW + 4 * C) % 8;
