@@ -235,6 +235,48 @@ def run_cfg3_shard(ik, ctx, torch, dev, dist, rank, world, barrier, args):
                     "api": "one ikc_resize_batch call per rank over its shard, pinned host buffers"}}
 
 
+def run_other_workloads(ik, ctx, torch, dev, dist, barrier, names):
+    """The other BASELINE workloads (configs 1 and 4; config 3 has its own leg), device-resident, 32 images per launch, the
+    same timing rules as the headline (inputs larger than L2, CUDA events on the launch stream, max over ranks): so that
+    the driver's record carries their roofline fractions too, not only the builder's runs."""
+    from imagekit_cuda.sharding import aggregate_throughput
+    peak, _ = measured_peak()
+    out = {}
+    for name in names:
+        sw, sh, ch, dw, dh, filt, _, desc = WORKLOADS[name]
+        batch = 32
+        g = torch.Generator(device=dev)
+        g.manual_seed(0xBEEF + len(name))
+        src = torch.randint(0, 256, (batch, sh, sw, ch), dtype=torch.uint8, device=dev, generator=g)
+        dst = torch.zeros((batch, dh, dw, ch), dtype=torch.uint8, device=dev)
+        jobs = [(src[i].data_ptr(), sw, sh, sw * ch, dst[i].data_ptr(), dw, dh, dw * ch, ch, filt) for i in range(batch)]
+        prepared = ctx.prepare_batch(0, jobs)
+        stream = torch.cuda.Stream(device=dev)
+        for _ in range(3):
+            prepared.launch(stream.cuda_stream)
+        stream.synchronize()
+        barrier()
+        steps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            prepared.launch(stream.cuda_stream)
+        e1.record(stream)
+        stream.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        _, ms_max, value = aggregate_throughput(batch * steps * dw * dh / 1e6, ms, dist, dev)
+        algo = batch * (sw * sh * ch + dw * dh * ch)
+        out[name] = {"workload": f"{name}: {desc}", "value": value, "unit": UNIT, "images_per_launch_per_gpu": batch, "steps": steps,
+                     "us_per_image_this_rank": ms / steps / batch * 1e3, "kernel": prepared.describe(),
+                     "roofline_frac_this_rank": algo / (ms / steps * 1e-3) / 1e9 / peak,
+                     "working_set_mb": algo / 1e6}
+        prepared.free()
+        del src, dst
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_cfg5_upload(ik, ctx, dist, dev, rank, world, barrier, args):
     """BASELINE config 5, the /upload shape (reference src/lib.rs:246-309): CPU decode -> GPU resize -> CPU webp q=80 encode
     over 256 synthetic 8 MP JPEGs, split over the ranks (one GPU each) and, inside a rank, over its share of the host
@@ -381,6 +423,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-shard", action="store_true", help="skip the cfg3_shard leg (1024 thumbnails, strong scaling)")
     ap.add_argument("--shard-images", type=int, default=1024)
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads leg (cfg1, cfg4 device-resident)")
     ap.add_argument("--no-upload", action="store_true", help="skip the cfg5_upload leg (decode -> resize -> webp encode of 8 MP JPEGs)")
     ap.add_argument("--upload-images", type=int, default=256)
     args = ap.parse_args()
@@ -540,6 +583,11 @@ def main():
     if not args.no_shard:
         cfg3_shard = run_cfg3_shard(ik, ctx, torch, dev, dist, rank, world, barrier, args)
 
+    # ---- the other device-resident BASELINE workloads, briefly (the headline stays the one named by --workload)
+    other_workloads = None
+    if not args.no_others:
+        other_workloads = run_other_workloads(ik, ctx, torch, dev, dist, barrier, [n for n in ("cfg1", "cfg4") if n != args.workload])
+
     # ---- BASELINE config 5 as it is stated: 256 x 8 MP JPEG uploads, CPU decode -> GPU resize -> CPU webp encode,
     # split over the ranks; the library's begin / end call lets every worker hide the GPU leg behind the codecs
     cfg5_upload = None
@@ -617,6 +665,7 @@ def main():
         "e2e_inprocess": e2e_inprocess,
         "cfg3_shard": cfg3_shard,
         "cfg5_upload": cfg5_upload,
+        "other_workloads": other_workloads,
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "parity": parity,
