@@ -273,7 +273,8 @@ IKC_API int ikc_resize_image_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, u
                                 size_t dst_capacity, uint32_t* tw, uint32_t* th);
 
 /* Batched resize of independent images (8-bit).  Jobs are sharded round-robin over the context's
- * devices (job i -> device i mod G); every device pipelines H2D / kernel / D2H over its lanes.
+ * devices (job i -> device i mod G); every device pipelines H2D / kernel / D2H over its lanes, and runs of small
+ * images (<= 1 MB of pixels each) share one staged upload, one plan, one launch per kernel variant and one download.
  * No collective: images are independent.  Returns IKC_OK if every job succeeded, else the first
  * failing status; per-job results are in jobs[i].status. */
 IKC_API int ikc_resize_batch(ikc_ctx* ctx, ikc_job* jobs, size_t n);

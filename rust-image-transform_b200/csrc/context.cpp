@@ -1189,10 +1189,44 @@ void Context::resize_batch_host(JobDesc* descs, size_t n, int* status, int* devi
                 }
             };
             int k = 0;
+            // Small images (thumbnail sources, icons) are not worth a plan, a descriptor upload, a launch and two copies each:
+            // runs of them are staged together and share ONE upload, plan, launch per kernel variant and download.
+            std::vector<size_t> small;
+            size_t small_bytes = 0;
+            auto flush_small = [&] {
+                if (small.empty()) return;
+                drain(k);
+                std::vector<JobDesc> gd(small.size());
+                std::vector<int> gst(small.size(), kOk);
+                std::vector<std::string> gerr(small.size());
+                for (size_t j = 0; j < small.size(); ++j) gd[j] = descs[small[j]];
+                try {
+                    resize_group_host(dev, gd.data(), gd.size(), gst.data(), gerr.data(), lanes[size_t(k)]);
+                } catch (const Error& e) {
+                    for (size_t j = 0; j < small.size(); ++j) { gst[j] = e.status; gerr[j] = e.what; }
+                }
+                for (size_t j = 0; j < small.size(); ++j) {
+                    status[small[j]] = gst[j];
+                    if (gst[j] != kOk) errors[size_t(g)] = gerr[j];
+                }
+                small.clear();
+                small_bytes = 0;
+                k = (k + 1) % L;
+            };
+            constexpr size_t kSmallJob = size_t(1) << 20, kSmallGroupJobs = 32, kSmallGroupBytes = size_t(16) << 20;
             for (size_t i = size_t(g); i < n; i += size_t(G)) {
                 next = i + size_t(G);
                 status[i] = kOk;
                 device_out[i] = g;
+                const size_t job_bytes = size_t(descs[i].sw) * descs[i].sh * size_t(descs[i].channels & 0xff) * size_t(std::max(descs[i].bps, 1)) +
+                                         size_t(descs[i].dw) * descs[i].dh * 4u * size_t(std::max(descs[i].bps, 1));
+                if (job_bytes <= kSmallJob) {   // (validated, counted and answered inside the group call)
+                    small.push_back(i);
+                    small_bytes += job_bytes;
+                    if (small.size() >= kSmallGroupJobs || small_bytes >= kSmallGroupBytes) flush_small();
+                    continue;
+                }
+                flush_small();
                 try {
                     validate_job(descs[i]);
                     if (trivial_resize(descs[i])) {
@@ -1210,6 +1244,7 @@ void Context::resize_batch_host(JobDesc* descs, size_t n, int* status, int* devi
                     cudaStreamSynchronize(lanes[size_t(k)]->stream);
                 }
             }
+            flush_small();
             for (int q = 0; q < L; ++q) drain(q);
         } catch (...) {
             // anything that is not an ikc::Error (std::bad_alloc from the planner's vectors, ...): nothing may cross the
@@ -1290,7 +1325,7 @@ void Context::end_host(void* ticket) {
 
 // ---- coalescing submit queue ---------------------------------------------------------------------
 
-void Context::resize_group_host(Device& dev, const JobDesc* descs, size_t n, int* status, std::string* errors) {
+void Context::resize_group_host(Device& dev, const JobDesc* descs, size_t n, int* status, std::string* errors, Lane* lane) {
     check_cuda(cudaSetDevice(dev.ordinal()), "cudaSetDevice");
     struct Slot { size_t in_off = 0, out_off = 0, in_pitch = 0, out_pitch = 0; bool live = false; };
     std::vector<Slot> slot(n);
@@ -1320,8 +1355,11 @@ void Context::resize_group_host(Device& dev, const JobDesc* descs, size_t n, int
     }
     if (total_in == 0) return;
     LaunchPlan lp;  // (declared before the lane guard: its table references go only after the guard has drained the stream)
-    Lane* l = dev.acquire_lane();
-    struct Release { Device& d; Lane* l; ~Release() { cudaStreamSynchronize(l->stream); d.release_lane(l); } } release{dev, l};
+    Lane* l = lane ? lane : dev.acquire_lane();
+    struct Release {
+        Device& d; Lane* l; bool own;
+        ~Release() { cudaStreamSynchronize(l->stream); if (own) d.release_lane(l); }
+    } release{dev, l, lane == nullptr};
     l->h_in.reserve(total_in);
     l->d_in.reserve(total_in);
     l->h_out.reserve(total_out);

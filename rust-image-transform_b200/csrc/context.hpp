@@ -207,7 +207,8 @@ public:
     void submit_host(const JobDesc& d);
     // One group of host jobs on one lane of `dev`: one staged upload, one plan, one launch per kernel variant, one
     // download.  Per-job results in status / errors (size n).
-    void resize_group_host(Device& dev, const JobDesc* descs, size_t n, int* status, std::string* errors);
+    // `lane`: a lane the caller already holds (else one is acquired for the call).
+    void resize_group_host(Device& dev, const JobDesc* descs, size_t n, int* status, std::string* errors, Lane* lane = nullptr);
 
 private:
     std::vector<std::unique_ptr<Device>> devs_;

@@ -517,3 +517,43 @@ def test_split_call_begin_end(ik, oracle):
     with pytest.raises(ik.ImageKitError):
         ctx.resize_begin(src, 100, 10, 9)
     ctx.close()
+
+
+def test_host_batch_groups_small_images(ik, oracle):
+    """ikc_resize_batch: runs of small images (<= 1 MB of pixels) share one staged upload, plan, launch per kernel variant and
+    download; big ones keep their per-image pipeline; a bad job in a run fails alone."""
+    ctx = ik.Context([0])
+    rng = np.random.default_rng(5)
+    srcs, sizes = [], []
+    for i in range(70):
+        if i % 23 == 11:
+            h, w, c = 1200, 1600, 3                                    # a big one in the middle of the run
+        else:
+            h, w, c = int(rng.integers(100, 300)), int(rng.integers(100, 400)), int(rng.choice([3, 3, 4]))
+        srcs.append(splitmix_noise((h, w, c), image_id=300 + i))
+        r = float(rng.uniform(2.0, 4.0))                               # thumbnails of small sources (same-size: a few)
+        sizes.append((w, h) if i % 17 == 3 else (max(8, int(w / r)), max(8, int(h / r))))
+    before = ctx.stats()
+    outs, jobs = ctx.resize_batch(srcs, sizes)
+    after = ctx.stats()
+    assert all(j.status == 0 for j in jobs)
+    for s, (dw, dh), o_ in zip(srcs, sizes, outs):
+        want = oracle.resize_exact(s, dw, dh, oracle.LANCZOS3) if (dw, dh) != (s.shape[1], s.shape[0]) else s
+        assert np.abs(o_.astype(int) - want.reshape(o_.shape).astype(int)).max() <= TOL, (s.shape, dw, dh)
+    assert after["calls"] - before["calls"] == 70 and after["trivial"] - before["trivial"] == sum(1 for i in range(70) if i % 17 == 3)
+    assert after["launches"] - before["launches"] <= 33, (before, after)    # 66 resizes: groups of up to 32 share their launches
+    # one bad job (unknown filter is per batch; use an absurd pitch instead) fails alone
+    L = ik._lib.load()
+    n = 5
+    arr = (ik._lib.Job * n)()
+    keep = []
+    for i in range(n):
+        s = splitmix_noise((64, 64, 3), image_id=i)
+        d = np.zeros((32, 32, 3), np.uint8)
+        keep.append((s, d))
+        arr[i] = ik._lib.Job(s.ctypes.data, d.ctypes.data, 64, 64, 32, 32, 64 * 3 if i != 2 else 5, 32 * 3, 3, ik.FILTER_LANCZOS3, 0, 0)
+    rc = L.ikc_resize_batch(ctx._h, arr, n)
+    assert rc != 0 and [arr[i].status for i in range(n)] == [0, 0, ik._lib.ERR_INVALID_ARG, 0, 0]
+    for i in (0, 1, 3, 4):
+        assert np.abs(keep[i][1].astype(int) - oracle.resize_exact(keep[i][0], 32, 32, oracle.LANCZOS3).astype(int)).max() <= TOL
+    ctx.close()
