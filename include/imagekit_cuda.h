@@ -209,13 +209,13 @@ IKC_API uint32_t ikc_pass_band8(int filter, uint32_t n_in, uint32_t n_out, uint3
                                 int8_t* tiles, size_t tiles_cap);
 
 /* Row-band form of the same integer weights (the A operand of the kernel whose accumulator lanes are output rows;
- * inspection for tests; no GPU needed).  Band r = outputs [128 r, 128 r + 128); its chunks of 32 source indices start at
- * k_lo[r].  tiles: per band, chunk (*chunks of them) and digit (most significant first) one s8 operand tile of 128 rows
+ * inspection for tests; no GPU needed).  Band r = outputs [*rows r, *rows r + *rows), *rows <= 128 (the height that costs
+ * least: 120 at exactly 2:1, where a band then spans 8 chunks instead of 9); its chunks of 32 source indices start at k_lo[r].  tiles: per band, chunk (*chunks of them) and digit (most significant first) one s8 operand tile of 128 rows
  * x 32 indices, element (row m, index k) at (k / 16) * 2048 + (m / 8) * 128 + (m % 8) * 16 + (k % 16).  Returns the
  * number of bands (0: the pass has no such form -- ratio well above 2, or no 8-bit band form at all -- or a buffer is too
- * small); k_lo == tiles == NULL: only *chunks and the count. */
-IKC_API uint32_t ikc_pass_band8t(int filter, uint32_t n_in, uint32_t n_out, uint32_t* chunks, int32_t* k_lo, int8_t* tiles,
-                                 size_t tiles_cap);
+ * small); k_lo == tiles == NULL: only *chunks, *rows and the count. */
+IKC_API uint32_t ikc_pass_band8t(int filter, uint32_t n_in, uint32_t n_out, uint32_t* chunks, uint32_t* rows, int32_t* k_lo,
+                                 int8_t* tiles, size_t tiles_cap);
 
 /* ---- host-buffer entry points (the drop-in path; include H2D + D2H) -------------------------- */
 

@@ -162,12 +162,14 @@ uint32_t ikc_pass_band8(int filter, uint32_t n_in, uint32_t n_out, uint32_t* lim
     return chunks;
 }
 
-uint32_t ikc_pass_band8t(int filter, uint32_t n_in, uint32_t n_out, uint32_t* chunks, int32_t* k_lo, int8_t* tiles, size_t tiles_cap) {
+uint32_t ikc_pass_band8t(int filter, uint32_t n_in, uint32_t n_out, uint32_t* chunks, uint32_t* rows, int32_t* k_lo, int8_t* tiles,
+                         size_t tiles_cap) {
     uint32_t bands = 0;
     guarded([&] {
         auto p = build_pass(filter, n_in, n_out);
         if (!p || p->band8t.chunks == 0) return;
         if (chunks) *chunks = uint32_t(p->band8t.chunks);
+        if (rows) *rows = uint32_t(p->band8t.rows);
         if (k_lo || tiles) {
             if (!k_lo || !tiles || tiles_cap < p->band8t.tiles.size()) return;
             std::memcpy(k_lo, p->band8t.k_lo.data(), sizeof(int32_t) * p->band8t.k_lo.size());

@@ -201,7 +201,7 @@ banded8t_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
 
     const WorkItem it = items[blockIdx.x];
     const DevJob* __restrict__ J = jobs + it.job;
-    const int band = it.oy0 / kTRows;
+    const int band = it.oy0 / J->v.band8t_rows;                    // (bands are band8t_rows <= 128 outputs high)
     const int nch = J->v.band8t_chunks;                            // tiles per band and digit (geom.chunks sizes shared memory)
     const int k_lo = __ldg(J->v.band8t_klo + band);
 
@@ -380,7 +380,6 @@ banded8t_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ it
 size_t banded8t_smem_bytes(const Band8TGeom& g) {
     return size_t(kTHeaderBytes) + size_t(kTStages) * kTBlockStage + size_t(g.chunks) * 2 * kTWTile;
 }
-int banded8t_band_rows() { return kTRows; }
 
 cudaError_t launch_banded8t(const DevJob* jobs, const WorkItem* items, const Band8TGeom& geom, cudaStream_t stream) {
     if (geom.chunks < 1 || geom.chunks > kBand8TMaxChunks) return cudaErrorInvalidValue;

@@ -397,6 +397,7 @@ std::shared_ptr<DevTables> Device::tables(int filter, uint32_t n_in, uint32_t n_
     t->pass.band8t_tiles = host->band8t.chunks ? reinterpret_cast<const int8_t*>(at(i_band8t)) : nullptr;
     t->pass.band8t_klo = host->band8t.chunks ? reinterpret_cast<const int32_t*>(at(i_klo8t)) : nullptr;
     t->pass.band8t_chunks = host->band8t.chunks;
+    t->pass.band8t_rows = host->band8t.rows;
     t->pass.up2_off = host->up2_off;
     t->pass.up2_taps = host->up2_taps;
     t->pass.up2_uni_lo = host->up2_uni_lo;
@@ -732,9 +733,11 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         FusedGroup* g = nullptr;
         for (auto& gg : lp.groups)
             if (gg.band8t) g = &gg;
-        const int rows = banded8t_band_rows();
         size_t bands = 0;
-        for (int idx : b8t_jobs) bands += (lp.jobs[size_t(idx)].dh + rows - 1) / rows;
+        for (int idx : b8t_jobs) {
+            const DevJob& j = lp.jobs[size_t(idx)];
+            bands += (j.dh + uint32_t(j.v.band8t_rows) - 1) / uint32_t(j.v.band8t_rows);
+        }
         int want = 1;
         double best = 1e30;
         for (int sgs = 1; sgs <= 64; ++sgs) {
@@ -744,7 +747,7 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
         }
         for (int idx : b8t_jobs) {
             const DevJob& j = lp.jobs[size_t(idx)];
-            const int dw = int(j.dw), dh = int(j.dh);
+            const int dw = int(j.dw), dh = int(j.dh), rows = j.v.band8t_rows;
             const int segs = std::max(1, std::min(want, dw / 128));
             for (int oy = 0; oy < dh; oy += rows)
                 for (int k = 0; k < segs; ++k) {

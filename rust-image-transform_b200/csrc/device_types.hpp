@@ -43,8 +43,9 @@ struct DevPass {
     // Row-band form of the same digits (plan.hpp: Band8T), used by the kernel whose accumulator lanes are output rows
     // (banded8t.cu).
     const int8_t* band8t_tiles;      // [n_bands][band8t_chunks][2][128 x 32] s8, operand layout; nullptr if none
-    const int32_t* band8t_klo;       // [n_bands] first source index of each band of 128 outputs
+    const int32_t* band8t_klo;       // [n_bands] first source index of each band
     int32_t band8t_chunks;           // operand tiles per band and digit (<= 10); 0 if none
+    int32_t band8t_rows;             // outputs per band (<= 128)
 };
 
 // One image resize, device pointers.

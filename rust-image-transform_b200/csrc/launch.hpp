@@ -43,8 +43,7 @@ cudaError_t launch_banded8(int channels, bool convert, const DevJob* jobs, const
                            cudaStream_t stream);
 
 // Banded8t kernel (banded8t.cu): Rgba8 downscales that are exactly 2:1 horizontally; accumulator lanes are output rows and
-// the horizontal pass runs from registers.  Work items are (band of banded8t_band_rows() output rows) x (column range).
-int banded8t_band_rows();
+// the horizontal pass runs from registers.  Work items are (band of the pass's band8t_rows output rows) x (column range).
 size_t banded8t_smem_bytes(const Band8TGeom& geom);
 cudaError_t launch_banded8t(const DevJob* jobs, const WorkItem* items, const Band8TGeom& geom, cudaStream_t stream);
 

@@ -410,21 +410,37 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
             p.band8.tiles.assign(size_t(n_chunks) * tile, 0);
             const double scale = std::ldexp(1.0, shift);
             std::vector<int64_t> W;
-            // row-band form: applicable when no band of 128 outputs spans more than kBand8TMaxChunks chunks
-            const uint32_t n_bands = (n_out + kBand8TRows - 1) / kBand8TRows;
+            // row-band form: applicable when no band spans more than kBand8TMaxChunks chunks.  The band height (<= 128
+            // outputs, the MMA's M) is the one that costs least: bands x (chunks + the epilogue's share).
+            int band_rows = kBand8TRows;
+            uint32_t n_bands = (n_out + kBand8TRows - 1) / kBand8TRows;
             int band_chunks = 0;
-            std::vector<int32_t> k_lo(n_bands, 0);
+            std::vector<int32_t> k_lo;
             if (limbs == 2) {
-                for (uint32_t r = 0; r < n_bands; ++r) {
-                    const uint32_t o0 = r * kBand8TRows, o1 = std::min(n_out, o0 + kBand8TRows);
-                    k_lo[r] = p.left[o0];  // the band's chunks start at its first source index (not on a multiple of 32)
-                    band_chunks = std::max(band_chunks, (p.right[o1 - 1] - k_lo[r] + kBand8Chunk - 1) / kBand8Chunk);
+                uint64_t best = ~uint64_t(0);
+                for (int rows = kBand8TRows; rows >= 96; rows -= 8) {
+                    const uint32_t nb = (n_out + uint32_t(rows) - 1) / uint32_t(rows);
+                    int chunks = 0;
+                    for (uint32_t r = 0; r < nb; ++r) {
+                        const uint32_t o0 = r * uint32_t(rows), o1 = std::min(n_out, o0 + uint32_t(rows));
+                        chunks = std::max(chunks, (p.right[o1 - 1] - p.left[o0] + kBand8Chunk - 1) / kBand8Chunk);
+                    }
+                    // (per band and block of columns: 2 MMAs per chunk on the tensor pipe, and an epilogue worth about 15 chunks)
+                    const uint64_t cost = uint64_t(nb) * uint64_t(chunks + 15);
+                    if (chunks <= kBand8TMaxChunks && cost < best) {
+                        best = cost;
+                        band_rows = rows;
+                        n_bands = nb;
+                        band_chunks = chunks;
+                    }
                 }
-                if (band_chunks > kBand8TMaxChunks) band_chunks = 0;
+                k_lo.assign(n_bands, 0);
+                for (uint32_t r = 0; r < n_bands; ++r) k_lo[r] = p.left[r * uint32_t(band_rows)];  // chunks start at the band's first source index
             }
             constexpr size_t kTTile = size_t(kBand8TRows) * kBand8Chunk;
             if (band_chunks) {
                 p.band8t.chunks = band_chunks;
+                p.band8t.rows = band_rows;
                 p.band8t.k_lo = k_lo;
                 p.band8t.tiles.assign(size_t(n_bands) * band_chunks * 2 * kTTile, 0);
             }
@@ -454,8 +470,8 @@ std::shared_ptr<const PassPlan> build_pass(int filter, uint32_t n_in, uint32_t n
                         const size_t at = size_t(kk / 16) * (size_t(limbs) * kBand8Window * 16) + size_t(n / 8) * 128 + size_t(n % 8) * 16 + size_t(kk % 16);
                         t[at] = int8_t(digit);
                         if (band_chunks) {  // the same digit in the row-band tile (band, chunk, digit): row m, index kt
-                            const uint32_t r = o / kBand8TRows;
-                            const int m = int(o % kBand8TRows);
+                            const uint32_t r = o / uint32_t(band_rows);
+                            const int m = int(o % uint32_t(band_rows));
                             const int ct = (y - k_lo[r]) / kBand8Chunk, kt = (y - k_lo[r]) % kBand8Chunk;
                             const size_t tt = ((size_t(r) * band_chunks + size_t(ct)) * 2 + size_t(d)) * kTTile;
                             p.band8t.tiles[tt + size_t(kt / 16) * (size_t(kBand8TRows) * 16) + size_t(m / 8) * 128 + size_t(m % 8) * 16 + size_t(kt % 16)] = int8_t(digit);

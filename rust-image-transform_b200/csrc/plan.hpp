@@ -34,16 +34,19 @@ struct Band8 {
     std::vector<int8_t> tiles;    // [n_chunks][limbs * 32 * 32]
 };
 constexpr int kBand8Chunk = 32, kBand8Group = 8, kBand8Window = 32;
+constexpr int kBand8TRowsMax = 128;
 constexpr int kBand8Base = 256;   // digit base: W = hi * 256 + lo, lo in [-128, 127], |hi| <= 127
 
 // Row-band form of the same integer weights, for the kernel whose accumulator lanes are OUTPUT rows (banded8t.cu): the
-// weights are the A operand.  Band r = outputs [128 r, 128 r + 128); its chunks (of kBand8Chunk source indices) start at
+// weights are the A operand.  Band r = outputs [rows r, rows r + rows), rows <= 128; its chunks (of kBand8Chunk source indices) start at
 // the band's first source index k_lo[r]: chunk c = indices k_lo[r] + 32 c .. + 31.  tiles: per band, chunk and digit (most significant first) one K-major s8 operand
 // tile of 128 rows x 32 indices in the shared-memory layout the MMA reads (8 x 16-byte core matrices: rows 128 bytes
 // apart, the two halves of the 32 indices 2048 bytes apart).  chunks == 0: not applicable (a band needs more than
 // kBand8TMaxChunks chunks, i.e. the ratio is well above 2).
 struct Band8T {
     int chunks = 0;
+    int rows = kBand8TRowsMax;   // outputs per band (<= 128 = the MMA's M; rows of a tile beyond it are zero): chosen to minimise
+                                  // bands x chunks, e.g. 120 at exactly 2:1 (8 chunks of 32 source indices instead of 9)
     std::vector<int32_t> k_lo;    // [n_bands] first source index of each band
     std::vector<int8_t> tiles;    // [n_bands][chunks][2][128 * 32]
 };

@@ -93,7 +93,7 @@ def load() -> C.CDLL:
     L.ikc_pass_band.restype = u32
     L.ikc_pass_band8.argtypes = [i32, u32, u32, pu32, pu32, C.POINTER(C.c_int32), C.POINTER(C.c_int8), sz]
     L.ikc_pass_band8.restype = u32
-    L.ikc_pass_band8t.argtypes = [i32, u32, u32, pu32, C.POINTER(C.c_int32), C.POINTER(C.c_int8), sz]
+    L.ikc_pass_band8t.argtypes = [i32, u32, u32, pu32, pu32, C.POINTER(C.c_int32), C.POINTER(C.c_int8), sz]
     L.ikc_pass_band8t.restype = u32
     L.ikc_pass_info.argtypes = [i32, u32, u32, C.POINTER(PassInfo)]
     L.ikc_pass_info.restype = i32

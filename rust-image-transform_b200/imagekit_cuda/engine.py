@@ -95,23 +95,23 @@ def pass_band8(filt: int, n_in: int, n_out: int):
 
 
 def pass_band8t(filt: int, n_in: int, n_out: int):
-    """(chunks, k_lo[n_bands], digits[n_bands, chunks, 2, 128 rows, 32 indices]) of a downscale pass: the s8 weight tiles of
-    the row-band integer tensor-core kernel, un-laid-out (row m of band r is output 128 r + m, index k of chunk c is source
+    """(chunks, k_lo[n_bands], digits[n_bands, chunks, 2, 128 rows, 32 indices], rows) of a pass: the s8 weight tiles of the
+    row-band integer tensor-core kernels, un-laid-out (row m of band r is output rows * r + m, index k of chunk c is source
     index k_lo[r] + 32 c + k); None if the pass has no such form."""
     L = _lib.load()
-    chunks = C.c_uint32()
-    bands = L.ikc_pass_band8t(filt, n_in, n_out, C.byref(chunks), None, None, 0)
+    chunks, rows = C.c_uint32(), C.c_uint32()
+    bands = L.ikc_pass_band8t(filt, n_in, n_out, C.byref(chunks), C.byref(rows), None, None, 0)
     if bands == 0:
         return None
     nc = chunks.value
     k_lo = np.zeros(bands, np.int32)
     raw = np.zeros(bands * nc * 2 * 128 * 32, np.int8)
-    got = L.ikc_pass_band8t(filt, n_in, n_out, C.byref(chunks), k_lo.ctypes.data_as(C.POINTER(C.c_int32)),
+    got = L.ikc_pass_band8t(filt, n_in, n_out, C.byref(chunks), C.byref(rows), k_lo.ctypes.data_as(C.POINTER(C.c_int32)),
                             raw.ctypes.data_as(C.POINTER(C.c_int8)), raw.size)
     assert got == bands
     t = raw.reshape(bands, nc, 2, 2, 16, 8, 16)                     # [band][chunk][digit][k / 16][m / 8][m % 8][k % 16]
     t = t.transpose(0, 1, 2, 4, 5, 3, 6).reshape(bands, nc, 2, 128, 32)
-    return nc, k_lo, t
+    return nc, k_lo, t, rows.value
 
 
 def pass_info(filt: int, n_in: int, n_out: int) -> dict:

@@ -222,9 +222,11 @@ def test_band8t_tiles_hold_the_same_integers_as_band8(ik, filt, n_in, n_out):
     limbs, shift, gbase, dig = engine.pass_band8(filt, n_in, n_out)
     band_t = engine.pass_band8t(filt, n_in, n_out)
     assert band_t is not None
-    nc, k_lo, t = band_t
+    nc, k_lo, t, rows = band_t
     bands = t.shape[0]
-    assert bands == (n_out + 127) // 128 and 1 <= nc <= 10
+    assert 96 <= rows <= 128 and bands == (n_out + rows - 1) // rows and 1 <= nc <= 10
+    if (n_in, n_out) == (2160, 1080):
+        assert (rows, nc, bands) == (120, 8, 9)          # exactly 2:1: 120-row bands span 8 chunks, 128-row bands 9
     W8 = np.zeros((n_out + 64, dig.shape[0] * 32 + 512), np.int64)
     for c in range(dig.shape[0]):
         val = dig[c, 0].astype(np.int64) * 256 + dig[c, 1].astype(np.int64)
@@ -235,9 +237,9 @@ def test_band8t_tiles_hold_the_same_integers_as_band8(ik, filt, n_in, n_out):
         for c in range(nc):
             val = t[r, c, 0].astype(np.int64) * 256 + t[r, c, 1].astype(np.int64)
             y0 = k_lo[r] + 32 * c
-            rows = min(128, WT.shape[0] - 128 * r)
-            assert not val[rows:].any()
-            WT[128 * r:128 * r + rows, y0:y0 + 32] += val[:rows]
+            live = min(rows, WT.shape[0] - rows * r)
+            assert not val[live:].any()
+            WT[rows * r:rows * r + live, y0:y0 + 32] += val[:live]
     assert np.array_equal(W8[:n_out], WT[:n_out]) and not WT[n_out:].any()
 
 
@@ -253,8 +255,8 @@ def test_band8t_of_a_2x_upscale_is_the_quantised_pass(ik, oracle, filt, n_in):
     integer weight within half a unit (plus the sum correction) of w * 2^shift."""
     from imagekit_cuda import engine
     n_out = 2 * n_in
-    nc, k_lo, t = engine.pass_band8t(filt, n_in, n_out)
-    assert 1 <= nc <= 4 and t.shape[0] == (n_out + 127) // 128
+    nc, k_lo, t, rows = engine.pass_band8t(filt, n_in, n_out)
+    assert rows == 128 and 1 <= nc <= 4 and t.shape[0] == (n_out + 127) // 128
     left, count, w = oracle.pass_table(filt, n_in, n_out)
     W = np.zeros((t.shape[0] * 128, n_in + 256), np.int64)
     for r in range(t.shape[0]):

@@ -22,4 +22,4 @@ if len(bad):
     y, x, ch = bad[0]
     print("first bad", (y, x, ch), "got", got[y, x], "want", want[y, x])
 from imagekit_cuda import engine
-print("v pass", engine.pass_info(filt, h, dh), "band8t", (lambda b: None if b is None else (b[0], b[1][:8]))(engine.pass_band8t(filt, h, dh)))
+print("v pass", engine.pass_info(filt, h, dh), "band8t", (lambda b: None if b is None else (b[0], b[3], b[1][:8]))(engine.pass_band8t(filt, h, dh)))
