@@ -79,8 +79,8 @@ enum ikc_dims_code {
 /* Arithmetic mode of the resampling kernels. */
 enum ikc_mode {
     IKC_MODE_FAST = 0,   /* fused single-launch kernels, FMA accumulation: max |delta| <= 1 LSB; downscales run
-                            their vertical pass on the tensor cores as an exact integer product (u8 source bytes x
-                            15-bit fixed-point weights, s32 accumulation)                             */
+                            their vertical pass (and exact 2x upscales theirs) on the tensor cores as an exact integer
+                            product (u8 source bytes x 16-bit fixed-point weights, s32 accumulation)          */
     IKC_MODE_EXACT = 1,  /* two-launch verification path: separate mul/add in ascending tap order,
                             vertical then horizontal, f32 intermediate in HBM: delta == 0 vs the
                             CPU restatement of image 0.25.8                                      */

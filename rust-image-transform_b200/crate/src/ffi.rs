@@ -14,6 +14,8 @@ pub struct ikc_batch {
 pub const IKC_OK: c_int = 0;
 pub const IKC_FILTER_LANCZOS3: c_int = 4;
 pub const IKC_DIMS_RESAMPLE: c_int = 0;
+pub const IKC_MODE_FAST: c_int = 0;
+pub const IKC_MODE_EXACT: c_int = 1;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -61,6 +63,7 @@ extern "C" {
     pub fn ikc_create(device_ids: *const c_int, n: c_int, out: *mut *mut ikc_ctx) -> c_int;
     pub fn ikc_destroy(ctx: *mut ikc_ctx);
     pub fn ikc_device_count(ctx: *const ikc_ctx) -> c_int;
+    pub fn ikc_set_mode(ctx: *mut ikc_ctx, mode: c_int) -> c_int;
     pub fn ikc_last_error() -> *const c_char;
     pub fn ikc_check_dims(sw: u32, sh: u32, dw: u32, dh: u32) -> c_int;
     pub fn ikc_target_dims(ow: u32, oh: u32, has_w: c_int, w: u32, has_h: c_int, h: u32, tw: *mut u32, th: *mut u32) -> c_int;

@@ -25,7 +25,16 @@ fn ctx() -> Result<*mut ffi::ikc_ctx, String> {
         let mut p = std::ptr::null_mut();
         // all visible devices; single-image calls are spread round-robin, batches are sharded
         let rc = unsafe { ffi::ikc_create(std::ptr::null(), 0, &mut p) };
-        if rc == ffi::IKC_OK { Ok(Ctx(p)) } else { Err(last_error()) }
+        if rc != ffi::IKC_OK {
+            return Err(last_error());
+        }
+        // Arithmetic mode.  Default FAST: fused single-launch kernels, every u8 sample within +-1 of the CPU crate's
+        // result (the drop-in's stated tolerance).  IMAGEKIT_CUDA_MODE=exact selects the two-launch kernels that
+        // reproduce image 0.25.8's f32 arithmetic operation by operation (bit-identical output, several times slower).
+        if std::env::var("IMAGEKIT_CUDA_MODE").map(|v| v.eq_ignore_ascii_case("exact")).unwrap_or(false) {
+            unsafe { ffi::ikc_set_mode(p, ffi::IKC_MODE_EXACT) };
+        }
+        Ok(Ctx(p))
     })
     .as_ref()
     .map(|c| c.0)
