@@ -557,3 +557,31 @@ def test_host_batch_groups_small_images(ik, oracle):
     for i in (0, 1, 3, 4):
         assert np.abs(keep[i][1].astype(int) - oracle.resize_exact(keep[i][0], 32, 32, oracle.LANCZOS3).astype(int)).max() <= TOL
     ctx.close()
+
+
+def test_fast_mode_delta_on_the_headline_config(ctx, ik, oracle):
+    """BASELINE config 2 at full size (4K Rgba8 -> 1080p Lanczos3, the row-band tensor-core kernel), on three kinds of
+    content: how many samples FAST mode moves by one level, never more.  The measured histograms are written to
+    gpurun_out/ (copied to profiles/r02_fast_mode_delta.json) -- the source of the figures DESIGN.md / INTEGRATION.md
+    quote."""
+    import json
+    import os
+    h, w, c, dw, dh = 2160, 3840, 4, 1920, 1080
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    smooth = np.stack([127 + 90 * np.sin(xx / (211.0 + 17 * k)) * np.cos(yy / (173.0 - 11 * k)) for k in range(c)], axis=2)
+    contents = {"noise": splitmix_noise((h, w, c), image_id=77), "photo_like": photo_like((h, w, c)),
+                "smooth": np.clip(smooth, 0, 255).astype(np.uint8)}
+    _fast(ctx, ik)
+    record = {}
+    before = ctx.stats()["launches_banded8t"]
+    for name, src in contents.items():
+        got = ctx.resize(src, dw, dh, 4)
+        want = oracle.resize_exact(src, dw, dh, 4)
+        hist = _check_fast(got, want, name)
+        record[name] = {"delta_histogram": {str(k): v for k, v in hist.items()},
+                        "fraction_off_by_one": sum(v for k, v in hist.items() if k != 0) / got.size}
+    assert ctx.stats()["launches_banded8t"] - before == len(contents)
+    out = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "fast_mode_delta.json"), "w") as f:
+            json.dump({"workload": "cfg2: 3840x2160 RGBA8 -> 1920x1080 Lanczos3, IKC_MODE_FAST vs CPU oracle", "contents": record}, f, indent=1)
