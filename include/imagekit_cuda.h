@@ -145,6 +145,7 @@ typedef struct ikc_stats_t {
     uint64_t table_hits, table_misses;   /* per-device weight-table cache */
     uint64_t submit_batches, submit_jobs;   /* ikc_submit_u8: launch groups formed / images they carried */
     uint64_t launches_banded8u;   /* the tensor-core 2x upscale kernel (appended: keeps the earlier fields in place) */
+    uint64_t staging_trims;       /* times a lane gave back staging buffers above 256 MB after an oversized request */
 } ikc_stats_t;
 IKC_API int ikc_get_stats(const ikc_ctx* ctx, ikc_stats_t* out);
 /* Thread-local text of the last failure on the calling thread ("" if none). */

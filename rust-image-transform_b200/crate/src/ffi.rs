@@ -57,6 +57,7 @@ pub struct ikc_stats_t {
     pub submit_batches: u64,
     pub submit_jobs: u64,
     pub launches_banded8u: u64,
+    pub staging_trims: u64,
 }
 
 extern "C" {

@@ -264,6 +264,7 @@ int ikc_get_stats(const ikc_ctx* ctx, ikc_stats_t* out) {
     out->table_hits = ld(s.table_hits); out->table_misses = ld(s.table_misses);
     out->submit_batches = ld(s.submit_batches); out->submit_jobs = ld(s.submit_jobs);
     out->launches_banded8u = ld(s.launches_by_family[7]);
+    out->staging_trims = ld(s.staging_trims);
     return IKC_OK;
 }
 

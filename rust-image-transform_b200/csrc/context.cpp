@@ -100,6 +100,16 @@ void Buffer::reserve(size_t bytes) {
     cap = want;
 }
 
+int Lane::trim(size_t keep) {
+    int n = 0;
+    for (Buffer* b : {&h_in, &h_out, &d_in, &d_out, &d_scratch})
+        if (b->cap > keep) {
+            b->release();
+            ++n;
+        }
+    return n;
+}
+
 DevTables::~DevTables() {
     if (!base && !ready) return;
     int cur = 0;
@@ -277,6 +287,10 @@ Lane* Device::acquire_lane(bool may_grow) {
     return l;
 }
 void Device::release_lane(Lane* l) {
+    // One oversized request (a 268 MP raster is more than a gigabyte) must not keep that much page-locked and device
+    // memory on the lane for the life of the process: buffers above the keep size go back now (the lane's stream is
+    // idle at every release), ordinary ones stay so that steady traffic never allocates.
+    if (l->trim(kLaneKeepBytes)) ctx_->stats.staging_trims.fetch_add(1, std::memory_order_relaxed);
     {
         std::lock_guard<std::mutex> lk(mu_);
         free_.push_back(l);

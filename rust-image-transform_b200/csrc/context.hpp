@@ -89,7 +89,7 @@ struct LaunchPlan {
     int launches() const { return int(groups.size()) + 2 * int(generic_jobs.size()); }
 };
 
-struct Buffer {  // grow-only device or pinned-host buffer
+struct Buffer {  // device or pinned-host buffer that grows on demand (Lane::trim gives oversized ones back)
     void* p = nullptr;
     size_t cap = 0;
     bool pinned_host = false;
@@ -122,6 +122,8 @@ struct Lane {
     std::vector<cudaEvent_t> out_events;  // one per staged D2H chunk of the job in flight
     Buffer h_in{nullptr, 0, true}, h_out{nullptr, 0, true}, h_desc{nullptr, 0, true};
     Buffer d_in, d_out, d_scratch, d_desc;
+    // Frees every buffer larger than `keep` bytes (the lane is idle); returns how many were freed.
+    int trim(size_t keep);
 };
 
 class Context;
@@ -140,6 +142,7 @@ public:
     void release_lane(Lane* l);
     int lane_count() const { return kBatchLanes; }   // lanes a batch worker takes (tickets may have grown the pool beyond it)
     static constexpr int kBatchLanes = 4;
+    static constexpr size_t kLaneKeepBytes = size_t(256) << 20;   // lane buffers above this are freed when the lane is released
     std::mutex batch_mu;  // serialises batch workers, which take every lane of the device
 
 private:
@@ -166,6 +169,7 @@ struct Stats {
     std::atomic<uint64_t> src_bytes{0}, dst_bytes{0}, busy_ns{0};
     std::atomic<uint64_t> table_hits{0}, table_misses{0};
     std::atomic<uint64_t> submit_batches{0}, submit_jobs{0};
+    std::atomic<uint64_t> staging_trims{0};
 };
 
 class SubmitQueue;

@@ -43,7 +43,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "calls", "failed", "trivial", "launches", "launches_banded8t", "launches_banded8", "launches_banded_f16", "launches_ring",
         "launches_up2", "launches_tile", "launches_generic", "src_bytes", "dst_bytes", "busy_ns", "table_hits", "table_misses",
-        "submit_batches", "submit_jobs", "launches_banded8u")]
+        "submit_batches", "submit_jobs", "launches_banded8u", "staging_trims")]
 
 
 class PassInfo(C.Structure):

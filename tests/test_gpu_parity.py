@@ -585,3 +585,24 @@ def test_fast_mode_delta_on_the_headline_config(ctx, ik, oracle):
     if os.path.isdir(out):
         with open(os.path.join(out, "fast_mode_delta.json"), "w") as f:
             json.dump({"workload": "cfg2: 3840x2160 RGBA8 -> 1920x1080 Lanczos3, IKC_MODE_FAST vs CPU oracle", "contents": record}, f, indent=1)
+
+
+def test_oversized_request_gives_its_staging_back(ik, oracle):
+    """One huge raster must not pin hundreds of megabytes on a lane for the life of the process: lane buffers above
+    256 MB are freed when the lane is released (ikc_stats_t.staging_trims counts it), and the next ordinary request
+    on that lane simply allocates ordinary buffers again."""
+    c = ik.Context([0])
+    try:
+        c.set_mode(ik.MODE_FAST)
+        big = np.full((7500, 10000, 4), 131, np.uint8)          # 300 MB: above the keep size
+        big[::97, ::89] = 17
+        got = c.resize(big, 100, 75, 4)
+        assert c.stats()["staging_trims"] >= 1
+        assert got.shape == (75, 100, 4) and int(got.min()) >= 16 and int(got.max()) <= 132
+        t0 = c.stats()["staging_trims"]
+        for i in range(6):                                     # ordinary traffic afterwards: no trims, right answers
+            src = splitmix_noise((240, 320, 4), image_id=900 + i)
+            _check_fast(c.resize(src, 160, 120, 4), oracle.resize_exact(src, 160, 120, 4), ("after trim", i))
+        assert c.stats()["staging_trims"] == t0 and c.stats()["failed"] == 0
+    finally:
+        c.close()
