@@ -277,6 +277,40 @@ def run_other_workloads(ik, ctx, torch, dev, dist, barrier, names):
     return out
 
 
+def run_call_latency(ik, ctx, names, no_cpu):
+    """Rank 0, one thread: what ONE request sees (config 1 is latency-bound, report us per call).  Each call
+    is one synchronous ikc_resize_u8 -- host buffer in, H2D, kernels, D2H, host buffer out -- from pageable memory (the Rust
+    wrapper's Vec<u8>) and from pinned memory, beside the CPU port's single-thread time for the same resize (what the same
+    request costs in the reference, which resizes inline on one worker)."""
+    out = {}
+    for name in names:
+        sw, sh, ch, dw, dh, filt, _, desc = WORKLOADS[name]
+        rng = np.random.default_rng(len(name))
+        pin_s, pin_d = ik.PinnedArray((sh, sw, ch)), ik.PinnedArray((dh, dw, ch))
+        pin_s.array[...] = rng.integers(0, 256, pin_s.shape, dtype=np.uint8)
+        page_s, page_d = np.array(pin_s.array), np.empty((dh, dw, ch), np.uint8)
+        calls = 200 if sw * sh <= 4_000_000 else 60
+        rec = {"workload": f"{name}: {desc}", "api": "ikc_resize_u8 (C ABI), one synchronous call per image, one thread", "calls": calls}
+        for label, src, dst in (("pageable", page_s, page_d), ("pinned", pin_s.array, pin_d.array)):
+            for _ in range(10):
+                ctx.resize(src, dw, dh, filt, out=dst)
+            t = np.empty(calls)
+            for i in range(calls):
+                t0 = time.perf_counter()
+                ctx.resize(src, dw, dh, filt, out=dst)
+                t[i] = time.perf_counter() - t0
+            rec[label] = {"p50_us": float(np.percentile(t, 50) * 1e6), "p99_us": float(np.percentile(t, 99) * 1e6),
+                          "mean_us": float(t.mean() * 1e6)}
+        if not no_cpu:
+            n = 12 if sw * sh <= 4_000_000 else 4
+            v, dt = cpu_port_rate(sw, sh, ch, dw, dh, filt, n, 1)
+            rec["cpu_port_1_thread_us"] = dt / n * 1e6
+        out[name] = rec
+        pin_s.free()
+        pin_d.free()
+    return out
+
+
 def run_cfg5_upload(ik, ctx, dist, dev, rank, world, barrier, args):
     """BASELINE config 5, the /upload shape (reference src/lib.rs:246-309): CPU decode -> GPU resize -> CPU webp q=80 encode
     over 256 synthetic 8 MP JPEGs, split over the ranks (one GPU each) and, inside a rank, over its share of the host
@@ -424,6 +458,7 @@ def main():
     ap.add_argument("--no-shard", action="store_true", help="skip the cfg3_shard leg (1024 thumbnails, strong scaling)")
     ap.add_argument("--shard-images", type=int, default=1024)
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads leg (cfg1, cfg4 device-resident)")
+    ap.add_argument("--no-latency", action="store_true", help="skip the call_latency leg (one ikc_resize_u8 call at a time)")
     ap.add_argument("--no-upload", action="store_true", help="skip the cfg5_upload leg (decode -> resize -> webp encode of 8 MP JPEGs)")
     ap.add_argument("--upload-images", type=int, default=256)
     args = ap.parse_args()
@@ -611,6 +646,11 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- one request at a time: per-call latency through ikc_resize_u8 (config 1 is the latency-bound one)
+    call_latency = None
+    if not args.no_latency:
+        call_latency = run_call_latency(ik, ctx, sorted({"cfg1", args.workload}), args.no_cpu)
+
     # ---- CPU baseline on the host cores (bounded sample; reported, not the target)
     cpu = None
     cpu_mt = None
@@ -666,6 +706,7 @@ def main():
         "cfg3_shard": cfg3_shard,
         "cfg5_upload": cfg5_upload,
         "other_workloads": other_workloads,
+        "call_latency": call_latency,
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "parity": parity,

@@ -98,23 +98,31 @@ struct Buffer {  // device or pinned-host buffer that grows on demand (Lane::tri
 };
 
 // A few helper threads that share the memcpy between pageable caller memory and the pinned staging buffers
-// (one thread moves ~8 GB/s, PCIe Gen5 ~50 GB/s).  parallel_for never blocks behind another caller: if the
-// helpers are busy the calling thread does the whole job itself.
+// (one thread moves ~15 GB/s, PCIe Gen5 ~55 GB/s).  parallel_for never blocks behind another caller: if the
+// helpers are busy the calling thread does the whole job itself.  Pieces are claimed with an atomic counter: the mutex
+// and the condition variable are touched only to wake the helpers and when one of them goes back to sleep.
 class CopyPool {
 public:
     explicit CopyPool(int helpers);
     ~CopyPool();
-    void parallel_for(size_t n, const std::function<void(size_t)>& fn);
+    // `wake`: how many helpers to wake for this job at most (each wake-up costs the caller a futex call; < 0: all).
+    void parallel_for(size_t n, const std::function<void(size_t)>& fn, const std::function<void()>* tick = nullptr, int wake = -1);
+    int helpers() const { return int(threads_.size()); }
 
 private:
     void worker();
     std::vector<std::thread> threads_;
     std::mutex mu_, run_mu_;
-    std::condition_variable cv_, done_cv_;
+    std::condition_variable cv_;
+    // the job in flight (published under mu_, pieces claimed lock-free)
     const std::function<void(size_t)>* fn_ = nullptr;
-    size_t n_ = 0, next_ = 0, running_ = 0;
-    uint64_t epoch_ = 0;
-    bool stop_ = false;
+    size_t n_ = 0;
+    std::atomic<size_t> next_{0}, done_{0};
+    int inside_ = 0;          // helpers that have joined the job and not left it yet (mu_)
+    int wanted_ = 0;          // helpers still allowed to join it (mu_)
+    bool open_ = false;       // (mu_)
+    uint64_t epoch_ = 0;      // (mu_)
+    bool stop_ = false;       // (mu_)
 };
 
 struct Lane {
