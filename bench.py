@@ -487,6 +487,7 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")   # host-side waits that must not occupy the GPUs (the in-process leg)
 
     sw, sh, ch, dw, dh, filt, batch_default, desc = WORKLOADS[args.workload]
     batch = args.batch or batch_default
@@ -639,6 +640,9 @@ def main():
         barrier()
         if rank == 0:
             e2e_inprocess = run_inprocess(ik, world, sw, sh, ch, dw, dh, filt, args)
+        # the idle ranks wait on the host: an NCCL barrier would park a spinning kernel on their GPUs, which are the
+        # very devices rank 0's context is driving in this leg
+        dist.barrier(group=host_group)
         barrier()
 
     if rank != 0:
