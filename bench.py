@@ -301,6 +301,16 @@ def run_call_latency(ik, ctx, names, no_cpu):
                 t[i] = time.perf_counter() - t0
             rec[label] = {"p50_us": float(np.percentile(t, 50) * 1e6), "p99_us": float(np.percentile(t, 99) * 1e6),
                           "mean_us": float(t.mean() * 1e6)}
+        # the call the Rust wrapper's resize_image makes (ikc_submit_u8: coalescing queue; a lone request runs on the caller)
+        for _ in range(10):
+            ctx.submit(page_s, dw, dh, filt)
+        t = np.empty(calls)
+        for i in range(calls):
+            t0 = time.perf_counter()
+            ctx.submit(page_s, dw, dh, filt)
+            t[i] = time.perf_counter() - t0
+        rec["submit_pageable"] = {"p50_us": float(np.percentile(t, 50) * 1e6), "p99_us": float(np.percentile(t, 99) * 1e6),
+                                  "mean_us": float(t.mean() * 1e6), "note": "ikc_submit_u8, result buffer allocated per call"}
         if not no_cpu:
             n = 12 if sw * sh <= 4_000_000 else 4
             v, dt = cpu_port_rate(sw, sh, ch, dw, dh, filt, n, 1)

@@ -1263,15 +1263,20 @@ void count_bytes(Stats& s, const JobDesc& d) {
 
 void Context::resize_host(const JobDesc& d, int* device_index_out) {
     CallTimer timer(stats);
+    Device& dev = device(next_device());
+    if (device_index_out) *device_index_out = dev.index();
+    resize_host_on(dev, d);
+    timer.ok = true;
+}
+
+// One image on one lane of `dev`: staged / in-place H2D, kernels, D2H, all on the lane's stream.
+void Context::resize_host_on(Device& dev, const JobDesc& d) {
     validate_job(d);
     if (trivial_resize(d)) {
         stats.trivial.fetch_add(1, std::memory_order_relaxed);
-        timer.ok = true;
         return;
     }
     count_bytes(stats, d);
-    Device& dev = device(next_device());
-    if (device_index_out) *device_index_out = dev.index();
     check_cuda(cudaSetDevice(dev.ordinal()), "cudaSetDevice");
     Lane* l = dev.acquire_lane();
     HostJobState st;  // (outlives the handler below: its plan holds the weight tables the enqueued kernels read)
@@ -1284,7 +1289,6 @@ void Context::resize_host(const JobDesc& d, int* device_index_out) {
         throw;
     }
     dev.release_lane(l);
-    timer.ok = true;
 }
 
 void Context::resize_batch_host(JobDesc* descs, size_t n, int* status, int* device_out) {
@@ -1568,6 +1572,23 @@ public:
     void submit(const JobDesc& d) {
         Pending p{d, kOk, {}, false};
         std::unique_lock<std::mutex> lk(mu_);
+        static const bool inline_lone = [] { const char* v = std::getenv("IKC_SUBMIT_INLINE"); return !(v && *v == '0'); }();
+        if (inline_lone && q_.empty() && busy_ == 0) {
+            // Nothing queued, nothing in flight: there is nobody to share a launch with, so the caller runs its image
+            // itself on the single-image path (chunked staging overlapped with the DMA, no hand-off to a dispatcher
+            // thread and back: two thread wake-ups, ~100 us on a virtual machine).  Requests that arrive meanwhile find
+            // busy_ != 0, queue up and are coalesced by the dispatchers as before.
+            ++busy_;
+            lk.unlock();
+            struct Done {
+                SubmitQueue& q;
+                ~Done() { std::lock_guard<std::mutex> g(q.mu_); --q.busy_; }
+            } done{*this};
+            ctx_->resize_host_on(*dev_, d);
+            ctx_->stats.submit_batches.fetch_add(1, std::memory_order_relaxed);
+            ctx_->stats.submit_jobs.fetch_add(1, std::memory_order_relaxed);
+            return;
+        }
         q_.push_back(&p);
         cv_.notify_one();
         done_cv_.wait(lk, [&] { return p.done; });
@@ -1592,6 +1613,7 @@ private:
                     bytes += size_t(p->d.sw) * p->d.sh * size_t(p->d.channels & 0xff) * p->d.bps;
                     group.push_back(p);
                 }
+                ++busy_;
             }
             const size_t n = group.size();
             std::vector<JobDesc> descs(n);
@@ -1611,6 +1633,7 @@ private:
             ctx_->stats.submit_jobs.fetch_add(n, std::memory_order_relaxed);
             {
                 std::lock_guard<std::mutex> lk(mu_);
+                --busy_;
                 for (size_t i = 0; i < n; ++i) {
                     group[i]->status = st[i];
                     group[i]->err = std::move(errs[i]);
@@ -1626,6 +1649,7 @@ private:
     std::condition_variable cv_, done_cv_;
     std::deque<Pending*> q_;
     std::vector<std::thread> threads_;
+    int busy_ = 0;   // groups in flight (dispatchers) + callers running their own image (mu_)
     bool stop_ = false;
 };
 

@@ -210,6 +210,7 @@ public:
 
     // Host-buffer resize of one image through a lane of some device.
     void resize_host(const JobDesc& d, int* device_index_out);
+    void resize_host_on(Device& dev, const JobDesc& d);
     void resize_batch_host(JobDesc* descs, size_t n, int* status, int* device_out);
     // Split host-buffer resize (ikc_resize_begin_u8 / ikc_resize_end): begin returns an opaque ticket (nullptr for a
     // raster answered without a kernel), end completes and frees it.  Both throw Error.
