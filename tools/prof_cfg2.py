@@ -1,5 +1,5 @@
 """Dev tool: a few device-resident launches of one BASELINE workload (cfg1..cfg4) for timing and ncu:
-    python tools/prof_cfg2.py cfg2 16     # prints the kernel(s) used and us/image"""
+    python tools/prof_cfg2.py cfg2 16 [fast|exact|f16|fp32]    # prints the kernel(s) used and us/image"""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "rust-image-transform_b200"))
@@ -11,6 +11,8 @@ shapes = {"cfg2": (3840, 2160, 4, 1920, 1080, 4), "cfg3": (4032, 3024, 3, 400, 3
           "cfg4": (1920, 1080, 3, 3840, 2160, 2)}
 sw, sh, ch, dw, dh, filt = shapes[wl]
 ctx = ik.Context([0])
+if len(sys.argv) > 3:
+    ctx.set_mode({"fast": ik.MODE_FAST, "exact": ik.MODE_EXACT, "f16": ik.MODE_FAST_F16, "fp32": ik.MODE_FAST_FP32}[sys.argv[3]])
 src = torch.randint(0, 256, (batch, sh, sw, ch), dtype=torch.uint8, device="cuda")
 dst = torch.zeros((batch, dh, dw, ch), dtype=torch.uint8, device="cuda")
 jobs = [(src[i].data_ptr(), sw, sh, sw * ch, dst[i].data_ptr(), dw, dh, dw * ch, ch, filt) for i in range(batch)]
