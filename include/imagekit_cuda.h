@@ -237,7 +237,8 @@ IKC_API int ikc_resize_end(ikc_ticket* ticket);
  * handler threads that each resize one image at a time (src/lib.rs:180, :286): calls that arrive while the device is
  * busy are coalesced -- staged into one pinned block, uploaded with one copy, planned together and run as ONE launch per
  * kernel variant -- instead of one plan + descriptor upload + launch + two copies each.  Blocks until this caller's image
- * is done.  A lone caller pays no waiting window: whatever is queued when the dispatcher comes round forms the group. */
+ * is done.  There is no waiting window: a call that finds nothing queued and nothing in flight runs at once on its own
+ * thread, exactly as ikc_resize_u8 would; calls that arrive meanwhile form the next group. */
 IKC_API int ikc_submit_u8(ikc_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch, int channels,
                           uint8_t* dst, uint32_t dw, uint32_t dh, size_t dst_pitch, int filter);
 
