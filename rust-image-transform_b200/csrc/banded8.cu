@@ -140,12 +140,44 @@ __device__ __forceinline__ void drain_group8(uint32_t taddr, uint32_t trow, int 
     if (lane == 0) mbar_arrive_at(empty_bar);
 }
 
+// One work item's geometry, as every role of the persistent CTA needs it.
+struct Item8 {
+    const DevJob* J;
+    const int32_t* gbase;
+    int ox0, ox1, oy0, oy1;
+    int b0, nblk;          // strip along x: source bytes [b0, b0 + nblk * 128), 16-byte aligned at both ends
+    int k0, nchunks;       // chunks [k0, k0 + nchunks) of the pass's global chunk grid
+    int g0, g_end;         // groups (of 8 outputs) the item's MMAs touch: [g0, g_end)
+};
+template <int C>
+__device__ __forceinline__ Item8 load_item8(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ items, int idx) {
+    const WorkItem it = items[idx];
+    Item8 r;
+    r.J = jobs + it.job;
+    r.ox0 = it.ox0; r.ox1 = it.ox1; r.oy0 = it.oy0; r.oy1 = it.oy1;
+    r.gbase = r.J->v.band8_gbase;
+    const int xl = __ldg(r.J->h.left + it.ox0);
+    const int xr = __ldg(r.J->h.right + it.ox1 - 1);
+    const int row_bytes = int(r.J->sw) * C;
+    r.b0 = (xl * C) & ~15;
+    const int b1 = min((xr * C + 15) & ~15, (row_bytes + 15) & ~15);
+    r.nblk = (b1 - r.b0 + 127) >> 7;
+    const int y_first = __ldg(r.J->v.left + it.oy0);
+    const int y_last = __ldg(r.J->v.right + it.oy1 - 1);
+    r.k0 = y_first / k8Chunk;
+    const int k1 = (y_last - 1) / k8Chunk;
+    r.nchunks = k1 - r.k0 + 1;
+    r.g0 = __ldg(r.gbase + r.k0);
+    r.g_end = __ldg(r.gbase + k1) + k8WinGroups;
+    return r;
+}
+
 constexpr bool k8Conv = IKC_BANDED8_CONV != 0;
 
 }  // namespace
 
 // Shared memory: [mbarriers (1 KB) | operand ring: 5 stages x 4 blocks x (32 rows x 128 B, swizzled) | weight-tile ring
-//                (4 x L * 1 KB) | horizontal weights of the strip | (left, right) of the strip's outputs |
+//                (4 x L * 1 KB) | 2 x horizontal weights of a strip | 2 x (left, right) of a strip's outputs |
 //                one intermediate tile per team: 16 rows x pitch floats]
 template <int C, int L, bool CONV>
 __global__ void __launch_bounds__(k8Threads, 1)
@@ -165,64 +197,38 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
     uint64_t* const b_empty = b_full + k8BStages;    // [k8BStages]
     uint64_t* const t_full = b_empty + k8BStages;    // [k8Ring] every MMA into the group has completed
     uint64_t* const t_empty = t_full + k8Ring;       // [k8Ring] the 4 warps of a team have drained and zeroed the group
+    uint64_t* const tab_full = t_empty + k8Ring;     // [2] the strip tables of an item are in their buffer (table warp)
+    uint64_t* const tab_empty = tab_full + 2;        // [2] every epilogue warp has left the item that used the buffer
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
     uint8_t* const ustage = smem + k8HeaderBytes;
     uint8_t* const bstage = ustage + k8UStages * k8UStageBytes;
-    float2* const hw = reinterpret_cast<float2*>(bstage + k8BStages * kBTile);
-    int2* const hlr = reinterpret_cast<int2*>(hw + ((geom.hw_pairs + 1) & ~1));
-    float* const tmp_all = reinterpret_cast<float*>(hlr + ((geom.max_out + 1) & ~1));  // k8Teams tiles
+    const int hw_cap = (geom.hw_pairs + 1) & ~1, hlr_cap = (geom.max_out + 1) & ~1;
+    float2* const hw_all = reinterpret_cast<float2*>(bstage + k8BStages * kBTile);       // [2][hw_cap]: item k uses buffer k & 1
+    int2* const hlr_all = reinterpret_cast<int2*>(hw_all + 2 * hw_cap);                  // [2][hlr_cap]
+    float* const tmp_all = reinterpret_cast<float*>(hlr_all + 2 * hlr_cap);              // k8Teams tiles
 
     int tid;  // read once: the compiler otherwise re-reads %tid.x (a ~20-cycle S2R) inside the epilogue loops
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
-    const WorkItem it = items[blockIdx.x];
-    const DevJob* __restrict__ J = jobs + it.job;
-    const int ox0 = it.ox0, ox1 = it.ox1, oy0 = it.oy0, oy1 = it.oy1;
-    const int32_t* __restrict__ hleft = J->h.left;
-    const int32_t* __restrict__ hright = J->h.right;
-    const int32_t* __restrict__ gbase = J->v.band8_gbase;
-
-    // Strip geometry along x: source bytes [b0, b0 + nb), 16-byte aligned at both ends.
-    const int xl = __ldg(hleft + ox0);
-    const int xr = __ldg(hright + ox1 - 1);
-    const int row_bytes = int(J->sw) * C;
-    const int b0 = (xl * C) & ~15;
-    const int b1 = min((xr * C + 15) & ~15, (row_bytes + 15) & ~15);
-    const int nb = b1 - b0;
-    const int nblk = (nb + 127) >> 7;
-    // Chunk geometry along y: source rows [y_first, y_last) -> chunks [k0, k1] of the pass's global chunk grid.
-    const int y_first = __ldg(J->v.left + oy0);
-    const int y_last = __ldg(J->v.right + oy1 - 1);
-    const int k0 = y_first / k8Chunk, k1 = (y_last - 1) / k8Chunk;
-    const int nchunks = k1 - k0 + 1;
-    const int g0 = __ldg(gbase + k0);                // first group (of 8 outputs) any MMA of this item touches
-    const int g_end = __ldg(gbase + k1) + k8WinGroups;  // one past the last
+    // Persistent CTA: items blockIdx.x, blockIdx.x + gridDim.x, ... ; every role walks the same sequence.  Ring slots and
+    // barrier phases follow a running group index (the item's group index + the groups of the CTA's earlier items), so the
+    // producer and the MMA warps run ahead into the next item while the epilogue teams finish the current one.
+    const int n_items = geom.n_items;
 
     if (tid == 0) {
         if (smem_addr(smem) & 1023u) __trap();  // the swizzled operand tiles need 1024-byte aligned shared memory
         for (int s = 0; s < k8UStages; ++s) { mbar_init(u_full + s, 1); mbar_init(u_empty + s, k8MmaWarps); }
         for (int s = 0; s < k8BStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, k8MmaWarps); }
         for (int s = 0; s < k8Ring; ++s) { mbar_init(t_full + s, k8MmaWarps); mbar_init(t_empty + s, 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tab_full + s, 1); mbar_init(tab_empty + s, k8Teams * 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    // Horizontal tables of the strip: (left, right) and the weights (x 2^-shift, duplicated for FFMA2) of every output.
-    const int n_out = ox1 - ox0;
-    const int hstride = J->h.stride;
-    for (int i = tid; i < n_out; i += k8Threads) hlr[i] = make_int2(__ldg(hleft + ox0 + i), __ldg(hright + ox0 + i));
-    {
-        const float* __restrict__ wsrc = J->h.w + size_t(ox0) * hstride;
-        const float unscale = __int_as_float((127 - J->v.band8_shift) << 23);  // 2^-shift: the vertical sums are integers x 2^shift
-        for (int i = tid; i < n_out * hstride; i += k8Threads) {
-            const float w = __ldg(wsrc + i) * unscale;
-            hw[i] = make_float2(w, w);
-        }
     }
     tc_fence_before();
     __syncthreads();
@@ -235,27 +241,30 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
         // ------------------------------------------------------------------------------ producer
         // (the whole warp runs the loop and polls; one elected lane issues the copies)
         const bool leader = elect_one();
-        const void* const src_map = J->src_map8;
-        if (leader) asm volatile("prefetch.tensormap [%0];" ::"l"(src_map) : "memory");
-        const uint8_t* const tiles = reinterpret_cast<const uint8_t*>(J->v.band8_tiles) + size_t(k0) * kBTile;
         int su = 0, sb = 0;
         uint32_t pu = 1, pb = 1;  // phase bits of the empty barriers (first pass: free)
-        for (int i = 0; i < nchunks; ++i) {
-            mbar_wait_parked(u_empty + su, pu);
-            if (leader) {
-                // one box per 128-byte block: 32 rows x 128 bytes, swizzled into the MMA's operand layout; bytes past the
-                // raster's pitch or rows read as zero
-                mbar_expect_tx(u_full + su, uint32_t(nblk) * k8BlockBytes);
-                for (int b = 0; b < nblk; ++b)
-                    tma_load_2d(ustage + su * k8UStageBytes + b * k8BlockBytes, src_map, b0 + b * 128, (k0 + i) * k8Chunk, u_full + su);
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const Item8 I = load_item8<C>(jobs, items, item);
+            const void* const src_map = I.J->src_map8;
+            if (leader) asm volatile("prefetch.tensormap [%0];" ::"l"(src_map) : "memory");
+            const uint8_t* const tiles = reinterpret_cast<const uint8_t*>(I.J->v.band8_tiles) + size_t(I.k0) * kBTile;
+            for (int i = 0; i < I.nchunks; ++i) {
+                mbar_wait_parked(u_empty + su, pu);
+                if (leader) {
+                    // one box per 128-byte block: 32 rows x 128 bytes, swizzled into the MMA's operand layout; bytes past the
+                    // raster's pitch or rows read as zero
+                    mbar_expect_tx(u_full + su, uint32_t(I.nblk) * k8BlockBytes);
+                    for (int b = 0; b < I.nblk; ++b)
+                        tma_load_2d(ustage + su * k8UStageBytes + b * k8BlockBytes, src_map, I.b0 + b * 128, (I.k0 + i) * k8Chunk, u_full + su);
+                }
+                mbar_wait_parked(b_empty + sb, pb);
+                if (leader) {
+                    mbar_expect_tx(b_full + sb, kBTile);
+                    bulk_load(bstage + sb * kBTile, tiles + size_t(i) * kBTile, kBTile, b_full + sb);
+                }
+                if (++su == k8UStages) { su = 0; pu ^= 1; }
+                if (++sb == k8BStages) { sb = 0; pb ^= 1; }
             }
-            mbar_wait_parked(b_empty + sb, pb);
-            if (leader) {
-                mbar_expect_tx(b_full + sb, kBTile);
-                bulk_load(bstage + sb * kBTile, tiles + size_t(i) * kBTile, kBTile, b_full + sb);
-            }
-            if (++su == k8UStages) { su = 0; pu ^= 1; }
-            if (++sb == k8BStages) { sb = 0; pb ^= 1; }
         }
         __syncwarp();
     } else if (warp <= k8MmaWarps) {
@@ -266,53 +275,91 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
         // every lane polls the barriers) and one elected lane issues the MMAs and commits.
         const int b_lo_blk = (warp - 1) * (k8Blocks / k8MmaWarps);
         const bool leader = elect_one();
-        int acquired = g0;   // groups [g0, acquired) belong to the MMAs (zeroed by the epilogue warps)
-        int completed = g0;  // groups [g0, completed) have been committed to the epilogue
         const uint32_t a_lo0 = ((smem_addr(ustage) >> 4) & 0x3fffu) | ((1024u >> 4) << 16);
         const uint32_t b_lo0 = ((smem_addr(bstage) >> 4) & 0x3fffu) | (((uint32_t(kN) * 16u) >> 4) << 16);
         constexpr uint32_t kBDescHi = (128u >> 4) | (1u << 14);
         const uint32_t bars_a = smem_addr(bars);
-        int gb_next = g0;
         int su = 0, sb = 0;
         uint32_t pu = 0, pb = 0;  // phase bits of the two operand rings
-        for (int i = 0; i < nchunks; ++i) {
-            const int gb = gb_next;
-            gb_next = (i + 1 < nchunks) ? __ldg(gbase + k0 + i + 1) : 0;
-            while (acquired < gb + k8WinGroups) {  // ring slot = absolute group & 7, use count = how often the item reached it
-                mbar_wait_at(bars_a + uint32_t(2 * k8UStages + 2 * k8BStages + k8Ring + (acquired & (k8Ring - 1))) * 8, ((acquired - g0) >> 3) & 1);
-                ++acquired;
-            }
-            mbar_wait_at(bars_a + uint32_t(su) * 8, pu);
-            mbar_wait_at(bars_a + uint32_t(2 * k8UStages + sb) * 8, pb);
-            tc_fence_after();
-            const uint32_t a_lo = a_lo0 + uint32_t(su) * (k8UStageBytes >> 4);
-            const uint32_t b_lo = b_lo0 + uint32_t(sb) * (kBTile >> 4);
-            const int s0 = gb & (k8Ring - 1);
-            const uint32_t n1 = uint32_t(min(k8WinGroups, k8Ring - s0) * k8Group * L), n2 = uint32_t(kN) - n1;  // n2 > 0: the window wraps
-            const uint32_t id1 = instr_desc_i8(n1), id2 = instr_desc_i8(n2);
-            const uint32_t c1 = tmem + uint32_t(s0 * k8Group * L);
-            if (leader) {
-#pragma unroll
-                for (int bb = 0; bb < k8Blocks / k8MmaWarps; ++bb) {
-                    const int b = b_lo_blk + bb;
-                    if (b < nblk) {
-                        const uint64_t a_desc = make_u64(a_lo + uint32_t(b) * (k8BlockBytes >> 4), a8_desc_hi());
-                        mma_i8_acc(c1 + uint32_t(b * kBlockCols), a_desc, make_u64(b_lo, kBDescHi), id1);
-                        if (n2) mma_i8_acc(tmem + uint32_t(b * kBlockCols), a_desc, make_u64(b_lo + (n1 >> 3) * (128u >> 4), kBDescHi), id2);
-                    }
+        int vbase = 0;            // groups of the CTA's earlier items
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const Item8 I = load_item8<C>(jobs, items, item);
+            const int32_t* __restrict__ gbase = I.gbase;
+            const int k0 = I.k0, nchunks = I.nchunks, nblk = I.nblk, g0 = I.g0;
+            const int voff = vbase - g0;   // group g of this item is running group g + voff: slot (g + voff) & 7, use ((g + voff) >> 3)
+            int acquired = g0;   // groups [g0, acquired) belong to the MMAs (zeroed by the epilogue warps)
+            int completed = g0;  // groups [g0, completed) have been committed to the epilogue
+            int gb_next = g0;
+            for (int i = 0; i < nchunks; ++i) {
+                const int gb = gb_next;
+                gb_next = (i + 1 < nchunks) ? __ldg(gbase + k0 + i + 1) : 0;
+                while (acquired < gb + k8WinGroups) {
+                    const int v = acquired + voff;
+                    mbar_wait_at(bars_a + uint32_t(2 * k8UStages + 2 * k8BStages + k8Ring + (v & (k8Ring - 1))) * 8, (v >> 3) & 1);
+                    ++acquired;
                 }
-                tc_commit(u_empty + su);
-                tc_commit(b_empty + sb);
+                mbar_wait_at(bars_a + uint32_t(su) * 8, pu);
+                mbar_wait_at(bars_a + uint32_t(2 * k8UStages + sb) * 8, pb);
+                tc_fence_after();
+                const uint32_t a_lo = a_lo0 + uint32_t(su) * (k8UStageBytes >> 4);
+                const uint32_t b_lo = b_lo0 + uint32_t(sb) * (kBTile >> 4);
+                const int s0 = (gb + voff) & (k8Ring - 1);
+                const uint32_t n1 = uint32_t(min(k8WinGroups, k8Ring - s0) * k8Group * L), n2 = uint32_t(kN) - n1;  // n2 > 0: the window wraps
+                const uint32_t id1 = instr_desc_i8(n1), id2 = instr_desc_i8(n2);
+                const uint32_t c1 = tmem + uint32_t(s0 * k8Group * L);
+                if (leader) {
+#pragma unroll
+                    for (int bb = 0; bb < k8Blocks / k8MmaWarps; ++bb) {
+                        const int b = b_lo_blk + bb;
+                        if (b < nblk) {
+                            const uint64_t a_desc = make_u64(a_lo + uint32_t(b) * (k8BlockBytes >> 4), a8_desc_hi());
+                            mma_i8_acc(c1 + uint32_t(b * kBlockCols), a_desc, make_u64(b_lo, kBDescHi), id1);
+                            if (n2) mma_i8_acc(tmem + uint32_t(b * kBlockCols), a_desc, make_u64(b_lo + (n1 >> 3) * (128u >> 4), kBDescHi), id2);
+                        }
+                    }
+                    tc_commit(u_empty + su);
+                    tc_commit(b_empty + sb);
+                }
+                const int final_below = (i + 1 < nchunks) ? gb_next : acquired;  // groups below it get no more contributions
+                for (; completed < final_below; ++completed)
+                    if (leader) tc_commit(t_full + ((completed + voff) & (k8Ring - 1)));
+                if (++su == k8UStages) { su = 0; pu ^= 1; }
+                if (++sb == k8BStages) { sb = 0; pb ^= 1; }
             }
-            const int final_below = (i + 1 < nchunks) ? gb_next : acquired;  // groups below it get no more contributions
-            for (; completed < final_below; ++completed)
-                if (leader) tc_commit(t_full + (completed & (k8Ring - 1)));
-            if (++su == k8UStages) { su = 0; pu ^= 1; }
-            if (++sb == k8BStages) { sb = 0; pb ^= 1; }
+            vbase += I.g_end - g0;
         }
         __syncwarp();
     }
-    // (warps 2 and 3 have no role: they gave their registers up and wait for the teardown)
+    else if (warp == 3) {
+        // ------------------------------------------------------------------------------ table warp
+        // Horizontal tables of the next item's strip -- (left, right) and the weights (x 2^-shift, duplicated for FFMA2) of
+        // every output -- go into the buffer the epilogue teams are not using, while they work on the current item.
+        int k = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+            const WorkItem it = items[item];
+            const DevJob* __restrict__ J = jobs + it.job;
+            const int buf = k & 1;
+            mbar_wait_parked(tab_empty + buf, uint32_t(((k >> 1) & 1) ^ 1));   // (first use of a buffer: free)
+            float2* const hw = hw_all + buf * hw_cap;
+            int2* const hlr = hlr_all + buf * hlr_cap;
+            const int n_out = it.ox1 - it.ox0;
+            const int hstride = J->h.stride;
+            const int32_t* __restrict__ hleft = J->h.left;
+            const int32_t* __restrict__ hright = J->h.right;
+            for (int i = lane; i < n_out; i += 32) hlr[i] = make_int2(__ldg(hleft + it.ox0 + i), __ldg(hright + it.ox0 + i));
+            const float* __restrict__ wsrc = J->h.w + size_t(it.ox0) * hstride;
+            const float unscale = __int_as_float((127 - J->v.band8_shift) << 23);  // 2^-shift: the vertical sums are integers x 2^shift
+            const int n = n_out * hstride;
+#pragma unroll 4
+            for (int i = lane; i < n; i += 32) {
+                const float w = __ldg(wsrc + i) * unscale;
+                hw[i] = make_float2(w, w);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tab_full + buf);
+        }
+    }
+    // (warp 2, when there is one MMA warp only, has no role: it gave its registers up and waits for the teardown)
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(k8RegsEpi));
         // ------------------------------------------------------------------------------ epilogue + horizontal pass
@@ -338,6 +385,20 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
 
         const int hrow = lane & 15;
         const int seg = 2 * q + (lane >> 4);
+        int vbase = 0;            // groups of the CTA's earlier items
+        int kitem = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++kitem) {
+        const Item8 I = load_item8<C>(jobs, items, item);
+        const DevJob* __restrict__ J = I.J;
+        const int ox0 = I.ox0, ox1 = I.ox1, oy0 = I.oy0, oy1 = I.oy1, b0 = I.b0, nblk = I.nblk, g0 = I.g0, g_end = I.g_end;
+        const int voff = vbase - g0;   // group g of this item is running group g + voff: slot (g + voff) & 7, use ((g + voff) >> 3)
+        // the strip's tables: filled by the table warp (buffer = item parity)
+        const int n_out = ox1 - ox0;
+        const int hstride = J->h.stride;
+        const int tbuf = kitem & 1;
+        const float2* const hw = hw_all + tbuf * hw_cap;
+        const int2* const hlr = hlr_all + tbuf * hlr_cap;
+        mbar_wait_at(smem_addr(tab_full + tbuf), uint32_t((kitem >> 1) & 1));
         const int CO = CONV ? J->out_channels : C;
         uint8_t* const dst_base = J->dst;
         const size_t dst_pitch = J->dst_pitch;
@@ -366,8 +427,8 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
             const bool live = tile_row0 < oy1 && tile_row0 + k8TileRows > oy0;
             const int g_lo = max(gt, g0), g_hi = min(gt + 2, g_end);
             for (int g = g_lo; g < g_hi; ++g) {
-                const int slot = g & (k8Ring - 1);
-                mbar_wait_at(t_full_a + slot * 8, ((g - g0) / k8Ring) & 1);
+                const int slot = (g + voff) & (k8Ring - 1);
+                mbar_wait_at(t_full_a + slot * 8, ((g + voff) >> 3) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tlane_p + uint32_t(slot * k8Group * L);   // the group's first column within block 0
                 const uint32_t trow = tcol_a + uint32_t((g & 1) * k8Group * kTmpPitch) * 4;
@@ -464,6 +525,10 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
             __syncwarp();
             team_barrier(team_p);  // the tile may be overwritten
         }
+        vbase += g_end - g0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tab_empty + tbuf);   // this warp is done with the item's tables
+        }   // items
     }
 
     // ---------------------------------------------------------------------------------- teardown
@@ -481,7 +546,7 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
 size_t banded8_smem_bytes(int channels, const Band8Geom& g) {
     const size_t tmp_pitch = size_t(tmp8_pitch_floats(channels));
     return size_t(k8HeaderBytes) + size_t(k8UStages) * k8UStageBytes + size_t(k8BStages) * size_t(g.limbs) * k8Window * k8Chunk +
-           size_t((g.hw_pairs + 1) & ~1) * sizeof(float2) + size_t((g.max_out + 1) & ~1) * sizeof(int2) +
+           2 * (size_t((g.hw_pairs + 1) & ~1) * sizeof(float2) + size_t((g.max_out + 1) & ~1) * sizeof(int2)) +
            size_t(k8Teams) * (size_t(k8TileRows) * tmp_pitch + k8TmpPad) * sizeof(float);
 }
 size_t banded8_max_smem() { return k8MaxSmem; }
@@ -499,7 +564,13 @@ static cudaError_t launch_one8(const DevJob* jobs, const WorkItem* items, const 
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(banded8_kernel<C, L, k8Conv>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    banded8_kernel<C, L, k8Conv><<<geom.n_items, k8Threads, smem, stream>>>(jobs, items, geom);
+    // persistent grid: one CTA per SM (the kernel's occupancy), each walking items blockIdx.x, + gridDim.x, ...
+    int dev = 0, sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    const int grid = geom.n_items < sms ? geom.n_items : sms;
+    if (grid <= 0) return cudaErrorInvalidConfiguration;
+    banded8_kernel<C, L, k8Conv><<<grid, k8Threads, smem, stream>>>(jobs, items, geom);
     return cudaGetLastError();
 }
 

@@ -728,7 +728,8 @@ LaunchPlan Context::plan(Device& dev, const JobDesc* descs, size_t n, int* statu
                 Band8Geom probe{tv->pass.band8_limbs, 2, 2, 0};
                 const size_t fixed = banded8_smem_bytes(d.channels, probe);
                 const size_t room = banded8_max_smem() > fixed ? banded8_max_smem() - fixed : 0;
-                const int max_out = int(std::min<size_t>(room / (8 * (size_t(th->pass.stride) + 1)), 512));
+                // (two table buffers per CTA: the next item's tables are loaded while the current item is processed)
+                const int max_out = int(std::min<size_t>(room / (16 * (size_t(th->pass.stride) + 1)), 512));
                 banded8 = max_out >= 1 &&
                           cut_strips(*th->host, d.channels, int(d.sw), banded8_max_src_bytes(), max_out, &c.strips) &&
                           encode_src_map8(lp.jobs[size_t(idx)].src_map8, d.src, d.sh, d.src_pitch);
