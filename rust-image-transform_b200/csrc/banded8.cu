@@ -387,6 +387,7 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
         const int seg = 2 * q + (lane >> 4);
         int vbase = 0;            // groups of the CTA's earlier items
         int kitem = 0;
+        int tbase = 0;            // tiles of the CTA's earlier items, mod k8Teams
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++kitem) {
         const Item8 I = load_item8<C>(jobs, items, item);
         const DevJob* __restrict__ J = I.J;
@@ -422,7 +423,12 @@ banded8_kernel(const DevJob* __restrict__ jobs, const WorkItem* __restrict__ ite
 
         // This team's tiles: every k8Teams-th pair (even group, its successor).  Groups are drained one by one, as soon as
         // they are final, so that their ring slots go back to the MMAs early.
-        for (int gt = (g0 & ~1) + 2 * team; gt < g_end; gt += 2 * k8Teams) {
+        // (the assignment of tiles to teams continues across items -- running tile index mod k8Teams -- so that the odd tiles
+        // of an item do not always fall to team 0)
+        const int gt0 = g0 & ~1;
+        const int first = (team - tbase + k8Teams) % k8Teams;
+        tbase = (tbase + ((g_end - gt0 + 1) >> 1)) % k8Teams;
+        for (int gt = gt0 + 2 * first; gt < g_end; gt += 2 * k8Teams) {
             const int tile_row0 = (gt >> 1) * k8TileRows;          // output row of the intermediate tile's first row
             const bool live = tile_row0 < oy1 && tile_row0 + k8TileRows > oy0;
             const int g_lo = max(gt, g0), g_hi = min(gt + 2, g_end);
