@@ -472,7 +472,8 @@ int ikc_batch_describe(const ikc_batch* b, char* out, size_t cap) {
         else if (g.up_taps) s += "up2_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.up_taps) + ">";
         else if (g.kv == 0) s += g.bps == 2 ? "tile_kernel<u16>" : "tile_kernel";
         else s += "fused_ring_kernel<" + std::to_string(g.channels) + "," + std::to_string(g.kv) + "," + std::to_string(g.kh) + "," + std::to_string(g.sv) + "," + std::to_string(g.sh) + ">";
-        s += " x " + std::to_string(g.items.size()) + (g.up_taps ? " tiles (persistent CTAs)" : " CTAs");
+        s += " x " + std::to_string(g.items.size()) +
+             (g.up_taps ? " tiles (persistent CTAs)" : (g.band8_limbs && !g.band8t && !g.band8u_taps) ? " items (persistent CTAs, one per SM)" : " CTAs");
     }
     if (!b->impl.lp.generic_jobs.empty()) {
         if (!s.empty()) s += "; ";
