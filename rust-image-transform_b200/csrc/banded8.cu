@@ -18,10 +18,13 @@
 //
 // The HORIZONTAL pass is banded.cu's: CUDA cores, output-stationary, lane = intermediate row, half warp = x segment.
 //
-// One CTA per SM (512 threads, all 512 TMEM columns, ~200 KB of shared memory):
+// One PERSISTENT CTA per SM (512 threads, all 512 TMEM columns, ~205 KB of shared memory) walks the work items
+// blockIdx.x, blockIdx.x + gridDim.x, ...; every role runs that sequence on its own, and ring slots / barrier phases follow
+// a running group index, so loads and MMAs of the next item start while the epilogue still works on the current one:
 //   warp 0      producer (TMA): 5-stage ring of source boxes + ring of weight tiles
-//   warps 1-2   MMA issuers (one lane each, two blocks each); warp 3 idle (registers go to the epilogue warpgroups)
-//   warps 4-15  three epilogue TEAMS of four warps (TMEM lane quarter = warp % 4).  Team t owns every third
+//   warps 1-2   MMA issuers (one lane each, two blocks each)
+//   warp 3      table warp: the next item's horizontal tables into the buffer the epilogue is not using
+//   warps 4-15  three epilogue TEAMS of four warps (TMEM lane quarter = warp % 4).  A team owns every third
 //               intermediate tile (16 output rows = 2 ring groups): it drains the tile's groups from TMEM as they become
 //               final (recombines the digits, writes its own shared-memory tile, zeroes and returns the ring slots) and
 //               then runs the tile's horizontal pass, while the other teams do the same for the next tiles and the MMAs
