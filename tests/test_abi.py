@@ -138,6 +138,39 @@ def test_header_is_plain_c_and_links(tmp_path):
     assert subprocess.call([str(exe)]) == 0
 
 
+def test_struct_layouts_match_the_header(ik, tmp_path):
+    """The ctypes mirrors (and, field for field, the Rust crate's ffi.rs) must lay out ikc_stats_t, ikc_job and
+    ikc_pass_info_t exactly as the C header does: sizes and the offsets of the last fields, printed by a C program."""
+    import os, re, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "imagekit_cuda.h"\n'
+                   "int main(void) {\n"
+                   '    printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(ikc_stats_t), offsetof(ikc_stats_t, staging_trims),\n'
+                   "           offsetof(ikc_stats_t, submit_batches), sizeof(ikc_job), offsetof(ikc_job, device), sizeof(ikc_pass_info_t));\n"
+                   "    return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call([gcc, "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    c_stats, c_trims, c_submit, c_job, c_job_dev, c_info = (int(x) for x in subprocess.check_output([str(exe)]).split())
+    S, J, P = ik._lib.Stats, ik._lib.Job, ik._lib.PassInfo
+    assert (ctypes.sizeof(S), S.staging_trims.offset, S.submit_batches.offset) == (c_stats, c_trims, c_submit)
+    assert (ctypes.sizeof(J), J.device.offset) == (c_job, c_job_dev)
+    assert ctypes.sizeof(P) == c_info
+    # the Rust mirror: same field names in the same order as the header's struct (all u64)
+    hdr = open(os.path.join(root, "include", "imagekit_cuda.h")).read()
+    body = hdr[hdr.index("typedef struct ikc_stats_t {"):hdr.index("} ikc_stats_t;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = [f.strip() for decl in re.findall(r"uint64_t([^;]*);", body) for f in decl.split(",")]
+    rs = open(os.path.join(root, "rust-image-transform_b200", "crate", "src", "ffi.rs")).read()
+    rs_body = rs[rs.index("pub struct ikc_stats_t {"):]
+    rs_body = rs_body[:rs_body.index("}")]
+    rs_fields = re.findall(r"pub (\w+): u64", rs_body)
+    assert c_fields == rs_fields == [n for n, _ in S._fields_]
+
+
 # ---- band form of a downscale pass: the weight tiles of the tensor-core vertical pass (host logic) ----
 @pytest.mark.parametrize("filt,n_in,n_out", [(4, 2160, 1080), (4, 3024, 300), (4, 1080, 225), (4, 1080, 1080), (4, 1000, 999),
                                              (4, 777, 388), (2, 500, 250), (1, 640, 123), (3, 333, 100), (0, 100, 37),
