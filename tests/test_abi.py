@@ -171,6 +171,28 @@ def test_struct_layouts_match_the_header(ik, tmp_path):
     assert c_fields == rs_fields == [n for n, _ in S._fields_]
 
 
+def test_rust_bindings_name_only_exported_entry_points(ik):
+    """Every extern "C" function the Rust crate binds (crate/src/ffi.rs; it cannot be compiled here) is declared in the
+    header and exported by the library, with the same number of parameters."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "imagekit_cuda.h")).read(), flags=re.S)
+    c_decl = {m.group(1): m.group(2) for m in re.finditer(r"IKC_API[^;(]*?\b(ikc_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)}
+    rs = open(os.path.join(root, "rust-image-transform_b200", "crate", "src", "ffi.rs")).read()
+    rs = re.sub(r"//[^\n]*", "", rs)
+    rs_decl = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (ikc_\w+)\s*\(([^)]*)\)", rs, flags=re.S)}
+    assert rs_decl, "no bindings found in ffi.rs"
+    lib = ik._lib.load()
+
+    def n_params(text):
+        text = text.strip()
+        return 0 if text in ("", "void") else len([p for p in text.split(",") if p.strip()])
+    for name, params in rs_decl.items():
+        assert name in c_decl, f"{name} is bound in ffi.rs but not declared in imagekit_cuda.h"
+        assert hasattr(lib, name), f"{name} is not exported by libimagekit_cuda.so"
+        assert n_params(params) == n_params(c_decl[name]), (name, params, c_decl[name])
+
+
 # ---- band form of a downscale pass: the weight tiles of the tensor-core vertical pass (host logic) ----
 @pytest.mark.parametrize("filt,n_in,n_out", [(4, 2160, 1080), (4, 3024, 300), (4, 1080, 225), (4, 1080, 1080), (4, 1000, 999),
                                              (4, 777, 388), (2, 500, 250), (1, 640, 123), (3, 333, 100), (0, 100, 37),
