@@ -236,15 +236,14 @@ def run_cfg3_shard(ik, ctx, torch, dev, dist, rank, world, barrier, args):
 
 
 def run_other_workloads(ik, ctx, torch, dev, dist, barrier, names):
-    """The other BASELINE workloads (configs 1 and 4; config 3 has its own leg), device-resident, 32 images per launch, the
+    """The other BASELINE workloads (configs 1 and 4; config 3 has its own leg), device-resident, their default batch per launch, the
     same timing rules as the headline (inputs larger than L2, CUDA events on the launch stream, max over ranks): so that
     the driver's record carries their roofline fractions too, not only the builder's runs."""
     from imagekit_cuda.sharding import aggregate_throughput
     peak, _ = measured_peak()
     out = {}
     for name in names:
-        sw, sh, ch, dw, dh, filt, _, desc = WORKLOADS[name]
-        batch = 32
+        sw, sh, ch, dw, dh, filt, batch, desc = WORKLOADS[name]   # (the workload's own default batch, as `--workload name` runs it)
         g = torch.Generator(device=dev)
         g.manual_seed(0xBEEF + len(name))
         src = torch.randint(0, 256, (batch, sh, sw, ch), dtype=torch.uint8, device=dev, generator=g)
